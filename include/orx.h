@@ -1,0 +1,173 @@
+/*
+ * orx.h -- C ABI of liborx.so, the B200 batched replacement for Optimax Rogue's turn
+ * dynamics. Plain pointers and sizes only; every device buffer is owned by the caller
+ * (PyTorch tensors on the host side); the library allocates nothing persistent, keeps
+ * no global state and enqueues all work on the caller's CUDA stream.
+ *
+ * The reference (Tjstretchalot/optimax_rogue) is pure Python and has no FFI; its seams
+ * are duck-typed objects. Each entry point below names the reference interface it
+ * replaces (file:line under the reference root):
+ *
+ *   orx_step        Updater.update(game_state, player1_move, player2_move)
+ *                       optimax_rogue/logic/updater.py:76-162  (+ handle_move :180-243,
+ *                       handle_combat :298-338, handle_descend :259-296, calculate_pos :340-351)
+ *                   GameState.on_tick  optimax_rogue/game/state.py:46-51 (derived stats)
+ *                   called from Server.update  optimax_rogue/networking/server.py:126
+ *   orx_reset       TogetherGameStartGenerator.setup_game   optimax_rogue/logic/worldgen.py:77-87
+ *                   SeparatedGameStartGenerator.setup_game  optimax_rogue/logic/worldgen.py:124-135
+ *                   EmptyDungeonGenerator.spawn_dungeon     optimax_rogue/logic/worldgen.py:33-43
+ *                   Dungeon.get_random_unblocked            optimax_rogue/game/world.py:57-66
+ *   orx_bot_moves   RandomBot.move     optimax_rogue_bots/randombot.py:20-21
+ *                   StaircaseBot.move  optimax_rogue_bots/staircasebot.py:9-20
+ *   orx_rollout     the tick loop  optimax_rogue/server/main.py:110-113 with both bots inlined
+ *   orx_observe     GameState.view_for  optimax_rogue/game/state.py:53-58
+ *   orx_step_host   orx_step with host command/result buffers (what a remote caller holds)
+ *
+ * Integer codes are the reference's enum values and must not change.
+ */
+#ifndef ORX_H_
+#define ORX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORX_ABI_VERSION 1
+
+/* logic/moves.py:6-12 */
+enum { ORX_MOVE_UP = 1, ORX_MOVE_RIGHT = 2, ORX_MOVE_DOWN = 3, ORX_MOVE_LEFT = 4, ORX_MOVE_STAY = 5 };
+/* logic/updater.py:16-21 */
+enum { ORX_RESULT_IN_PROGRESS = 1, ORX_RESULT_PLAYER1_WIN = 2, ORX_RESULT_PLAYER2_WIN = 3, ORX_RESULT_TIE = 4 };
+/* game/world.py:10-17 */
+enum { ORX_TILE_GROUND = 1, ORX_TILE_WALL = 2, ORX_TILE_STAIRCASE_DOWN = 3 };
+/* game/modifiers.py:7-12 */
+enum { ORX_FLAG_BLOCK = 1, ORX_FLAG_AMBUSH = 2, ORX_FLAG_FLEE = 3, ORX_FLAG_PARRY = 4 };
+/* logic/updater.py:47-50 */
+enum { ORX_DESPAWN_UNREACHABLE = 1, ORX_DESPAWN_UNUSED = 2 };
+
+/* DungeonGenerator kinds (logic/worldgen.py:9-43). FIXED is a plugin generator that returns
+ * the same tile grid at every depth (the reference loads generators by dotted path). */
+enum { ORX_DGEN_EMPTY = 0, ORX_DGEN_FIXED = 1 };
+/* GameStartGenerator kinds (logic/worldgen.py:60-137) */
+enum { ORX_START_TOGETHER = 0, ORX_START_SEPARATED = 1 };
+/* Bot policies (optimax_rogue_bots/) */
+enum { ORX_BOT_NONE = 0, ORX_BOT_RANDOM = 1, ORX_BOT_STAIRCASE = 2 };
+
+/* GameStateUpdate kinds emitted by the updater (logic/updates.py). MOVE and DESCEND are both
+ * EntityPositionUpdate (:186); DESCEND has old_depth == depth - 1. */
+enum { ORX_EV_NONE = 0, ORX_EV_MOVE = 1, ORX_EV_COMBAT = 2, ORX_EV_DUNGEON = 3, ORX_EV_DEATH = 4, ORX_EV_DESCEND = 5 };
+
+#define ORX_NO_STAIRS 255      /* stairs plane value for a level without a staircase */
+#define ORX_MAX_NPC 8          /* static NPC slots per game (updater.py:116-128) */
+#define ORX_MAX_EVENTS_BASE 4  /* two movers x (DungeonCreated + Position) */
+#define ORX_MAX_DIM 255        /* coordinates are stored as uint8 */
+
+/* error codes: 0 ok, negative failure; -(100 + cudaError_t) wraps a CUDA error */
+#define ORX_OK 0
+#define ORX_ERR_BAD_ARG (-1)
+#define ORX_ERR_UNSUPPORTED (-2)
+#define ORX_ERR_CUDA_BASE (-100)
+
+typedef struct OrxConfig {
+    uint32_t struct_size;       /* = sizeof(OrxConfig), checked */
+    int32_t width, height;      /* server/main.py:27-28 (--width 60 --height 10) */
+    int32_t dgen_kind;          /* ORX_DGEN_* */
+    int32_t start_kind;         /* ORX_START_* */
+    int32_t start_depth[2];     /* worldgen.py:78 (0,0) / :110-111 (0,1000) */
+    int32_t despawn_strat;      /* ORX_DESPAWN_*; affects DungeonCreated events only, because
+                                   levels are pure functions of (seed, game, episode, depth) */
+    int32_t max_ticks;          /* updater.py:158; 0 = unlimited */
+    int32_t hp[2];              /* worldgen.py:85-86: health = base_max_health = 10 */
+    int32_t damage[2];          /* base_damage = 2 */
+    int32_t armor[2];           /* base_armor = 1 (damage dealt = attacker.damage - attacker.armor, updater.py:313) */
+    int32_t auto_reset;         /* 1: a finished game is re-initialised (episode+1) inside the step */
+    int32_t n_npc;              /* NPC slots in use, 0..ORX_MAX_NPC */
+    uint64_t seed;              /* Philox key */
+    /* ORX_DGEN_FIXED only (device pointers, shared by all games): */
+    const uint8_t* fixed_tiles;   /* uint8[width*height], x-major (tiles[x*height+y]), ORX_TILE_* */
+    const uint16_t* fixed_ground; /* flat indices of the Ground tiles in ascending (x-major) order */
+    int32_t fixed_n_ground;
+    int32_t fixed_stairs[2];      /* first StaircaseDown in x-major order, or ORX_NO_STAIRS */
+    int32_t reserved;
+} OrxConfig;
+
+/* Structure-of-arrays game state; game i of the batch is element i of every plane. */
+typedef struct OrxState {
+    uint8_t* pos;       /* [n][4]  x1 y1 x2 y2                       Entity.x/.y   entities.py:35-37 */
+    int16_t* hp;        /* [n][2]  health                            Entity.health entities.py:38 */
+    int32_t* depth;     /* [n][2]  dungeon depth                     Entity.depth  entities.py:34 */
+    uint8_t* stairs;    /* [n][4]  staircase (x,y) of each player's current level  world.py:52-55 */
+    int32_t* tick;      /* [n]     GameState.tick (starts at 1)      state.py:29, worldgen.py:87 */
+    uint32_t* episode;  /* [n]     resets seen by this lane (Philox counter word) */
+    uint8_t* status;    /* [n]     ORX_RESULT_* of the lane */
+    /* NPC slots, nullable when n_npc == 0; slot k of game i at [i*n_npc + k] */
+    uint8_t* npc_pos;   /* [n][n_npc][2] */
+    int16_t* npc_hp;    /* [n][n_npc]    */
+    int32_t* npc_depth; /* [n][n_npc]    -1 = empty slot */
+} OrxState;
+
+/* One replication-log record (logic/updates.py); slots of game i at events[i*max_events + k],
+ * in emission order, kind == ORX_EV_NONE terminates. */
+typedef struct OrxEvent {
+    uint8_t kind;   /* ORX_EV_* */
+    uint8_t iden;   /* MOVE/DESCEND/DEATH: entity iden; COMBAT: attacker iden; DUNGEON: 0 */
+    uint8_t a;      /* MOVE/DESCEND: posx; COMBAT: defender iden; DUNGEON: stair x */
+    uint8_t b;      /* MOVE/DESCEND: posy; COMBAT: CombatFlag;    DUNGEON: stair y */
+    int32_t depth;  /* MOVE/DESCEND/DUNGEON: (new) depth; COMBAT: og_damage */
+} OrxEvent;
+
+/* Aggregate counters written by orx_rollout / orx_stats (uint64 each). */
+enum {
+    ORX_STAT_TICKS = 0, ORX_STAT_P1_WINS = 1, ORX_STAT_P2_WINS = 2, ORX_STAT_TIES = 3,
+    ORX_STAT_EVENTS = 4, ORX_STAT_DESCENTS = 5, ORX_STAT_HITS = 6, ORX_STAT_RESERVED = 7,
+    ORX_STAT_COUNT = 8
+};
+
+int orx_abi_version(void);
+const char* orx_strerror(int code);
+
+/* Bytes of per-game mutable state (S_rw of the roofline formula) for this config. */
+size_t orx_state_bytes(const OrxConfig* cfg);
+/* Event slots per game per tick for this config (ORX_MAX_EVENTS_BASE + n_npc). */
+int orx_max_events(const OrxConfig* cfg);
+
+/* Episode reset (worldgen.py:77-87 / :124-135). mask: device uint8[n], nullable = all lanes.
+ * bump_episode != 0 increments episode[i] before drawing (use 0 for the first initialisation
+ * or when the caller wrote the episode plane itself). */
+int orx_reset(const OrxConfig* cfg, const OrxState* st, const uint8_t* mask, int bump_episode,
+              int64_t n, uint64_t game_id_base, void* cuda_stream);
+
+/* One tick for n games (updater.py:76-162). moves: device uint8[n][2] (p1, p2), codes outside
+ * 1..5 are treated as Stay; result: device uint8[n]; events: device OrxEvent[n][orx_max_events]
+ * or NULL. Lanes whose status is not IN_PROGRESS are left untouched (result = status). */
+int orx_step(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uint8_t* result,
+             OrxEvent* events, int64_t n, uint64_t game_id_base, void* cuda_stream);
+
+/* orx_step with HOST command/result buffers: H2D copy of moves, the tick, D2H copy of result,
+ * all on cuda_stream (pinned host memory makes the copies asynchronous). moves_dev/result_dev
+ * are caller-owned device staging buffers of the same shapes. */
+int orx_step_host(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
+                  uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
+                  uint64_t game_id_base, void* cuda_stream);
+
+/* Command generation for scripted bots; ORX_BOT_NONE leaves that player's byte untouched. */
+int orx_bot_moves(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2,
+                  uint8_t* moves, int64_t n, uint64_t game_id_base, void* cuda_stream);
+
+/* n_ticks fused ticks with both bots on device; state stays in registers between ticks.
+ * stats: device uint64[ORX_STAT_COUNT], accumulated (not cleared). */
+int orx_rollout(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2, int n_ticks,
+                unsigned long long* stats, int64_t n, uint64_t game_id_base, void* cuda_stream);
+
+/* Per-player observation (state.py:53-58): obs int16[n][2][ORX_OBS_LEN]. */
+#define ORX_OBS_LEN 12
+int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stairs_radius,
+                int64_t n, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORX_H_ */

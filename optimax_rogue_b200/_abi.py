@@ -1,0 +1,88 @@
+"""ctypes mirror of ``include/orx.h`` (struct layouts, codes, function prototypes).
+
+Kept free of torch so that the CPU test-suite can check the ABI without a GPU.
+"""
+import ctypes as C
+
+ABI_VERSION = 1
+
+MAX_NPC = 8
+MAX_EVENTS_BASE = 4
+MAX_DIM = 255
+NO_STAIRS = 255
+OBS_LEN = 12
+STAT_COUNT = 8
+STAT_NAMES = ('ticks', 'p1_wins', 'p2_wins', 'ties', 'events', 'descents', 'hits', 'reserved')
+
+DGEN_EMPTY, DGEN_FIXED = 0, 1
+START_TOGETHER, START_SEPARATED = 0, 1
+BOT_NONE, BOT_RANDOM, BOT_STAIRCASE = 0, 1, 2
+EV_NONE, EV_MOVE, EV_COMBAT, EV_DUNGEON, EV_DEATH, EV_DESCEND = 0, 1, 2, 3, 4, 5
+
+OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA_BASE = 0, -1, -2, -100
+
+
+class OrxConfig(C.Structure):
+    _fields_ = [
+        ('struct_size', C.c_uint32),
+        ('width', C.c_int32), ('height', C.c_int32),
+        ('dgen_kind', C.c_int32),
+        ('start_kind', C.c_int32),
+        ('start_depth', C.c_int32 * 2),
+        ('despawn_strat', C.c_int32),
+        ('max_ticks', C.c_int32),
+        ('hp', C.c_int32 * 2),
+        ('damage', C.c_int32 * 2),
+        ('armor', C.c_int32 * 2),
+        ('auto_reset', C.c_int32),
+        ('n_npc', C.c_int32),
+        ('seed', C.c_uint64),
+        ('fixed_tiles', C.c_void_p),
+        ('fixed_ground', C.c_void_p),
+        ('fixed_n_ground', C.c_int32),
+        ('fixed_stairs', C.c_int32 * 2),
+        ('reserved', C.c_int32),
+    ]
+
+
+class OrxState(C.Structure):
+    _fields_ = [
+        ('pos', C.c_void_p), ('hp', C.c_void_p), ('depth', C.c_void_p), ('stairs', C.c_void_p),
+        ('tick', C.c_void_p), ('episode', C.c_void_p), ('status', C.c_void_p),
+        ('npc_pos', C.c_void_p), ('npc_hp', C.c_void_p), ('npc_depth', C.c_void_p),
+    ]
+
+
+class OrxEvent(C.Structure):
+    _fields_ = [('kind', C.c_uint8), ('iden', C.c_uint8), ('a', C.c_uint8), ('b', C.c_uint8),
+                ('depth', C.c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/orx.h declares
+PROTOTYPES = {
+    'orx_abi_version': (C.c_int, []),
+    'orx_strerror': (C.c_char_p, [C.c_int]),
+    'orx_state_bytes': (C.c_size_t, [C.POINTER(OrxConfig)]),
+    'orx_max_events': (C.c_int, [C.POINTER(OrxConfig)]),
+    'orx_reset': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_int,
+                            C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
+                           C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step_host': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_bot_moves': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_int, C.c_int,
+                                C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_rollout': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_observe': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_int,
+                              C.c_int64, C.c_void_p]),
+}
+
+
+def bind(lib, prototypes=None):
+    """Sets restype/argtypes on a loaded CDLL; raises AttributeError on a missing symbol."""
+    for name, (res, args) in (prototypes or PROTOTYPES).items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
