@@ -1,0 +1,199 @@
+"""Game state containers.
+
+``BatchedGameState`` holds N independent games as structure-of-arrays tensors in HBM (the planes
+of ``include/orx.h:OrxState``). It replaces the reference's per-game object graph
+(optimax_rogue/game/state.py:10-88): positions ARE the lookup, so ``pos_lookup``/``iden_lookup``
+have no counterpart. ``GameState`` is the host-side single-game view with the reference's
+attribute names, used for interop with code written against the reference.
+"""
+import typing
+
+import numpy as np
+import torch
+
+from .. import _abi
+from ..config import SimConfig
+from .entities import Entity
+from .world import Dungeon, Tile, World
+
+
+class GameState:
+    """Single-game host view (state.py:10-45 attribute names)."""
+
+    def __init__(self, is_authoritative: bool, tick: int, player_1_iden: int, player_2_iden: int,
+                 world: World, entities: typing.List[Entity]):
+        self.is_authoritative = is_authoritative
+        self.tick = tick
+        self.player_1_iden = player_1_iden
+        self.player_2_iden = player_2_iden
+        self.world = world
+        self.entities = entities
+        self.pos_lookup = dict(((ent.depth, ent.x, ent.y), ent) for ent in entities)
+        self.iden_lookup = dict((ent.iden, ent) for ent in entities)
+
+    @property
+    def player_1(self) -> Entity:
+        return self.iden_lookup[self.player_1_iden]
+
+    @property
+    def player_2(self) -> Entity:
+        return self.iden_lookup[self.player_2_iden]
+
+    def view_for(self, entity: Entity, reduce_tick: bool = False) -> 'GameState':
+        """state.py:53-58: only the viewer's depth is kept."""
+        world = World({entity.depth: self.world.dungeons[entity.depth]})
+        ents = [e for e in self.entities if e.depth == entity.depth]
+        return GameState(False, self.tick - 1 if reduce_tick else self.tick,
+                         self.player_1_iden, self.player_2_iden, world, ents)
+
+
+def empty_room_tiles(width: int, height: int, stairs: typing.Tuple[int, int]) -> np.ndarray:
+    """The tile grid EmptyDungeonGenerator builds (worldgen.py:34-42) for a given staircase."""
+    tiles = np.full((width, height), int(Tile.Ground), 'int32')
+    tiles[[0, -1], :] = int(Tile.Wall)
+    tiles[:, [0, -1]] = int(Tile.Wall)
+    if stairs[0] != _abi.NO_STAIRS:
+        tiles[stairs[0], stairs[1]] = int(Tile.StaircaseDown)
+    return tiles
+
+
+class BatchedGameState:
+    """N games as SoA tensors on one CUDA device.
+
+    Planes (game i = row i): ``pos`` uint8[N,4] (x1,y1,x2,y2), ``hp`` int16[N,2],
+    ``depth`` int32[N,2], ``stairs`` uint8[N,4] (staircase of each player's current level),
+    ``tick`` int32[N], ``episode`` int32[N] (bit pattern of a uint32), ``status`` uint8[N]
+    (UpdateResult code), plus NPC slot planes when ``cfg.n_npc > 0``.
+    """
+
+    PLANES = ('pos', 'hp', 'depth', 'stairs', 'tick', 'episode', 'status',
+              'npc_pos', 'npc_hp', 'npc_depth')
+
+    def __init__(self, cfg: SimConfig, n: int, device='cuda', game_id_base: int = 0):
+        cfg.validate()
+        self.cfg = cfg
+        self.n = int(n)
+        self.device = torch.device(device)
+        self.game_id_base = int(game_id_base)
+        dev = self.device
+        self.pos = torch.zeros((n, 4), dtype=torch.uint8, device=dev)
+        self.hp = torch.zeros((n, 2), dtype=torch.int16, device=dev)
+        self.depth = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+        self.stairs = torch.zeros((n, 4), dtype=torch.uint8, device=dev)
+        self.tick = torch.zeros((n,), dtype=torch.int32, device=dev)
+        self.episode = torch.zeros((n,), dtype=torch.int32, device=dev)
+        self.status = torch.ones((n,), dtype=torch.uint8, device=dev)
+        e = max(cfg.n_npc, 1)
+        self.npc_pos = torch.zeros((n, e, 2), dtype=torch.uint8, device=dev)
+        self.npc_hp = torch.zeros((n, e), dtype=torch.int16, device=dev)
+        self.npc_depth = torch.full((n, e), -1, dtype=torch.int32, device=dev)
+        # the fixed map (shared by all games) lives beside the state
+        self.fixed_tiles = self.fixed_ground = None
+        self._fixed_stairs = (_abi.NO_STAIRS, _abi.NO_STAIRS)
+        if cfg.dgen_kind == _abi.DGEN_FIXED:
+            tiles, ground, stairs = cfg.fixed_tables()
+            self.fixed_tiles = torch.from_numpy(tiles).to(dev)
+            # uint16 table shipped as int16 bit pattern (torch has no general uint16 support)
+            self.fixed_ground = torch.from_numpy(ground.view(np.int16).copy()).to(dev)
+            self._fixed_stairs = stairs
+
+    # -- ABI views -----------------------------------------------------------------------------
+    def c_struct(self) -> _abi.OrxState:
+        st = _abi.OrxState()
+        for name in self.PLANES:
+            setattr(st, name, getattr(self, name).data_ptr())
+        return st
+
+    def c_config(self, **overrides) -> _abi.OrxConfig:
+        """OrxConfig for this state; the updater overrides despawn_strat/max_ticks/auto_reset."""
+        cfg = self.cfg
+        if self.fixed_tiles is not None:
+            c = cfg.to_c(self.fixed_tiles.data_ptr(), self.fixed_ground.data_ptr(),
+                         int(self.fixed_ground.numel()), self._fixed_stairs)
+        else:
+            c = cfg.to_c()
+        for k, v in overrides.items():
+            setattr(c, k, v)
+        return c
+
+    # -- convenience views ---------------------------------------------------------------------
+    @property
+    def player_1(self):
+        return {'x': self.pos[:, 0], 'y': self.pos[:, 1], 'depth': self.depth[:, 0], 'health': self.hp[:, 0]}
+
+    @property
+    def player_2(self):
+        return {'x': self.pos[:, 2], 'y': self.pos[:, 3], 'depth': self.depth[:, 1], 'health': self.hp[:, 1]}
+
+    def planes_cpu(self) -> typing.Dict[str, np.ndarray]:
+        return {name: getattr(self, name).cpu().numpy() for name in self.PLANES}
+
+    def clone(self) -> 'BatchedGameState':
+        o = BatchedGameState.__new__(BatchedGameState)
+        o.__dict__.update(self.__dict__)
+        for name in self.PLANES:
+            setattr(o, name, getattr(self, name).clone())
+        return o
+
+    def state_dict(self):
+        """Checkpoint: plain tensors + scalars (``torch.save``-able)."""
+        d = {name: getattr(self, name) for name in self.PLANES}
+        d['game_id_base'] = self.game_id_base
+        return d
+
+    def load_state_dict(self, d):
+        for name in self.PLANES:
+            getattr(self, name).copy_(d[name])
+        self.game_id_base = int(d['game_id_base'])
+
+    def set_npc(self, lane: int, slot: int, depth: int, x: int, y: int, health: int):
+        """Places a static NPC (an extra Entity after the players, updater.py:116-128)."""
+        if not 0 <= slot < self.cfg.n_npc:
+            raise ValueError('slot out of range')
+        self.npc_depth[lane, slot] = depth
+        self.npc_pos[lane, slot, 0] = x
+        self.npc_pos[lane, slot, 1] = y
+        self.npc_hp[lane, slot] = health
+
+    # -- interop with single-game objects ------------------------------------------------------
+    def level_tiles(self, stairs: typing.Tuple[int, int]) -> np.ndarray:
+        if self.cfg.dgen_kind == _abi.DGEN_FIXED:
+            return np.asarray(self.cfg.fixed_tiles, dtype='int32').copy()
+        return empty_room_tiles(self.cfg.width, self.cfg.height, stairs)
+
+    def to_game_state(self, i: int, planes=None) -> GameState:
+        """Materialises game ``i`` as a host GameState holding the levels the players stand on
+        (the levels in between are re-derivable but not stored). Pass ``planes=planes_cpu()``
+        when converting many lanes."""
+        p = self.planes_cpu() if planes is None else planes
+        cfg = self.cfg
+        ents = []
+        dungeons = {}
+        for k in range(2):
+            d = int(p['depth'][i, k])
+            ents.append(Entity(k + 1, d, int(p['pos'][i, 2 * k]), int(p['pos'][i, 2 * k + 1]),
+                               int(p['hp'][i, k]), cfg.hp[k], cfg.damage[k], cfg.armor[k]))
+            st = (int(p['stairs'][i, 2 * k]), int(p['stairs'][i, 2 * k + 1]))
+            dungeons[d] = Dungeon(self.level_tiles(st))
+        for k in range(cfg.n_npc):
+            d = int(p['npc_depth'][i, k])
+            if d >= 0:
+                hpv = int(p['npc_hp'][i, k])
+                ents.append(Entity(3 + k, d, int(p['npc_pos'][i, k, 0]), int(p['npc_pos'][i, k, 1]),
+                                   hpv, hpv, 0, 0))
+        return GameState(True, int(p['tick'][i]), 1, 2, World(dungeons), ents)
+
+    def load_game_state(self, i: int, gs: GameState):
+        """Writes a host GameState into lane ``i`` (players + their levels' staircases)."""
+        for k, ent in enumerate((gs.player_1, gs.player_2)):
+            self.pos[i, 2 * k] = ent.x
+            self.pos[i, 2 * k + 1] = ent.y
+            self.depth[i, k] = ent.depth
+            self.hp[i, k] = ent.health
+            dung = gs.world.dungeons[ent.depth]
+            hits = np.argwhere(np.asarray(dung.tiles) == int(Tile.StaircaseDown))
+            sx, sy = (int(hits[0][0]), int(hits[0][1])) if len(hits) else (_abi.NO_STAIRS, _abi.NO_STAIRS)
+            self.stairs[i, 2 * k] = sx
+            self.stairs[i, 2 * k + 1] = sy
+        self.tick[i] = gs.tick
+        self.status[i] = 1

@@ -1,0 +1,1 @@
+"""Batched counterparts of the reference's ``optimax_rogue/logic`` package."""

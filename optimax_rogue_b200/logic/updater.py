@@ -1,0 +1,200 @@
+"""``BatchedUpdater``: the reference's ``Updater`` (optimax_rogue/logic/updater.py:52-162) over N
+games. Same constructor arguments and ``update(game_state, player1_move, player2_move)`` call;
+moves and results are tensors with one element per game. All work is done by the sm_100a kernels
+in ``liborx.so`` through the C ABI -- there is no CPU path."""
+import ctypes as C
+import enum
+import typing
+
+import torch
+
+from .. import _abi, _lib
+from ..game.state import BatchedGameState
+from .worldgen import DungeonGenerator
+
+
+class UpdateResult(enum.IntEnum):
+    """updater.py:16-21"""
+    InProgress = 1
+    Player1Win = 2
+    Player2Win = 3
+    Tie = 4
+
+
+class DungeonDespawningStrategy(enum.IntEnum):
+    """updater.py:47-50"""
+    Unreachable = 1
+    Unused = 2
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(gs: BatchedGameState):
+    if gs.device.type != 'cuda':
+        raise RuntimeError('BatchedGameState must live on a CUDA device: there is no CPU fallback')
+
+
+def reset_games(gs: BatchedGameState, mask: typing.Optional[torch.Tensor] = None,
+                bump_episode: bool = False, **cfg_overrides):
+    """Episode reset for the masked lanes (setup_game, worldgen.py:77-87 / :124-135)."""
+    _require_cuda(gs)
+    cfg = gs.c_config(**cfg_overrides)
+    st = gs.c_struct()
+    mptr = None
+    if mask is not None:
+        mask = mask.to(device=gs.device, dtype=torch.uint8).contiguous()
+        mptr = mask.data_ptr()
+    with torch.cuda.device(gs.device):
+        rc = _lib.lib().orx_reset(C.byref(cfg), C.byref(st), mptr, int(bump_episode), gs.n,
+                                  gs.game_id_base, _stream_ptr(gs.device))
+    _lib.check(rc, 'orx_reset')
+
+
+class BatchedUpdater:
+    """Moves N games forward in time.
+
+    Attributes mirror the reference: ``dgen``, ``despawn_strat``, ``max_ticks`` (None = never),
+    and ``current_update_order`` (here a per-game int64 tensor, created on first use).
+    ``auto_reset=True`` re-initialises a finished game inside the same tick (episode + 1) so a
+    rollout never stalls; otherwise finished lanes are frozen until ``reset_games``.
+    """
+
+    def __init__(self, dgen: DungeonGenerator, despawn_strat: DungeonDespawningStrategy,
+                 max_ticks: typing.Optional[int] = None, *, auto_reset: bool = False):
+        if int(despawn_strat) not in (1, 2):
+            raise ValueError(f'Unknown despawn strat {despawn_strat} (type={type(despawn_strat)})')
+        self.dgen = dgen
+        self.despawn_strat = DungeonDespawningStrategy(int(despawn_strat))
+        self.max_ticks = max_ticks
+        self.auto_reset = auto_reset
+        self.current_update_order = None
+        self._cache = None
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _cfg(self, gs: BatchedGameState):
+        key = (id(gs), gs.game_id_base, int(self.despawn_strat), int(self.max_ticks or 0), int(self.auto_reset),
+               gs.pos.data_ptr())
+        if self._cache is None or self._cache[0] != key:
+            if (gs.cfg.width, gs.cfg.height, gs.cfg.dgen_kind) != (self.dgen.width, self.dgen.height, self.dgen.kind):
+                raise ValueError('updater.dgen does not match the generator the game state was built with')
+            cfg = gs.c_config(despawn_strat=int(self.despawn_strat), max_ticks=int(self.max_ticks or 0),
+                              auto_reset=int(self.auto_reset))
+            self._cache = (key, cfg, gs.c_struct())
+        return self._cache[1], self._cache[2]
+
+    @staticmethod
+    def _as_moves(gs, player1_move, player2_move):
+        if player2_move is None:
+            mv = player1_move
+        else:
+            mv = torch.stack((torch.as_tensor(player1_move), torch.as_tensor(player2_move)), dim=1)
+        if mv.dtype != torch.uint8:
+            mv = mv.to(torch.uint8)
+        if tuple(mv.shape) != (gs.n, 2):
+            raise ValueError(f'moves must have shape ({gs.n}, 2), got {tuple(mv.shape)}')
+        return mv.contiguous()
+
+    # -- the tick --------------------------------------------------------------------------------
+    def update(self, game_state: BatchedGameState, player1_move, player2_move=None, *,
+               want_events: bool = False, out: typing.Optional[torch.Tensor] = None):
+        """One tick for every game (updater.py:76-162).
+
+        ``player1_move``/``player2_move``: uint8[N] Move codes, or pass a single uint8[N,2]
+        tensor as ``player1_move`` (fast path, no stacking). CUDA tensors are consumed in place;
+        CPU tensors (pinned for asynchrony) go through ``orx_step_host`` and the result comes
+        back in a CPU tensor. Returns ``(result uint8[N] of UpdateResult codes, events)`` where
+        events is None or an int32[N, max_events, 2] tensor of raw OrxEvent records
+        (see logic/updates.py:decode_events).
+        """
+        gs = game_state
+        _require_cuda(gs)
+        mv = self._as_moves(gs, player1_move, player2_move)
+        if not mv.is_cuda:
+            if want_events:
+                raise ValueError('events are only produced for device-resident moves')
+            return self._update_host(gs, mv, out), None
+        cfg, st = self._cfg(gs)
+        result = out if out is not None else torch.empty((gs.n,), dtype=torch.uint8, device=gs.device)
+        events = None
+        if want_events:
+            events = torch.empty((gs.n, _abi.MAX_EVENTS_BASE + gs.cfg.n_npc, 2), dtype=torch.int32,
+                                 device=gs.device)
+        with torch.cuda.device(gs.device):
+            rc = _lib.lib().orx_step(C.byref(cfg), C.byref(st), mv.data_ptr(), result.data_ptr(),
+                                     events.data_ptr() if events is not None else None, gs.n,
+                                     gs.game_id_base, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_step')
+        if events is not None:
+            self._advance_order(gs, events)
+        return result, events
+
+    def _update_host(self, gs, moves_host, out):
+        cfg, st = self._cfg(gs)
+        if not hasattr(self, '_stage') or self._stage[0].shape[0] != gs.n or self._stage[0].device != gs.device:
+            self._stage = (torch.empty((gs.n, 2), dtype=torch.uint8, device=gs.device),
+                           torch.empty((gs.n,), dtype=torch.uint8, device=gs.device))
+        result_host = out if out is not None else torch.empty((gs.n,), dtype=torch.uint8, pin_memory=True)
+        with torch.cuda.device(gs.device):
+            rc = _lib.lib().orx_step_host(C.byref(cfg), C.byref(st), moves_host.data_ptr(),
+                                          result_host.data_ptr(), self._stage[0].data_ptr(),
+                                          self._stage[1].data_ptr(), gs.n, gs.game_id_base,
+                                          _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_step_host')
+        return result_host
+
+    def _advance_order(self, gs, events):
+        if self.current_update_order is None:
+            self.current_update_order = torch.zeros((gs.n,), dtype=torch.int64, device=gs.device)
+        self.current_update_order += ((events[:, :, 0] & 0xFF) != 0).sum(dim=1)
+
+    def get_incr_upd_order(self):
+        """Per-game count of GameStateUpdates emitted so far (updater.py:71-74)."""
+        return self.current_update_order
+
+    # -- fused paths -------------------------------------------------------------------------------
+    def bot_moves(self, game_state: BatchedGameState, bot_p1: int, bot_p2: int,
+                  out: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Commands of the scripted bots for the current tick -> uint8[N,2]."""
+        gs = game_state
+        _require_cuda(gs)
+        cfg, st = self._cfg(gs)
+        moves = out if out is not None else torch.full((gs.n, 2), 5, dtype=torch.uint8, device=gs.device)
+        with torch.cuda.device(gs.device):
+            rc = _lib.lib().orx_bot_moves(C.byref(cfg), C.byref(st), int(bot_p1), int(bot_p2),
+                                          moves.data_ptr(), gs.n, gs.game_id_base, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_bot_moves')
+        return moves
+
+    def rollout(self, game_state: BatchedGameState, bot_p1: int, bot_p2: int, n_ticks: int,
+                stats: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``n_ticks`` fused ticks with both bots on device (the loop of server/main.py:110-113).
+        Returns the int64[STAT_COUNT] device tensor of accumulated counters."""
+        gs = game_state
+        _require_cuda(gs)
+        cfg, st = self._cfg(gs)
+        if stats is None:
+            stats = torch.zeros((_abi.STAT_COUNT,), dtype=torch.int64, device=gs.device)
+        with torch.cuda.device(gs.device):
+            rc = _lib.lib().orx_rollout(C.byref(cfg), C.byref(st), int(bot_p1), int(bot_p2), int(n_ticks),
+                                        stats.data_ptr(), gs.n, gs.game_id_base, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_rollout')
+        return stats
+
+    def observe(self, game_state: BatchedGameState, stairs_radius: int = -1,
+                out: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Per-player observation int16[N,2,OBS_LEN] (GameState.view_for, state.py:53-58, plus the
+        README's "ladder visible when near" as an optional Chebyshev radius; -1 = always)."""
+        gs = game_state
+        _require_cuda(gs)
+        cfg, st = self._cfg(gs)
+        obs = out if out is not None else torch.empty((gs.n, 2, _abi.OBS_LEN), dtype=torch.int16, device=gs.device)
+        with torch.cuda.device(gs.device):
+            rc = _lib.lib().orx_observe(C.byref(cfg), C.byref(st), obs.data_ptr(), int(stairs_radius),
+                                        gs.n, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_observe')
+        return obs
+
+    def reset(self, game_state: BatchedGameState, mask=None, bump_episode: bool = True):
+        reset_games(game_state, mask, bump_episode)

@@ -1,0 +1,199 @@
+"""-m gpu: the CUDA path (through the C ABI) against the C oracle, bit-exact, on the same seeded
+inputs. The oracle itself is pinned to the live reference by tests/golden + test_oracle_*."""
+import numpy as np
+import pytest
+import torch
+
+from optimax_rogue_b200 import SimConfig, _abi
+from optimax_rogue_b200.game.state import BatchedGameState
+from optimax_rogue_b200.logic.updater import BatchedUpdater, reset_games
+
+import gpu_util as gu
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x0A11CE
+
+
+@pytest.mark.parametrize('w,h', [(60, 10), (4, 4), (5, 7), (255, 255), (16, 4)])
+@pytest.mark.parametrize('start', [_abi.START_TOGETHER, _abi.START_SEPARATED])
+def test_reset_parity(w, h, start):
+    cfg = SimConfig(width=w, height=h, start_kind=start,
+                    start_depth=(0, 1000) if start == _abi.START_SEPARATED else (0, 0), seed=SEED)
+    gs, upd, orc = gu.make_pair(cfg, 5000, game_id_base=(1 << 40) + 17)
+    gu.assert_state_equal(gs, orc, 'reset')
+    # masked reset with episode bump touches only the masked lanes
+    mask = (np.arange(5000) % 3 == 0).astype(np.uint8)
+    reset_games(gs, torch.from_numpy(mask), bump_episode=True)
+    orc.reset(mask, bump_episode=True)
+    gu.assert_state_equal(gs, orc, 'masked reset')
+    assert int(gs.episode.sum()) == int(mask.sum())
+
+
+@pytest.mark.parametrize('bots', [(1, 1), (2, 1), (2, 2), (1, 2)])
+@pytest.mark.parametrize('despawn', [1, 2])
+def test_step_parity_bots(bots, despawn):
+    cfg = SimConfig(max_ticks=150, seed=SEED, despawn_strat=despawn, auto_reset=True)
+    gu.run_parity(cfg, 2048, 320, bots=bots, events=True)
+
+
+def test_step_parity_frozen_without_auto_reset():
+    cfg = SimConfig(max_ticks=40, seed=7, auto_reset=False, hp=(2, 2))
+    gs, upd, orc = gu.run_parity(cfg, 1024, 60, bots=(1, 1), events=True)
+    assert (gs.status != 1).all()
+
+
+def test_step_parity_small_rooms_fight():
+    # tiny rooms force combat, double deaths and descents every few ticks
+    for (w, h) in [(4, 4), (5, 5), (6, 4)]:
+        cfg = SimConfig(width=w, height=h, max_ticks=64, seed=99, auto_reset=True, hp=(3, 3))
+        gu.run_parity(cfg, 1024, 200, bots=(1, 1), events=True)
+
+
+def test_step_parity_separated_start_and_stats():
+    cfg = SimConfig(start_kind=_abi.START_SEPARATED, start_depth=(3, 5), max_ticks=300, seed=5,
+                    auto_reset=True, hp=(4, 7), damage=(3, 2), armor=(1, 0))
+    gu.run_parity(cfg, 1024, 400, bots=(2, 1), events=True)
+
+
+def test_step_out_of_range_commands_are_stay():
+    cfg = SimConfig(max_ticks=0, seed=3)
+    rng = np.random.default_rng(0)
+
+    def moves_fn(t, orc):
+        return rng.integers(0, 256, size=(orc.n, 2), dtype=np.uint8)
+    gu.run_parity(cfg, 2048, 50, moves_fn=moves_fn, events=True)
+
+
+def fixed_map(w=60, h=10, p=0.10, stairs=False, seed=0):
+    rng = np.random.default_rng(seed)
+    t = np.full((w, h), 1, np.uint8)
+    t[[0, -1], :] = 2
+    t[:, [0, -1]] = 2
+    inner = rng.random((w - 2, h - 2)) < p
+    t[1:-1, 1:-1][inner] = 2
+    if stairs:
+        g = np.argwhere(t == 1)
+        for k in (len(g) // 3, 2 * len(g) // 3):
+            t[g[k][0], g[k][1]] = 3
+    return t
+
+
+@pytest.mark.parametrize('stairs', [False, True])
+def test_step_parity_fixed_map(stairs):
+    cfg = SimConfig(dgen_kind=_abi.DGEN_FIXED, fixed_tiles=fixed_map(stairs=stairs), max_ticks=200,
+                    seed=SEED, auto_reset=True, hp=(3, 3))
+    gu.run_parity(cfg, 4096, 300, bots=(1, 1) if not stairs else (2, 1), events=True)
+
+
+def test_step_parity_npcs():
+    cfg = SimConfig(width=8, height=6, max_ticks=0, seed=11, n_npc=3, hp=(50, 50))
+
+    def setup(gs, orc):
+        rng = np.random.default_rng(1)
+        for lane in range(gs.n):
+            for k in range(3):
+                if rng.random() < 0.8:
+                    d, x, y, hp = int(rng.integers(0, 3)), int(rng.integers(1, 7)), int(rng.integers(1, 5)), int(rng.integers(1, 4))
+                    orc.state.npc_depth[lane, k] = d
+                    orc.state.npc_pos[lane, k] = (x, y)
+                    orc.state.npc_hp[lane, k] = hp
+        gs.npc_depth.copy_(torch.from_numpy(orc.state.npc_depth))
+        gs.npc_pos.copy_(torch.from_numpy(orc.state.npc_pos))
+        gs.npc_hp.copy_(torch.from_numpy(orc.state.npc_hp))
+    gu.run_parity(cfg, 512, 150, bots=(1, 2), events=True, setup=setup)
+
+
+@pytest.mark.parametrize('bots', [(1, 1), (2, 1)])
+def test_rollout_matches_oracle(bots):
+    cfg = SimConfig(max_ticks=100, seed=SEED, auto_reset=True)
+    gs, upd, orc = gu.make_pair(cfg, 10000, game_id_base=123456789)
+    stats = upd.rollout(gs, bots[0], bots[1], 257)
+    ostats = orc.rollout(bots[0], bots[1], 257)
+    gu.assert_state_equal(gs, orc, 'rollout')
+    assert np.array_equal(stats.cpu().numpy().astype(np.uint64), ostats)
+    assert int(stats[0]) == 10000 * 257
+
+
+def test_rollout_equals_step_loop():
+    cfg = SimConfig(max_ticks=64, seed=1, auto_reset=True)
+    gs, upd, _ = gu.make_pair(cfg, 4096)
+    gs2 = gs.clone()
+    upd.rollout(gs, 1, 2, 100)
+    for _ in range(100):
+        mv = upd.bot_moves(gs2, 1, 2)
+        upd.update(gs2, mv)
+    for name in gu.PLANES:
+        assert torch.equal(getattr(gs, name), getattr(gs2, name)), name
+
+
+def test_shard_invariance():
+    """Game g gives the same trajectory whichever shard (game_id_base) holds it."""
+    cfg = SimConfig(max_ticks=80, seed=SEED, auto_reset=True)
+    full, upd, _ = gu.make_pair(cfg, 4096, game_id_base=0)
+    upd.rollout(full, 1, 1, 200)
+    for base, cnt in ((0, 1024), (1024, 3072)):
+        part = BatchedGameState(cfg, cnt, 'cuda', game_id_base=base)
+        reset_games(part)
+        upd.rollout(part, 1, 1, 200)
+        for name in gu.PLANES:
+            assert torch.equal(getattr(part, name), getattr(full, name)[base:base + cnt]), name
+
+
+def test_step_host_buffers():
+    cfg = SimConfig(max_ticks=50, seed=2, auto_reset=True)
+    gs, upd, orc = gu.make_pair(cfg, 3000)
+    host_moves = torch.empty((3000, 2), dtype=torch.uint8, pin_memory=True)
+    host_res = torch.empty((3000,), dtype=torch.uint8, pin_memory=True)
+    for t in range(60):
+        mv = orc.bot_moves(1, 1)
+        host_moves.copy_(torch.from_numpy(mv))
+        res, _ = upd.update(gs, host_moves, out=host_res)
+        torch.cuda.synchronize()
+        res_o, _ = orc.step(mv)
+        assert np.array_equal(res.numpy(), res_o)
+    gu.assert_state_equal(gs, orc, 'host path')
+
+
+def test_observe():
+    cfg = SimConfig(max_ticks=0, seed=4)
+    gs, upd, orc = gu.make_pair(cfg, 2000)
+    upd.rollout(gs, 2, 1, 40)
+    obs = upd.observe(gs, stairs_radius=3).cpu().numpy()
+    p = gs.planes_cpu()
+    for pl in range(2):
+        o = 1 - pl
+        assert np.array_equal(obs[:, pl, 0], p['pos'][:, 2 * pl])
+        assert np.array_equal(obs[:, pl, 1], p['pos'][:, 2 * pl + 1])
+        assert np.array_equal(obs[:, pl, 2], p['depth'][:, pl])
+        assert np.array_equal(obs[:, pl, 3], p['hp'][:, pl])
+        same = p['depth'][:, 0] == p['depth'][:, 1]
+        assert np.array_equal(obs[:, pl, 4], same.astype(np.int16))
+        assert np.array_equal(obs[:, pl, 5], np.where(same, p['pos'][:, 2 * o], -1))
+        cheb = np.maximum(np.abs(p['stairs'][:, 2 * pl].astype(int) - p['pos'][:, 2 * pl]),
+                          np.abs(p['stairs'][:, 2 * pl + 1].astype(int) - p['pos'][:, 2 * pl + 1]))
+        vis = cheb <= 3
+        assert np.array_equal(obs[:, pl, 8], vis.astype(np.int16))
+        assert np.array_equal(obs[:, pl, 9], np.where(vis, p['stairs'][:, 2 * pl], -1))
+        assert np.array_equal(obs[:, pl, 11], p['tick'])
+
+
+def test_bad_arguments_fail_loudly():
+    from optimax_rogue_b200 import _lib
+    import ctypes as C
+    cfg = SimConfig(seed=1)
+    gs = BatchedGameState(cfg, 16, 'cuda')
+    c = gs.c_config()
+    st = gs.c_struct()
+    lib = _lib.lib()
+    assert lib.orx_step(C.byref(c), C.byref(st), None, None, None, 16, 0, None) == _abi.ERR_BAD_ARG
+    c.struct_size = 4
+    assert lib.orx_reset(C.byref(c), C.byref(st), None, 0, 16, 0, None) == _abi.ERR_BAD_ARG
+    c = gs.c_config()
+    c.width = 3
+    assert lib.orx_reset(C.byref(c), C.byref(st), None, 0, 16, 0, None) == _abi.ERR_BAD_ARG
+    with pytest.raises(RuntimeError):
+        _lib.check(_abi.ERR_BAD_ARG, 'x')
+    # n == 0 is a no-op
+    c = gs.c_config()
+    assert lib.orx_reset(C.byref(c), C.byref(st), None, 0, 0, 0, None) == 0
