@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: game-ticks/s of the batched Optimax Rogue updater.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--games-per-gpu G] [--impl b200|reference]
+
+A "step" is one tick (one ``Updater.update``, optimax_rogue/logic/updater.py:76-162) for every game
+of one batch of G games per GPU, with auto-reset and on-device level generation
+(BASELINE.json configs[3]: 1M games, reference-exact ruleset R0, RandomBot-style uniform command
+streams). Rank r owns games [r*G, (r+1)*G) (weak scaling, no collective on the step path).
+
+Timed regions (CUDA events on the launching stream, max over ranks):
+  value     K steps captured in one CUDA graph, commands already resident in HBM
+  e2e       the public ``BatchedUpdater.update`` call with HOST command/result buffers: pinned H2D
+            copy of the step's commands, the tick, D2H copy of the results, sync -- every step
+  rollout   (extra) fused multi-tick kernel with both bots on device
+L2: the timed loop rotates over B independent batches whose combined state exceeds the 126 MB L2.
+
+``--impl reference`` times the CPU side instead: the plain-C restatement of the reference updater
+(oracle/orx_oracle.c, kind "port" -- the Python reference itself cannot travel to the GPU box) with
+OpenMP over all host cores on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'game-ticks/sec (whole box), 1M games per B200, ruleset R0'
+UNIT = 'game-ticks/s'
+WORKLOAD = 'configs[3]: 2^20 concurrent games per GPU, 60x10 EmptyDungeon levels generated on device, ' \
+           'auto-reset, max_ticks=1000, uniform random commands (RandomBot vs RandomBot)'
+MAX_TICKS = 1000
+SEED = 0x0A11CE
+B_ALG = 61   # bytes per game-tick: 2 x 29 B state planes + 2 B commands + 1 B result
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--games-per-gpu', type=int, default=1 << 20)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--rollout-ticks', type=int, default=64)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def recorded_traffic():
+    """dram bytes per launch of k_step from the committed ncu --set full capture, or None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(smax), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def sim_config(auto_reset=True):
+    from optimax_rogue_b200 import SimConfig
+    return SimConfig(width=60, height=10, max_ticks=MAX_TICKS, seed=SEED, auto_reset=auto_reset)
+
+
+# ------------------------------------------------------------------------------------------ CPU side
+def cpu_port_run(n_games, seconds, steps=None, game_id_base=0):
+    """Times the C restatement (OpenMP, all cores) ticking ``n_games`` games with RandomBot commands.
+    Returns (ticks_per_s, cores, ticks_done, elapsed)."""
+    import numpy as np
+    from oracle import cport
+    cfg = sim_config()
+    orc = cport.Oracle(cfg, n_games, game_id_base)
+    orc.reset()
+    stats = np.zeros(8, np.uint64)
+    orc.rollout(1, 1, 1, stats)                       # warm: page in, spin up the thread pool
+    stats[:] = 0
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        orc.rollout(1, 1, 1, stats)
+        done += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and done >= steps) or (steps is None and el >= seconds):
+            break
+    el = time.perf_counter() - t0
+    return float(stats[0]) / el, os.cpu_count(), int(stats[0]), el
+
+
+def run_reference(args, rank, world):
+    """--impl reference: rank 0 alone, host cores only."""
+    if rank != 0:
+        return
+    n = args.games_per_gpu * world      # the reference arm has no GPUs to shard over: whole-box batch on the host
+    n_sample = min(n, 1 << 20)
+    t_w0 = time.perf_counter()
+    import numpy as np
+    from oracle import cport
+    cfg = sim_config()
+    orc = cport.Oracle(cfg, n_sample, 0)
+    orc.reset()
+    stats = np.zeros(8, np.uint64)
+    for _ in range(max(args.warmup, 1)):
+        orc.rollout(1, 1, 1, stats)
+    stats[:] = 0
+    steps = min(args.steps, 200)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.rollout(1, 1, 1, stats)
+    el = time.perf_counter() - t0
+    val = float(stats[0]) / el
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': world,
+        'steps': steps, 'warmup': max(args.warmup, 1), 'ms_per_step': 1e3 * el / steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
+        'data': 'synthetic', 'config': {'workload': WORKLOAD, 'games_per_step': n_sample},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': f'{steps} steps x {n_sample} games, oracle/orx_oracle.c oro_rollout(1 tick, RandomBot x2), OpenMP'},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'wall_s': time.perf_counter() - t_w0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU side
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from optimax_rogue_b200 import _lib
+    from optimax_rogue_b200.game.state import BatchedGameState
+    from optimax_rogue_b200.logic.updater import BatchedUpdater, reset_games
+    from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
+
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback')
+    _lib.lib()   # fail loudly if the extension is missing
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    G, K, W = args.games_per_gpu, args.steps, args.warmup
+    cfg = sim_config()
+    # rotating batches: combined state must exceed L2 so no step finds its planes cached
+    state_bytes = 29 * G
+    n_batches = max(2, -(-300_000_000 // (state_bytes + 3 * G)))
+    n_batches = min(n_batches, 64)
+    upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, MAX_TICKS, auto_reset=True)
+    batches = []
+    for b in range(n_batches):
+        gs = BatchedGameState(cfg, G, dev, game_id_base=(rank * n_batches + b) * G)
+        reset_games(gs)
+        batches.append(gs)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    n_move_sets = 16
+    moves = torch.randint(1, 6, (n_move_sets, G, 2), dtype=torch.uint8, device=dev, generator=gen)
+    results = [torch.empty((G,), dtype=torch.uint8, device=dev) for _ in range(n_batches)]
+    stream = torch.cuda.Stream(dev)
+
+    def step(k):
+        b = k % n_batches
+        upd.update(batches[b], moves[k % n_move_sets], out=results[b])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    with torch.cuda.stream(stream):
+        # de-phase the batches so they are not all at the same tick (spreads resets), untimed
+        for b in range(n_batches):
+            upd.rollout(batches[b], 1, 1, 37 * (b + 1))
+        for k in range(max(W, 3)):
+            step(k)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for k in range(K):
+                step(k)
+        graph.replay()      # one untimed replay (graph upload)
+        torch.cuda.synchronize(dev)
+
+        # ---- value: K steps, commands resident in HBM
+        barrier()
+        t_wall0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        graph.replay()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        t_wall1 = time.time()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+
+        # ---- e2e: public API with host buffers, every step H2D + tick + D2H + sync
+        host_moves = [torch.empty((G, 2), dtype=torch.uint8, pin_memory=True) for _ in range(4)]
+        for hm in host_moves:
+            hm.copy_(moves[0].cpu())
+        host_res = torch.empty((G,), dtype=torch.uint8, pin_memory=True)
+        k_e2e = max(10, min(K, 200))
+        for k in range(3):
+            upd.update(batches[k % n_batches], host_moves[k % 4], out=host_res)
+            stream.synchronize()
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        for k in range(k_e2e):
+            upd.update(batches[k % n_batches], host_moves[k % 4], out=host_res)
+            stream.synchronize()          # the caller reads host_res here
+        e3.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms_e2e = e2.elapsed_time(e3)
+
+        # ---- rollout (extra): fused T-tick kernel, both bots on device
+        T = args.rollout_ticks
+        stats = torch.zeros((8,), dtype=torch.int64, device=dev)
+        r_launches = max(2, min(n_batches, 8))
+        for b in range(2):
+            upd.rollout(batches[b], 1, 1, T, stats)
+        torch.cuda.synchronize(dev)
+        stats.zero_()
+        barrier()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record(stream)
+        for b in range(r_launches):
+            upd.rollout(batches[b % n_batches], 1, 1, T, stats)
+        e5.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms_roll = e4.elapsed_time(e5)
+        roll_ticks = int(stats[0].item())
+
+    if rank == 0:
+        time.sleep(0.15)
+        sampler.stop()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_total = max_over_ranks(ms_total)
+    ms_e2e = max_over_ranks(ms_e2e)
+    ms_roll = max_over_ranks(ms_roll)
+    if world > 1:
+        t = torch.tensor([roll_ticks], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)          # the optional end-of-rollout stats gather (tiny, off the step path)
+        roll_ticks_all = int(t.item())
+    else:
+        roll_ticks_all = roll_ticks
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ms_step = ms_total / K
+        value = world * G * K / (ms_total * 1e-3)
+        achieved = B_ALG * G / (ms_step * 1e-3) / 1e9
+        tr = recorded_traffic()
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'int32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'games_per_gpu': G, 'global_games': G * world,
+                       'parallelism': f'{world} shard(s) of independent games, no collective on the step path',
+                       'l2': f'rotating {n_batches} independent batches per GPU ({n_batches * (state_bytes + 3 * G) / 1e6:.0f} MB of planes > 126 MB L2), no flush needed',
+                       'launch': 'K steps captured in one CUDA graph'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': (tr or {}).get('dram_bytes_per_launch'), 'peak_source': peak_src,
+                         'kernel': 'k_step<EMPTY,false,false>', 'alg_bytes_per_game_tick': B_ALG,
+                         'games_per_launch': G},
+            'e2e': {'value': world * G * k_e2e / (ms_e2e * 1e-3), 'unit': UNIT,
+                    'h2d_bytes_per_step': 2 * G, 'd2h_bytes_per_step': G, 'steps': k_e2e,
+                    'api': 'BatchedUpdater.update(state, pinned host uint8[N,2]) -> pinned host uint8[N] (orx_step_host), sync every step'},
+            'gpu_launches': K,
+            'rollout': {'value': roll_ticks_all / (ms_roll * 1e-3), 'unit': UNIT, 'ticks_per_launch': T,
+                        'launches': r_launches, 'fused': True,
+                        'note': 'orx_rollout: bots + tick fused, state in registers for T ticks'},
+            'clocks': sampler.summary(t_wall0, t_wall1),
+        }
+        if not args.no_cpu_baseline:
+            v, cores, ticks, el = cpu_port_run(1 << 18, args.cpu_seconds)
+            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': f'{ticks} game-ticks in {el:.1f} s: 2^18 games, same config, oracle/orx_oracle.c oro_rollout (RandomBot x2), OpenMP over all host cores'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world == 1 and args.gpus > 1 and 'RANK' not in os.environ:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

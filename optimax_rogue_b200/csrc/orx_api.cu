@@ -12,6 +12,32 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxFixedTiles = 16384;   // shared-memory staging of the fixed map
+constexpr int64_t kMaxGamesPerCall = 1ll << 30;   // 32-bit lane index inside the kernels; larger batches: call per chunk
+
+__device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int2 ldg_s32x2(const int2* p)
+{
+    int2 v;
+    asm volatile("ld.global.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_u16(const uint16_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.u16 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
 __device__ __forceinline__ const uint8_t* stage_tiles(const Params& P, uint8_t* smem)
 {
@@ -23,39 +49,46 @@ __device__ __forceinline__ const uint8_t* stage_tiles(const Params& P, uint8_t* 
 }
 
 // ------------------------------------------------------------------ K1: one tick
+// One thread per game. All eight plane loads are issued before anything depends on them; the
+// per-game traffic is 29 B of planes in, 29 B out, 2 B of commands in, 1 B of result out.
 template <int DGEN, bool NPC, bool EV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 k_step(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result,
        uint2* __restrict__ events, int max_ev)
 {
     extern __shared__ uint8_t smem[];
     const uint8_t* tiles = nullptr;
     if (DGEN == ORX_DGEN_FIXED) tiles = stage_tiles(P, smem);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        const int status = P.status[i];
-        EvSink<EV> ev{EV ? events + i * max_ev : nullptr, 0, max_ev};
-        if (status != ORX_RESULT_IN_PROGRESS) {   // finished lanes are frozen until reset
-            result[i] = (uint8_t)status;
-            ev.finish();
-            continue;
-        }
-        Lane L;
-        load_lane(P, i, L);
-        const uint16_t mv = moves[i];
-        Stream s = make_stream(P, i, L.episode);
-        const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
-        Counters cnt{};
-        int res = tick_lane<DGEN, NPC, EV>(P, tiles, L, mv & 255, mv >> 8, blk.z, s, i, ev, cnt);
+    const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P.n) return;
+    // Eight independent loads in flight per thread before the first use (asm volatile keeps ptxas
+    // from sinking them below the frozen-lane test, which would serialise two DRAM round trips).
+    const uint32_t pos = ldg_u32(P.pos + i), hpw = ldg_u32(P.hp + i), stw = ldg_u32(P.stairs + i);
+    const uint32_t ep = ldg_u32(P.episode + i);
+    const int tick = (int)ldg_u32(reinterpret_cast<const uint32_t*>(P.tick) + i);
+    const int2 dep = ldg_s32x2(P.depth + i);
+    const int status = (int)ldg_u8(P.status + i);
+    const uint32_t mv = ldg_u16(moves + i);
+    EvSink<EV> ev{EV ? events + (size_t)i * max_ev : nullptr, 0, max_ev};
+    if (status != ORX_RESULT_IN_PROGRESS) {   // finished lanes are frozen until reset
+        result[i] = (uint8_t)status;
         ev.finish();
-        result[i] = (uint8_t)res;
-        if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
-            s.episode += 1;
-            reset_lane<DGEN, NPC>(P, L, s, i);
-            res = ORX_RESULT_IN_PROGRESS;
-        }
-        store_lane(P, i, L, res);
+        return;
     }
+    Lane L;
+    unpack_lane(L, pos, hpw, dep, stw, tick, ep);
+    Stream s = make_stream(P, i, ep);
+    const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)tick);
+    Counters cnt{};
+    int res = tick_lane<DGEN, NPC, EV>(P, tiles, L, mv, blk.z, s, i, ev, cnt);
+    ev.finish();
+    result[i] = (uint8_t)res;
+    if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
+        s.episode += 1;
+        reset_lane<DGEN, NPC>(P, L, s, i);
+        res = ORX_RESULT_IN_PROGRESS;
+    }
+    store_lane(P, i, L, res);
 }
 
 // ------------------------------------------------------------------ K2: masked episode reset
@@ -63,35 +96,33 @@ template <int DGEN, bool NPC>
 __global__ void __launch_bounds__(kThreads)
 k_reset(const __grid_constant__ Params P, const uint8_t* __restrict__ mask, int bump)
 {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        if (mask != nullptr && mask[i] == 0) continue;
-        Lane L;
-        Stream s = make_stream(P, i, P.episode[i] + (bump ? 1u : 0u));
-        reset_lane<DGEN, NPC>(P, L, s, i);
-        store_lane(P, i, L, ORX_RESULT_IN_PROGRESS);
-    }
+    const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P.n) return;
+    if (mask != nullptr && mask[i] == 0) return;
+    Lane L;
+    Stream s = make_stream(P, i, P.episode[i] + (bump ? 1u : 0u));
+    reset_lane<DGEN, NPC>(P, L, s, i);
+    store_lane(P, i, L, ORX_RESULT_IN_PROGRESS);
 }
 
 // ------------------------------------------------------------------ K3: scripted bots
 __global__ void __launch_bounds__(kThreads)
 k_bot_moves(const __grid_constant__ Params P, int bot1, int bot2, uint8_t* __restrict__ moves)
 {
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P.n) return;
     const bool need_rng = bot1 == ORX_BOT_RANDOM || bot2 == ORX_BOT_RANDOM;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        Lane L;
-        load_lane(P, i, L);
-        uint4 blk = make_uint4(0, 0, 0, 0);
-        if (need_rng) blk = draw_block(make_stream(P, i, L.episode), DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
-        if (bot1 != ORX_BOT_NONE && bot2 != ORX_BOT_NONE) {
-            const int m1 = bot_move(bot1, L.p1, blk.x), m2 = bot_move(bot2, L.p2, blk.y);
-            reinterpret_cast<uint16_t*>(moves)[i] = (uint16_t)(m1 | (m2 << 8));
-        } else if (bot1 != ORX_BOT_NONE) {
-            moves[2 * i] = (uint8_t)bot_move(bot1, L.p1, blk.x);
-        } else if (bot2 != ORX_BOT_NONE) {
-            moves[2 * i + 1] = (uint8_t)bot_move(bot2, L.p2, blk.y);
-        }
+    const uint32_t pos = P.pos[i], st = P.stairs[i];
+    uint4 blk = make_uint4(0, 0, 0, 0);
+    if (need_rng) blk = draw_block(make_stream(P, i, P.episode[i]), DOM_TICK, SUB_MAIN, (uint32_t)P.tick[i]);
+    if (bot1 != ORX_BOT_NONE && bot2 != ORX_BOT_NONE) {
+        const uint32_t m1 = bot_move(bot1, pos & 0xFFFFu, st & 0xFFFFu, blk.x);
+        const uint32_t m2 = bot_move(bot2, pos >> 16, st >> 16, blk.y);
+        reinterpret_cast<uint16_t*>(moves)[i] = (uint16_t)(m1 | (m2 << 8));
+    } else if (bot1 != ORX_BOT_NONE) {
+        moves[2 * (size_t)i] = (uint8_t)bot_move(bot1, pos & 0xFFFFu, st & 0xFFFFu, blk.x);
+    } else if (bot2 != ORX_BOT_NONE) {
+        moves[2 * (size_t)i + 1] = (uint8_t)bot_move(bot2, pos >> 16, st >> 16, blk.y);
     }
 }
 
@@ -114,34 +145,36 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
     if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     Counters cnt{};
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+    const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i < P.n) {
         int status = P.status[i];
-        if (status != ORX_RESULT_IN_PROGRESS) continue;
-        Lane L;
-        load_lane(P, i, L);
-        Stream s = make_stream(P, i, L.episode);
-        EvSink<false> ev{nullptr, 0, 0};
-        for (int t = 0; t < n_ticks; ++t) {
-            const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
-            const int m1 = bot_move(bot1, L.p1, blk.x), m2 = bot_move(bot2, L.p2, blk.y);
-            const int res = tick_lane<DGEN, NPC, false>(P, tiles, L, m1, m2, blk.z, s, i, ev, cnt);
-            ++cnt.ticks;
-            if (res != ORX_RESULT_IN_PROGRESS) {
-                cnt.p1 += res == ORX_RESULT_PLAYER1_WIN;
-                cnt.p2 += res == ORX_RESULT_PLAYER2_WIN;
-                cnt.ties += res == ORX_RESULT_TIE;
-                if (P.auto_reset) {
-                    s.episode += 1;
-                    reset_lane<DGEN, NPC>(P, L, s, i);
-                } else {
-                    status = res;
-                    break;
+        if (status == ORX_RESULT_IN_PROGRESS) {
+            Lane L;
+            load_lane(P, i, L);
+            Stream s = make_stream(P, i, L.episode);
+            EvSink<false> ev{nullptr, 0, 0};
+            for (int t = 0; t < n_ticks; ++t) {
+                const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
+                const uint32_t m1 = bot_move(bot1, L.pos & 0xFFFFu, L.st & 0xFFFFu, blk.x);
+                const uint32_t m2 = bot_move(bot2, L.pos >> 16, L.st >> 16, blk.y);
+                const int res = tick_lane<DGEN, NPC, false>(P, tiles, L, m1 | (m2 << 8), blk.z, s, i, ev, cnt);
+                ++cnt.ticks;
+                if (res != ORX_RESULT_IN_PROGRESS) {
+                    cnt.p1 += res == ORX_RESULT_PLAYER1_WIN;
+                    cnt.p2 += res == ORX_RESULT_PLAYER2_WIN;
+                    cnt.ties += res == ORX_RESULT_TIE;
+                    if (P.auto_reset) {
+                        s.episode += 1;
+                        reset_lane<DGEN, NPC>(P, L, s, i);
+                    } else {
+                        status = res;
+                        break;
+                    }
                 }
             }
+            cnt.events += (unsigned int)ev.n;
+            store_lane(P, i, L, status);
         }
-        cnt.events += (unsigned int)ev.n;
-        store_lane(P, i, L, status);
     }
     if (stats != nullptr) {
         unsigned int v[7] = {cnt.ticks, cnt.p1, cnt.p2, cnt.ties, cnt.events, cnt.descents, cnt.hits};
@@ -162,27 +195,27 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
 __global__ void __launch_bounds__(kThreads)
 k_observe(const __grid_constant__ Params P, int16_t* __restrict__ obs, int radius)
 {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        Lane L;
-        load_lane(P, i, L);
-        const bool same = L.p1.depth == L.p2.depth;   // view_for keeps entities on the viewer's depth
-        const int tk = min(L.tick, 32767);
+    const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P.n) return;
+    Lane L;
+    load_lane(P, i, L);
+    const bool same = L.d1 == L.d2;   // view_for keeps entities on the viewer's depth
+    const int tk = min(L.tick, 32767);
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const Mover& me = p == 0 ? L.p1 : L.p2;
-            const Mover& ot = p == 0 ? L.p2 : L.p1;
-            const bool has_st = me.sx != ORX_NO_STAIRS;
-            const bool st_vis = has_st && (radius < 0 || max(abs(me.sx - me.x), abs(me.sy - me.y)) <= radius);
-            // packed as 3 x 8-byte stores of int16 quads
-            const short q0[4] = {(short)me.x, (short)me.y, (short)min(me.depth, 32767), (short)me.hp};
-            const short q1[4] = {(short)same, (short)(same ? ot.x : -1), (short)(same ? ot.y : -1), (short)(same ? ot.hp : 0)};
-            const short q2[4] = {(short)st_vis, (short)(st_vis ? me.sx : -1), (short)(st_vis ? me.sy : -1), (short)tk};
-            short* o = obs + (i * 2 + p) * ORX_OBS_LEN;
-            *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(q0);
-            *reinterpret_cast<uint2*>(o + 4) = *reinterpret_cast<const uint2*>(q1);
-            *reinterpret_cast<uint2*>(o + 8) = *reinterpret_cast<const uint2*>(q2);
-        }
+    for (int p = 0; p < 2; ++p) {
+        const uint32_t me = p == 0 ? (L.pos & 0xFFFFu) : (L.pos >> 16), ot = p == 0 ? (L.pos >> 16) : (L.pos & 0xFFFFu);
+        const uint32_t sxy = p == 0 ? (L.st & 0xFFFFu) : (L.st >> 16);
+        const int mx = me & 255u, my = me >> 8, sx = sxy & 255u, sy = sxy >> 8;
+        const int md = p == 0 ? L.d1 : L.d2, mh = p == 0 ? L.hp1 : L.hp2, oh = p == 0 ? L.hp2 : L.hp1;
+        const bool has_st = sx != ORX_NO_STAIRS;
+        const bool st_vis = has_st && (radius < 0 || max(abs(sx - mx), abs(sy - my)) <= radius);
+        const short q0[4] = {(short)mx, (short)my, (short)min(md, 32767), (short)mh};
+        const short q1[4] = {(short)same, (short)(same ? (int)(ot & 255u) : -1), (short)(same ? (int)(ot >> 8) : -1), (short)(same ? oh : 0)};
+        const short q2[4] = {(short)st_vis, (short)(st_vis ? sx : -1), (short)(st_vis ? sy : -1), (short)tk};
+        short* o = obs + ((size_t)i * 2 + p) * ORX_OBS_LEN;
+        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(q0);
+        *reinterpret_cast<uint2*>(o + 4) = *reinterpret_cast<const uint2*>(q1);
+        *reinterpret_cast<uint2*>(o + 8) = *reinterpret_cast<const uint2*>(q2);
     }
 }
 
@@ -194,6 +227,7 @@ bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) &
 int check_common(const OrxConfig* cfg, const OrxState* st, int64_t n)
 {
     if (cfg == nullptr || st == nullptr || n < 0) return ORX_ERR_BAD_ARG;
+    if (n > kMaxGamesPerCall) return ORX_ERR_UNSUPPORTED;
     if (cfg->struct_size != sizeof(OrxConfig)) return ORX_ERR_BAD_ARG;
     if (cfg->width < 4 || cfg->height < 4 || cfg->width > ORX_MAX_DIM || cfg->height > ORX_MAX_DIM) return ORX_ERR_BAD_ARG;
     if (cfg->n_npc < 0 || cfg->n_npc > ORX_MAX_NPC) return ORX_ERR_BAD_ARG;
@@ -233,18 +267,14 @@ Params make_params(const OrxConfig* c, const OrxState* st, int64_t n, uint64_t g
     P.depth = reinterpret_cast<int2*>(st->depth); P.stairs = reinterpret_cast<uint32_t*>(st->stairs);
     P.tick = st->tick; P.episode = st->episode; P.status = st->status;
     P.npc_pos = st->npc_pos; P.npc_hp = st->npc_hp; P.npc_depth = st->npc_depth;
-    P.n = n; P.gid_base = gid_base;
+    P.lim_lo = 0xFFu | (1u << 8) | ((uint32_t)(c->width - 2) << 16) | ((uint32_t)(c->height - 2) << 24);
+    P.lim_hi = 1u | 0xFFFFFF00u;
+    P.n = (unsigned int)n; P.gid_base = gid_base;
     return P;
 }
 
-int grid_for(int64_t n, int ctas_per_sm)
-{
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t need = (n + kThreads - 1) / kThreads;
-    const int64_t cap = (int64_t)sms * ctas_per_sm;      // whole waves of resident CTAs
-    return (int)(need < cap ? need : cap);
-}
+int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
+
 
 size_t tiles_smem(const OrxConfig* c) { return c->dgen_kind == ORX_DGEN_FIXED ? (size_t)c->width * c->height : 0; }
 
@@ -296,7 +326,7 @@ int orx_reset(const OrxConfig* cfg, const OrxState* st, const uint8_t* mask, int
     if (n == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, game_id_base);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    const int grid = grid_for(n, 8);
+    const int grid = grid_for(n);
     return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
         k_reset<DGEN, NPC><<<grid, kThreads, 0, s>>>(P, mask, bump_episode);
         return launch_done();
@@ -312,7 +342,7 @@ int orx_step(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uin
     if (n == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, game_id_base);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    const int grid = grid_for(n, 8);
+    const int grid = grid_for(n);
     const size_t smem = tiles_smem(cfg);
     const uint16_t* mv = reinterpret_cast<const uint16_t*>(moves);
     uint2* ev = reinterpret_cast<uint2*>(events);
@@ -350,7 +380,7 @@ int orx_bot_moves(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_
     if (bot_p1 < ORX_BOT_NONE || bot_p1 > ORX_BOT_STAIRCASE || bot_p2 < ORX_BOT_NONE || bot_p2 > ORX_BOT_STAIRCASE) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, game_id_base);
-    k_bot_moves<<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P, bot_p1, bot_p2, moves);
+    k_bot_moves<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P, bot_p1, bot_p2, moves);
     return launch_done();
 }
 
@@ -364,7 +394,7 @@ int orx_rollout(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2
     if (n == 0 || n_ticks == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, game_id_base);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    const int grid = grid_for(n, 8);
+    const int grid = grid_for(n);
     const size_t smem = tiles_smem(cfg);
     return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
         k_rollout<DGEN, NPC><<<grid, kThreads, smem, s>>>(P, bot_p1, bot_p2, n_ticks, stats);
@@ -380,7 +410,7 @@ int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stai
     if (obs == nullptr || !aligned(obs, 8)) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, 0);
-    k_observe<<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P, obs, stairs_radius);
+    k_observe<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P, obs, stairs_radius);
     return launch_done();
 }
 

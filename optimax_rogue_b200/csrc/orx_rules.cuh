@@ -1,6 +1,13 @@
-// Data-parallel formulation of one Optimax Rogue tick: one thread owns one game, the whole
-// game state lives in registers, and the two movers are resolved in initiative order by
-// swapping roles with selects (no divergent "who goes first" branch, no local-memory arrays).
+// Data-parallel formulation of one Optimax Rogue tick: one thread owns one game and the whole
+// game state lives in a handful of registers, in the same packed form the HBM planes use:
+//
+//   pos  = x1 | y1<<8 | x2<<16 | y2<<24      (one 16-bit "xy" per player)
+//   st   = staircase xy of each player's level, same packing
+//   a command is reduced to a signed xy delta (Up -256, Right +1, Down +256, Left -1, Stay 0)
+//
+// so that "move" is one add on the packed word, "is that tile occupied / the staircase" is one
+// 16-bit compare, and "who goes first" is a byte permute (PRMT) of the two halves instead of a
+// divergent branch or an array in local memory.
 //
 // Reference behaviour restated here (paths under the reference root):
 //   Updater.update            optimax_rogue/logic/updater.py:76-162
@@ -28,20 +35,21 @@ struct Params {
     int dmg0, dmg1;            // damage - armor of the ATTACKER (updater.py:313)
     int auto_reset, n_npc;
     uint32_t k0, k1;
+    uint32_t lim_lo, lim_hi;   // per-command wall limit of the moved coordinate (EMPTY rooms)
     const uint8_t* tiles;      // DGEN_FIXED: uint8[W*H] x-major
     const uint16_t* ground;    // DGEN_FIXED: Ground tile list
     int n_ground, fsx, fsy;
-    uint32_t* pos;             // x1 | y1<<8 | x2<<16 | y2<<24
+    uint32_t* pos;
     uint32_t* hp;              // int16 hp1 | int16 hp2 << 16
     int2* depth;
-    uint32_t* stairs;          // sx1 | sy1<<8 | sx2<<16 | sy2<<24
+    uint32_t* stairs;
     int* tick;
     uint32_t* episode;
     uint8_t* status;
     uint8_t* npc_pos;
     int16_t* npc_hp;
     int* npc_depth;
-    long long n;
+    unsigned int n;            // games in this launch (host chunks batches above 2^30)
     unsigned long long gid_base;
 };
 
@@ -49,7 +57,12 @@ struct Counters {               // per-thread, reduced at the end of orx_rollout
     unsigned int ticks, p1, p2, ties, events, descents, hits;
 };
 
-struct Mover { int x, y, hp, depth, sx, sy, mv, id, dmg; };
+// Game state of one lane in registers.
+struct Lane {
+    uint32_t pos, st;
+    int hp1, hp2, d1, d2, tick;
+    uint32_t episode;
+};
 
 template <bool EV>
 struct EvSink {
@@ -69,22 +82,6 @@ struct EvSink {
 };
 
 // ---------------------------------------------------------------- level model
-template <int DGEN>
-__device__ __forceinline__ bool is_blocked(const Params& P, const uint8_t* tiles, int x, int y)
-{
-    if (DGEN == ORX_DGEN_EMPTY)   // border walls; out of bounds is covered by the same compare
-        return (x <= 0) | (y <= 0) | (x >= P.W - 1) | (y >= P.H - 1);
-    if ((unsigned)x >= (unsigned)P.W || (unsigned)y >= (unsigned)P.H) return true;
-    return tiles[x * P.H + y] == ORX_TILE_WALL;
-}
-
-template <int DGEN>
-__device__ __forceinline__ bool is_stairs(const Params& P, const uint8_t* tiles, int x, int y, int sx, int sy)
-{
-    if (DGEN == ORX_DGEN_EMPTY) return (x == sx) & (y == sy);
-    return tiles[x * P.H + y] == ORX_TILE_STAIRCASE_DOWN;
-}
-
 // worldgen.py:39-40 (numpy randint is high-exclusive: W-3 / H-3 values starting at 1)
 template <int DGEN>
 __device__ __forceinline__ void level_stairs(const Params& P, const Stream& s, int depth, int& sx, int& sy)
@@ -122,10 +119,10 @@ __device__ __forceinline__ void kth_ground(const Params& P, int sx, int sy, int 
     }
 }
 
-__device__ __forceinline__ int npc_at(const Params& P, long long lane, int depth, int x, int y)
+__device__ __forceinline__ int npc_at(const Params& P, unsigned int lane, int depth, int x, int y)
 {
     for (int k = 0; k < P.n_npc; ++k) {
-        const long long j = lane * P.n_npc + k;
+        const size_t j = (size_t)lane * P.n_npc + k;
         if (P.npc_depth[j] == depth && P.npc_pos[2 * j] == x && P.npc_pos[2 * j + 1] == y) return k;
     }
     return -1;
@@ -142,10 +139,10 @@ __device__ __forceinline__ bool level_exists(const Params& P, int pid, int depth
 
 // ---------------------------------------------------------------- rare paths (kept out of line)
 // handle_descend draws: stairs of the new level, then spawn tries until the tile is free
-// (updater.py:282-285). Returns sx | sy<<8 | x<<16 | y<<24.
+// (updater.py:282-285). Returns sx | sy<<8 | x<<16 | y<<24  (= new st half | new pos half << 16).
 template <int DGEN, bool NPC>
 __device__ __noinline__ uint32_t descend_draw(const Params& P, Stream s, int tick, int pid, int new_depth,
-                                              int ox, int oy, int odepth, long long lane)
+                                              uint32_t oxy, int odepth, unsigned int lane)
 {
     int sx, sy, x, y;
     level_stairs<DGEN>(P, s, new_depth, sx, sy);
@@ -155,7 +152,7 @@ __device__ __noinline__ uint32_t descend_draw(const Params& P, Stream s, int tic
     do {
         const int k = (int)seq_bounded(s, DOM_TICK, SUB_DESCEND + 64u * (uint32_t)pid, (uint32_t)tick, q++, (uint32_t)ng);
         kth_ground<DGEN>(P, sx, sy, k, x, y);
-        taken = (odepth == new_depth) & (ox == x) & (oy == y);
+        taken = (odepth == new_depth) & (oxy == ((uint32_t)x | ((uint32_t)y << 8)));
         if (NPC) taken = taken || npc_at(P, lane, new_depth, x, y) >= 0;
     } while (taken);
     return (uint32_t)sx | ((uint32_t)sy << 8) | ((uint32_t)x << 16) | ((uint32_t)y << 24);
@@ -185,94 +182,118 @@ __device__ __noinline__ uint2 reset_draw(const Params& P, Stream s)
                       (uint32_t)sx1 | ((uint32_t)sy1 << 8) | ((uint32_t)sx2 << 16) | ((uint32_t)sy2 << 24));
 }
 
-// ---------------------------------------------------------------- one mover (updater.py:180-243)
-template <int DGEN, bool NPC, bool EV, int IND>
-__device__ __forceinline__ void do_move(const Params& P, const uint8_t* tiles, Mover& me, Mover& ot,
-                                        const Stream& s, int tick, long long lane, EvSink<EV>& ev, Counters& cnt)
+// ---------------------------------------------------------------- command -> clamped xy delta
+// Returns 0 for Stay, for codes outside Move (logic/moves.py:6-12) and for a move into a Wall or
+// off the map (updater.py:90-98, world.py:41-46), evaluated from the pre-tick position.
+template <int DGEN>
+__device__ __forceinline__ int clamped_delta(const Params& P, const uint8_t* tiles, uint32_t m, uint32_t xy)
 {
-    if (me.mv == ORX_MOVE_STAY) return;
-    const int nx = me.x + (me.mv == ORX_MOVE_RIGHT) - (me.mv == ORX_MOVE_LEFT);
-    const int ny = me.y + (me.mv == ORX_MOVE_DOWN) - (me.mv == ORX_MOVE_UP);
-    if ((ot.depth == me.depth) & (ot.x == nx) & (ot.y == ny)) {
-        // Block if the occupant's (clamped) move is Stay; otherwise Ambush when the occupant acted
-        // earlier (it just arrived) or Flee when it acts later. Parry (updater.py:229-234) needs
-        // occupant.pos + delta == occupant.pos with a non-Stay move: unreachable.
-        const int flag = ot.mv == ORX_MOVE_STAY ? ORX_FLAG_BLOCK : (IND == 1 ? ORX_FLAG_AMBUSH : ORX_FLAG_FLEE);
-        if (me.dmg > 0) { ot.hp -= me.dmg; ++cnt.hits; }
-        ev.emit(ORX_EV_COMBAT, me.id + 1, ot.id + 1, flag, me.dmg);
-        return;                                   // the attacker never advances (updater.py:222-243)
-    }
-    if (NPC) {
-        const int k = npc_at(P, lane, me.depth, nx, ny);
-        if (k >= 0) {                             // NPC moves are always Stay (updater.py:165-178)
-            if (me.dmg > 0) { P.npc_hp[lane * P.n_npc + k] -= (int16_t)me.dmg; ++cnt.hits; }
-            ev.emit(ORX_EV_COMBAT, me.id + 1, 3 + k, ORX_FLAG_BLOCK, me.dmg);
-            return;
+    const bool odd = (m & 1u) != 0;                     // Up(1)/Down(3) move y, Right(2)/Left(4) move x
+    const int dd = odd ? ((int)(m - 2u) << 8) : (int)(3u - m);
+    bool ok = (m - 1u) < 4u;
+    if (DGEN == ORX_DGEN_EMPTY) {
+        // Inside an empty room only the border blocks: the moved coordinate must not already sit
+        // next to it. lim bytes (indexed by the command): Up 1, Right W-2, Down H-2, Left 1.
+        const uint32_t c = odd ? (xy >> 8) : (xy & 255u);
+        const uint32_t lim = __byte_perm(P.lim_lo, P.lim_hi, m & 7u) & 255u;
+        ok = ok & (c != lim);
+    } else {
+        const int x = (int)(xy & 255u) + (odd ? 0 : (int)(3u - m));
+        const int y = (int)(xy >> 8) + (odd ? (int)(m - 2u) : 0);
+        if (ok) {
+            ok = (unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H;
+            if (ok) ok = tiles[x * P.H + y] != ORX_TILE_WALL;
         }
     }
-    if (is_stairs<DGEN>(P, tiles, nx, ny, me.sx, me.sy)) {
-        const int nd = me.depth + 1;
-        const uint32_t r = descend_draw<DGEN, NPC>(P, s, tick, me.id, nd, ot.x, ot.y, ot.depth, lane);
-        const int nsx = r & 255, nsy = (r >> 8) & 255, sxp = (r >> 16) & 255, syp = r >> 24;
-        if (!level_exists(P, me.id, nd, ot.depth)) ev.emit(ORX_EV_DUNGEON, 0, nsx, nsy, nd);
-        ev.emit(ORX_EV_DESCEND, me.id + 1, sxp, syp, nd);
-        me.depth = nd; me.x = sxp; me.y = syp; me.sx = nsx; me.sy = nsy;
-        ++cnt.descents;
-        return;
-    }
-    ev.emit(ORX_EV_MOVE, me.id + 1, nx, ny, me.depth);
-    me.x = nx; me.y = ny;
+    return ok ? dd : 0;
 }
 
-// Game state of one lane, unpacked into registers.
-struct Lane {
-    Mover p1, p2;       // .mv/.id/.dmg filled by tick_lane
-    int tick;
-    uint32_t episode;
-};
-
-__device__ __forceinline__ Mover pick(bool c, const Mover& a, const Mover& b)
+template <int DGEN>
+__device__ __forceinline__ bool is_stairs(const Params& P, const uint8_t* tiles, uint32_t txy, uint32_t sxy)
 {
-    Mover r;
-    r.x = c ? a.x : b.x; r.y = c ? a.y : b.y; r.hp = c ? a.hp : b.hp; r.depth = c ? a.depth : b.depth;
-    r.sx = c ? a.sx : b.sx; r.sy = c ? a.sy : b.sy; r.mv = c ? a.mv : b.mv; r.id = c ? a.id : b.id;
-    r.dmg = c ? a.dmg : b.dmg;
-    return r;
+    if (DGEN == ORX_DGEN_EMPTY) return txy == sxy;
+    return tiles[(txy & 255u) * P.H + (txy >> 8)] == ORX_TILE_STAIRCASE_DOWN;
 }
 
-// One Updater.update. w_init is word 2 of the tick's main block. Returns the UpdateResult.
+// One Updater.update. mv = p1 command | p2 command << 8; w_init is word 2 of the tick's main
+// block. Returns the UpdateResult.
 template <int DGEN, bool NPC, bool EV>
-__device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, Lane& L, int m1, int m2,
-                                         uint32_t w_init, const Stream& s, long long lane,
+__device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, Lane& L, uint32_t mv,
+                                         uint32_t w_init, const Stream& s, unsigned int lane,
                                          EvSink<EV>& ev, Counters& cnt)
 {
-    // commands outside Move (logic/moves.py:6-12) are Stay
-    m1 = (m1 >= ORX_MOVE_UP && m1 <= ORX_MOVE_LEFT) ? m1 : ORX_MOVE_STAY;
-    m2 = (m2 >= ORX_MOVE_UP && m2 <= ORX_MOVE_LEFT) ? m2 : ORX_MOVE_STAY;
-    // wall clamp from pre-tick positions, before the shuffle (updater.py:90-98)
-    {
-        const int nx = L.p1.x + (m1 == ORX_MOVE_RIGHT) - (m1 == ORX_MOVE_LEFT);
-        const int ny = L.p1.y + (m1 == ORX_MOVE_DOWN) - (m1 == ORX_MOVE_UP);
-        if (is_blocked<DGEN>(P, tiles, nx, ny)) m1 = ORX_MOVE_STAY;
+    const int dl1 = clamped_delta<DGEN>(P, tiles, mv & 255u, L.pos & 0xFFFFu);
+    const int dl2 = clamped_delta<DGEN>(P, tiles, (mv >> 8) & 255u, L.pos >> 16);
+    // random.shuffle([p1, p2]) (updater.py:114): j = randbelow(2) = w >> 31; j == 0 swaps => p2 first.
+    // Roles: A acts first and lives in the LOW half of pos/st, B acts second in the HIGH half.
+    const bool p2_first = (int)w_init >= 0;
+    const uint32_t sel = p2_first ? 0x1032u : 0x3210u;
+    uint32_t pos = __byte_perm(L.pos, 0u, sel);
+    uint32_t st = __byte_perm(L.st, 0u, sel);
+    const int dA = p2_first ? dl2 : dl1, dB = p2_first ? dl1 : dl2;
+    int depA = p2_first ? L.d2 : L.d1, depB = p2_first ? L.d1 : L.d2;
+    int hpA = p2_first ? L.hp2 : L.hp1, hpB = p2_first ? L.hp1 : L.hp2;
+    const int dmgA = p2_first ? P.dmg1 : P.dmg0, dmgB = p2_first ? P.dmg0 : P.dmg1;
+    const int idA = p2_first ? 1 : 0, idB = idA ^ 1;
+
+    // ---- first mover (handle_move, updater.py:180-243)
+    if (dA != 0) {
+        const uint32_t tA = (pos + (uint32_t)dA) & 0xFFFFu;
+        int npc = -1;
+        if ((depA == depB) & (tA == (pos >> 16))) {
+            // Occupied by B, who acts later: Block if B stays, else Flee. (Parry, updater.py:229-234,
+            // would need B.pos + delta == B.pos with a non-Stay move: unreachable.)
+            if (dmgA > 0) { hpB -= dmgA; ++cnt.hits; }
+            ev.emit(ORX_EV_COMBAT, idA + 1, idB + 1, dB == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_FLEE, dmgA);
+        } else if (NPC && (npc = npc_at(P, lane, depA, tA & 255u, tA >> 8)) >= 0) {
+            if (dmgA > 0) { P.npc_hp[(size_t)lane * P.n_npc + npc] -= (int16_t)dmgA; ++cnt.hits; }
+            ev.emit(ORX_EV_COMBAT, idA + 1, 3 + npc, ORX_FLAG_BLOCK, dmgA);
+        } else if (is_stairs<DGEN>(P, tiles, tA, st & 0xFFFFu)) {
+            const int nd = depA + 1;
+            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idA, nd, pos >> 16, depB, lane);
+            if (!level_exists(P, idA, nd, depB)) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
+            ev.emit(ORX_EV_DESCEND, idA + 1, (r >> 16) & 255u, r >> 24, nd);
+            depA = nd;
+            pos = (pos & 0xFFFF0000u) | (r >> 16);
+            st = (st & 0xFFFF0000u) | (r & 0xFFFFu);
+            ++cnt.descents;
+        } else {
+            ev.emit(ORX_EV_MOVE, idA + 1, tA & 255u, tA >> 8, depA);
+            pos += (uint32_t)dA;          // the clamp keeps the target on the map: no carry between halves
+        }
     }
-    {
-        const int nx = L.p2.x + (m2 == ORX_MOVE_RIGHT) - (m2 == ORX_MOVE_LEFT);
-        const int ny = L.p2.y + (m2 == ORX_MOVE_DOWN) - (m2 == ORX_MOVE_UP);
-        if (is_blocked<DGEN>(P, tiles, nx, ny)) m2 = ORX_MOVE_STAY;
+    // ---- second mover: sees A's updated position and depth
+    if (dB != 0) {
+        const uint32_t tB = ((pos >> 16) + (uint32_t)dB) & 0xFFFFu;
+        int npc = -1;
+        if ((depA == depB) & (tB == (pos & 0xFFFFu))) {
+            if (dmgB > 0) { hpA -= dmgB; ++cnt.hits; }
+            ev.emit(ORX_EV_COMBAT, idB + 1, idA + 1, dA == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_AMBUSH, dmgB);
+        } else if (NPC && (npc = npc_at(P, lane, depB, tB & 255u, tB >> 8)) >= 0) {
+            if (dmgB > 0) { P.npc_hp[(size_t)lane * P.n_npc + npc] -= (int16_t)dmgB; ++cnt.hits; }
+            ev.emit(ORX_EV_COMBAT, idB + 1, 3 + npc, ORX_FLAG_BLOCK, dmgB);
+        } else if (is_stairs<DGEN>(P, tiles, tB, st >> 16)) {
+            const int nd = depB + 1;
+            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idB, nd, pos & 0xFFFFu, depA, lane);
+            if (!level_exists(P, idB, nd, depA)) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
+            ev.emit(ORX_EV_DESCEND, idB + 1, (r >> 16) & 255u, r >> 24, nd);
+            depB = nd;
+            pos = (pos & 0xFFFFu) | (r & 0xFFFF0000u);
+            st = (st & 0xFFFFu) | (r << 16);
+            ++cnt.descents;
+        } else {
+            ev.emit(ORX_EV_MOVE, idB + 1, tB & 255u, tB >> 8, depB);
+            pos += (uint32_t)dB << 16;
+        }
     }
-    L.p1.mv = m1; L.p1.id = 0; L.p1.dmg = P.dmg0;
-    L.p2.mv = m2; L.p2.id = 1; L.p2.dmg = P.dmg1;
-    // random.shuffle([p1, p2]) (updater.py:114): j = randbelow(2); j == 0 swaps => p2 first
-    const bool p2_first = bounded(w_init, 2u) == 0u;
-    Mover A = pick(p2_first, L.p2, L.p1);
-    Mover B = pick(p2_first, L.p1, L.p2);
-    do_move<DGEN, NPC, EV, 0>(P, tiles, A, B, s, L.tick, lane, ev, cnt);
-    do_move<DGEN, NPC, EV, 1>(P, tiles, B, A, s, L.tick, lane, ev, cnt);
-    L.p1 = pick(p2_first, B, A);
-    L.p2 = pick(p2_first, A, B);
+    // ---- back to player order
+    L.pos = __byte_perm(pos, 0u, sel);
+    L.st = __byte_perm(st, 0u, sel);
+    L.d1 = p2_first ? depB : depA; L.d2 = p2_first ? depA : depB;
+    L.hp1 = p2_first ? hpB : hpA; L.hp2 = p2_first ? hpA : hpB;
     if (NPC) {   // dead NPCs leave in reverse entity order (updater.py:137-145)
         for (int k = P.n_npc - 1; k >= 0; --k) {
-            const long long j = lane * P.n_npc + k;
+            const size_t j = (size_t)lane * P.n_npc + k;
             if (P.npc_depth[j] >= 0 && P.npc_hp[j] <= 0) {
                 ev.emit(ORX_EV_DEATH, 3 + k, 0, 0, 0);
                 P.npc_depth[j] = -1;
@@ -282,50 +303,50 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
     L.tick += 1;                                                         // updater.py:148
     int res = ORX_RESULT_IN_PROGRESS;
     if (P.max_ticks != 0 && L.tick >= P.max_ticks) res = ORX_RESULT_TIE; // :158
-    if (L.p2.hp <= 0) res = ORX_RESULT_PLAYER1_WIN;                      // :155-157
-    if (L.p1.hp <= 0) res = L.p2.hp <= 0 ? ORX_RESULT_TIE : ORX_RESULT_PLAYER2_WIN;  // :151-154
+    if (L.hp2 <= 0) res = ORX_RESULT_PLAYER1_WIN;                        // :155-157
+    if (L.hp1 <= 0) res = L.hp2 <= 0 ? ORX_RESULT_TIE : ORX_RESULT_PLAYER2_WIN;  // :151-154
     return res;
 }
 
 // Re-initialise a lane for the episode already stored in s.episode.
 template <int DGEN, bool NPC>
-__device__ __forceinline__ void reset_lane(const Params& P, Lane& L, const Stream& s, long long lane)
+__device__ __forceinline__ void reset_lane(const Params& P, Lane& L, const Stream& s, unsigned int lane)
 {
     const uint2 r = reset_draw<DGEN>(P, s);
-    L.p1.x = r.x & 255; L.p1.y = (r.x >> 8) & 255; L.p2.x = (r.x >> 16) & 255; L.p2.y = r.x >> 24;
-    L.p1.sx = r.y & 255; L.p1.sy = (r.y >> 8) & 255; L.p2.sx = (r.y >> 16) & 255; L.p2.sy = r.y >> 24;
-    L.p1.hp = P.hp0; L.p2.hp = P.hp1;
-    L.p1.depth = P.sd0;
-    L.p2.depth = P.start_kind == ORX_START_SEPARATED ? P.sd1 : P.sd0;
+    L.pos = r.x; L.st = r.y;
+    L.hp1 = P.hp0; L.hp2 = P.hp1;
+    L.d1 = P.sd0;
+    L.d2 = P.start_kind == ORX_START_SEPARATED ? P.sd1 : P.sd0;
     L.tick = 1;                                                          // worldgen.py:87
     L.episode = s.episode;
-    if (NPC) for (int k = 0; k < P.n_npc; ++k) P.npc_depth[lane * P.n_npc + k] = -1;
+    if (NPC) for (int k = 0; k < P.n_npc; ++k) P.npc_depth[(size_t)lane * P.n_npc + k] = -1;
 }
 
-__device__ __forceinline__ void load_lane(const Params& P, long long i, Lane& L)
+__device__ __forceinline__ void unpack_lane(Lane& L, uint32_t pos, uint32_t hp, int2 d, uint32_t st, int tick, uint32_t ep)
 {
-    const uint32_t pos = P.pos[i], hp = P.hp[i], st = P.stairs[i];
-    const int2 d = P.depth[i];
-    L.p1.x = pos & 255; L.p1.y = (pos >> 8) & 255; L.p2.x = (pos >> 16) & 255; L.p2.y = pos >> 24;
-    L.p1.hp = (int)(int16_t)(hp & 0xFFFF); L.p2.hp = (int)(int16_t)(hp >> 16);
-    L.p1.depth = d.x; L.p2.depth = d.y;
-    L.p1.sx = st & 255; L.p1.sy = (st >> 8) & 255; L.p2.sx = (st >> 16) & 255; L.p2.sy = st >> 24;
-    L.tick = P.tick[i];
-    L.episode = P.episode[i];
+    L.pos = pos; L.st = st;
+    L.hp1 = (int)(int16_t)(hp & 0xFFFFu); L.hp2 = (int)hp >> 16;
+    L.d1 = d.x; L.d2 = d.y;
+    L.tick = tick; L.episode = ep;
 }
 
-__device__ __forceinline__ void store_lane(const Params& P, long long i, const Lane& L, int status)
+__device__ __forceinline__ void load_lane(const Params& P, unsigned int i, Lane& L)
 {
-    P.pos[i] = (uint32_t)L.p1.x | ((uint32_t)L.p1.y << 8) | ((uint32_t)L.p2.x << 16) | ((uint32_t)L.p2.y << 24);
-    P.hp[i] = ((uint32_t)L.p1.hp & 0xFFFFu) | ((uint32_t)L.p2.hp << 16);
-    P.depth[i] = make_int2(L.p1.depth, L.p2.depth);
-    P.stairs[i] = (uint32_t)L.p1.sx | ((uint32_t)L.p1.sy << 8) | ((uint32_t)L.p2.sx << 16) | ((uint32_t)L.p2.sy << 24);
+    unpack_lane(L, P.pos[i], P.hp[i], P.depth[i], P.stairs[i], P.tick[i], P.episode[i]);
+}
+
+__device__ __forceinline__ void store_lane(const Params& P, unsigned int i, const Lane& L, int status)
+{
+    P.pos[i] = L.pos;
+    P.hp[i] = ((uint32_t)L.hp1 & 0xFFFFu) | ((uint32_t)L.hp2 << 16);
+    P.depth[i] = make_int2(L.d1, L.d2);
+    P.stairs[i] = L.st;
     P.tick[i] = L.tick;
     P.episode[i] = L.episode;
     P.status[i] = (uint8_t)status;
 }
 
-__device__ __forceinline__ Stream make_stream(const Params& P, long long i, uint32_t episode)
+__device__ __forceinline__ Stream make_stream(const Params& P, unsigned int i, uint32_t episode)
 {
     const unsigned long long gid = P.gid_base + (unsigned long long)i;
     Stream s;
@@ -333,12 +354,13 @@ __device__ __forceinline__ Stream make_stream(const Params& P, long long i, uint
     return s;
 }
 
-// randombot.py:20-21 / staircasebot.py:9-20. w is this player's word of the tick's main block.
-__device__ __forceinline__ int bot_move(int kind, const Mover& m, uint32_t w)
+// randombot.py:20-21 / staircasebot.py:9-20. w is this player's word of the tick's main block;
+// xy / sxy are the player's packed position and its level's staircase.
+__device__ __forceinline__ uint32_t bot_move(int kind, uint32_t xy, uint32_t sxy, uint32_t w)
 {
-    if (kind == ORX_BOT_RANDOM) return 1 + (int)bounded(w, 5u);
+    if (kind == ORX_BOT_RANDOM) return 1u + bounded(w, 5u);
     if (kind == ORX_BOT_STAIRCASE) {
-        const int dx = m.sx - m.x, dy = m.sy - m.y;
+        const int dx = (int)(sxy & 255u) - (int)(xy & 255u), dy = (int)(sxy >> 8) - (int)(xy >> 8);
         if (abs(dx) > abs(dy)) return dx > 0 ? ORX_MOVE_RIGHT : ORX_MOVE_LEFT;
         return dy > 0 ? ORX_MOVE_DOWN : ORX_MOVE_UP;
     }

@@ -255,7 +255,7 @@ def snapshot(gs, result, events):
 def play_episode(seed, game_id, episode=0, *, bots=('random', 'random'), width=60, height=10,
                  start='together', p_depths=(0, 1000), despawn='unreachable', max_ticks=512,
                  fixed_tiles=None, npcs=(), scripts=None, limit_ticks=None,
-                 hp=10, damage=2, armor=1, want_order=False):
+                 hp=10, damage=2, armor=1, want_order=False, place=None):
     """Plays one episode on the live reference under injected draws.
 
     Returns the list of records: record 0 is the post-reset state, record t>0 the
@@ -277,10 +277,14 @@ def play_episode(seed, game_id, episode=0, *, bots=('random', 'random'), width=6
         inj.site, inj.q = ('reset',), 0
         gs = gen.setup_game()
         inj.site = None
-        if (hp, damage, armor) != (10, 2, 1):
-            for ent in (gs.player_1, gs.player_2):
-                ent.health, ent.base_max_health = hp, hp
-                ent.base_damage, ent.base_armor = damage, armor
+        hp2, dmg2, arm2 = (v if isinstance(v, (tuple, list)) else (v, v) for v in (hp, damage, armor))
+        for k, ent in enumerate((gs.player_1, gs.player_2)):
+            ent.health, ent.base_max_health = hp2[k], hp2[k]
+            ent.base_damage, ent.base_armor = dmg2[k], arm2[k]
+        if place is not None:
+            for ent, (px_, py_) in zip((gs.player_1, gs.player_2), place):
+                ent.x, ent.y = int(px_), int(py_)
+            gs.pos_lookup = dict(((e.depth, e.x, e.y), e) for e in gs.entities)
         for k, (nd, nx, ny, nhp) in enumerate(npcs):
             gs.add_entity(ref.entities.Entity(3 + k, nd, nx, ny, nhp, nhp, 0, 0, [], dict()))
         strat = (ref.updater.DungeonDespawningStrategy.Unreachable if despawn == 'unreachable'

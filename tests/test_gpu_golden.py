@@ -1,0 +1,56 @@
+"""-m gpu: the CUDA path against the fixtures generated from the LIVE reference
+(oracle/gen_golden.py): 2 x 10k replayed episodes, every tick folded into a digest that covers
+(x, y, depth, health) x 2, tick, result, the staircases and the ordered event records."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from optimax_rogue_b200 import SimConfig
+from optimax_rogue_b200.game.state import BatchedGameState
+from optimax_rogue_b200.logic.updater import BatchedUpdater, reset_games
+from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
+
+import trace_util as tu
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.mark.parametrize('suite', ['stair_vs_random', 'random_vs_random'])
+@pytest.mark.parametrize('fused_bots', [False, True])
+def test_ten_thousand_replayed_episodes_bit_exact(suite, fused_bots):
+    meta = json.load(open(os.path.join(GOLD, 'digests_meta.json')))
+    want = np.load(os.path.join(GOLD, f'digests_{suite}.npy'))
+    kw = meta['suites'][suite]
+    n = len(want)
+    cfg = SimConfig(max_ticks=kw['max_ticks'], seed=meta['seed'])
+    gs = BatchedGameState(cfg, n, 'cuda')
+    reset_games(gs)
+    upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, kw['max_ticks'])
+    bots = [tu.BOT_CODES[b] for b in kw['bots']]
+    dg = tu.BatchDigest(n)
+    active = np.ones(n, bool)
+    p = gs.planes_cpu()
+    dg.update(p['pos'], p['hp'], p['depth'], p['stairs'], p['tick'], p['status'], None, active)
+    moves = torch.full((n, 2), 5, dtype=torch.uint8, device='cuda')
+    for _ in range(kw['max_ticks']):
+        if fused_bots:
+            upd.bot_moves(gs, bots[0], bots[1], out=moves)
+        else:   # one launch per player, as two independent Bot objects would do
+            upd.bot_moves(gs, bots[0], 0, out=moves)
+            upd.bot_moves(gs, 0, bots[1], out=moves)
+        res, ev = upd.update(gs, moves, want_events=True)
+        p = gs.planes_cpu()
+        r = res.cpu().numpy()
+        dg.update(p['pos'], p['hp'], p['depth'], p['stairs'], p['tick'], r, ev.cpu().numpy(), active)
+        active &= r == 1
+        if not active.any():
+            break
+    assert not active.any()
+    bad = np.flatnonzero(dg.h != want)
+    assert len(bad) == 0, f'{len(bad)} of {n} episodes differ from the reference, first {bad[:5]}'
+    hist = {str(k): int((p['status'] == k).sum()) for k in (2, 3, 4)}
+    assert hist == kw['result_hist']

@@ -169,12 +169,12 @@ def test_observe():
         assert np.array_equal(obs[:, pl, 3], p['hp'][:, pl])
         same = p['depth'][:, 0] == p['depth'][:, 1]
         assert np.array_equal(obs[:, pl, 4], same.astype(np.int16))
-        assert np.array_equal(obs[:, pl, 5], np.where(same, p['pos'][:, 2 * o], -1))
+        assert np.array_equal(obs[:, pl, 5], np.where(same, p['pos'][:, 2 * o].astype(int), -1))
         cheb = np.maximum(np.abs(p['stairs'][:, 2 * pl].astype(int) - p['pos'][:, 2 * pl]),
                           np.abs(p['stairs'][:, 2 * pl + 1].astype(int) - p['pos'][:, 2 * pl + 1]))
         vis = cheb <= 3
         assert np.array_equal(obs[:, pl, 8], vis.astype(np.int16))
-        assert np.array_equal(obs[:, pl, 9], np.where(vis, p['stairs'][:, 2 * pl], -1))
+        assert np.array_equal(obs[:, pl, 9], np.where(vis, p['stairs'][:, 2 * pl].astype(int), -1))
         assert np.array_equal(obs[:, pl, 11], p['tick'])
 
 

@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference interface: configuration errors, enums, wire formats, event
+decoding. No GPU."""
+import numpy as np
+import pytest
+
+from oracle import ref_harness as rh
+from optimax_rogue_b200 import SimConfig, _abi
+from optimax_rogue_b200.game.state import GameState, empty_room_tiles
+from optimax_rogue_b200.game.entities import Entity
+from optimax_rogue_b200.game.world import Dungeon, Tile, World
+from optimax_rogue_b200.logic import updates
+from optimax_rogue_b200.logic.moves import Move
+from optimax_rogue_b200.logic.updater import BatchedUpdater, DungeonDespawningStrategy, UpdateResult
+from optimax_rogue_b200.logic.worldgen import (EmptyDungeonGenerator, FixedDungeonGenerator,
+                                               SeparatedGameStartGenerator, TogetherGameStartGenerator)
+
+
+def test_enum_codes_are_the_references():
+    assert [m.value for m in Move] == [1, 2, 3, 4, 5] and Move.Stay == 5          # logic/moves.py:6-12
+    assert [r.value for r in UpdateResult] == [1, 2, 3, 4]                          # updater.py:16-21
+    assert [t.value for t in Tile] == [1, 2, 3]                                     # world.py:10-17
+    assert DungeonDespawningStrategy.Unreachable == 1 and DungeonDespawningStrategy.Unused == 2
+
+
+@pytest.mark.skipif(not rh.reference_available(), reason='reference tree not present')
+def test_enum_codes_against_live_reference():
+    ref = rh.load_reference()
+    assert {m.name: m.value for m in Move} == {m.name: m.value for m in ref.moves.Move}
+    assert {m.name: m.value for m in UpdateResult} == {m.name: m.value for m in ref.updater.UpdateResult}
+    assert {m.name: m.value for m in Tile} == {m.name: m.value for m in ref.world.Tile}
+    assert {m.name: m.value for m in DungeonDespawningStrategy} == \
+        {m.name: m.value for m in ref.updater.DungeonDespawningStrategy}
+    import optimax_rogue.game.modifiers as mods
+    assert (mods.CombatFlag.Block, mods.CombatFlag.Ambush, mods.CombatFlag.Flee, mods.CombatFlag.Parry) == (1, 2, 3, 4)
+
+
+def test_config_validation_errors():
+    with pytest.raises(ValueError):
+        SimConfig(width=3).validate()
+    with pytest.raises(ValueError):
+        SimConfig(height=300).validate()
+    with pytest.raises(ValueError):
+        SimConfig(n_npc=9).validate()
+    with pytest.raises(ValueError, match='Unknown despawn strat'):
+        SimConfig(despawn_strat=3).validate()
+    with pytest.raises(ValueError, match='cannot use SeparatedGameStartGenerator'):
+        SeparatedGameStartGenerator(EmptyDungeonGenerator(60, 10), 4, 4)          # worldgen.py:112-114
+    with pytest.raises(ValueError):
+        SimConfig(dgen_kind=_abi.DGEN_FIXED, fixed_tiles=np.ones((5, 5), np.uint8)).validate()
+    with pytest.raises(ValueError, match='Unknown despawn strat'):
+        BatchedUpdater(EmptyDungeonGenerator(60, 10), 7)
+
+
+def test_generators_carry_reference_defaults():
+    gen = TogetherGameStartGenerator()
+    cfg = gen.sim_config(seed=5)
+    assert (cfg.width, cfg.height) == (60, 10)                                      # worldgen.py:67
+    assert cfg.hp == (10, 10) and cfg.damage == (2, 2) and cfg.armor == (1, 1)      # worldgen.py:85-86
+    sep = SeparatedGameStartGenerator()
+    assert sep.sim_config().start_depth == (0, 1000)                                # worldgen.py:110-111
+    fx = FixedDungeonGenerator(np.full((7, 5), 1, np.uint8))
+    assert (fx.width, fx.height) == (7, 5)
+
+
+def test_fixed_tables_rank_order_is_x_major():
+    t = np.full((5, 4), 2, np.uint8)
+    t[1, 1] = t[1, 2] = t[3, 1] = 1
+    t[2, 2] = 3
+    cfg = SimConfig(width=5, height=4, dgen_kind=_abi.DGEN_FIXED, fixed_tiles=t)
+    flat, ground, stairs = cfg.fixed_tables()
+    assert ground.tolist() == [1 * 4 + 1, 1 * 4 + 2, 3 * 4 + 1]                     # world.py:60 flat = x*H + y
+    assert stairs == (2, 2)
+    assert flat[2 * 4 + 2] == 3
+
+
+def test_dungeon_and_world_wire_format_roundtrip():
+    tiles = empty_room_tiles(6, 5, (2, 3))
+    d = Dungeon(tiles)
+    raw = d.to_prims()
+    assert raw[:8] == (6).to_bytes(4, 'big') + (5).to_bytes(4, 'big')               # world.py:76-77
+    assert raw[8:] == tiles.astype('uint8').tobytes()
+    assert Dungeon.from_prims(raw) == d
+    assert d.staircase() == (2, 3) and d.is_blocked(0, 0) and d.is_blocked(-1, 2) and not d.is_blocked(2, 3)
+    w = World({0: d, 7: Dungeon(empty_room_tiles(6, 5, (1, 1)))})
+    assert World.from_prims(w.to_prims()) == w
+
+
+@pytest.mark.skipif(not rh.reference_available(), reason='reference tree not present')
+def test_wire_format_is_byte_identical_to_reference():
+    ref = rh.load_reference()
+    tiles = empty_room_tiles(60, 10, (17, 4))
+    ours = World({0: Dungeon(tiles), 3: Dungeon(empty_room_tiles(60, 10, (2, 2)))})
+    theirs = ref.world.World({0: ref.world.Dungeon(tiles.copy()), 3: ref.world.Dungeon(empty_room_tiles(60, 10, (2, 2)))})
+    assert ours.to_prims() == theirs.to_prims()
+    back = ref.world.World.from_prims(ours.to_prims())
+    assert back == theirs
+
+
+def test_game_state_view_for_filters_by_depth():
+    d0, d1 = Dungeon(empty_room_tiles(6, 5, (2, 2))), Dungeon(empty_room_tiles(6, 5, (3, 3)))
+    e1, e2 = Entity(1, 0, 1, 1, 10, 10, 2, 1), Entity(2, 1, 2, 2, 10, 10, 2, 1)
+    gs = GameState(True, 5, 1, 2, World({0: d0, 1: d1}), [e1, e2])
+    v = gs.view_for(e1)
+    assert list(v.world.dungeons) == [0] and [e.iden for e in v.entities] == [1] and not v.is_authoritative
+    assert gs.view_for(e2, reduce_tick=True).tick == 4                              # state.py:56
+
+
+def test_event_decoding():
+    def rec(kind, iden, a, b, depth):
+        return [kind | (iden << 8) | (a << 16) | (b << 24), depth]
+    raw = np.array([rec(3, 0, 4, 5, 2), rec(5, 1, 7, 3, 2), rec(2, 2, 1, 3, 1), rec(1, 2, 9, 8, 0), [0, 0]], np.int64).astype(np.int32)
+    un = updates.unpack_events(raw)
+    evs = updates.decode_events(un, first_order=10, width=12, height=9)
+    assert [type(e).__name__ for e in evs] == ['DungeonCreatedUpdate', 'EntityPositionUpdate', 'EntityCombatUpdate', 'EntityPositionUpdate']
+    assert [e.order for e in evs] == [10, 11, 12, 13]
+    assert evs[0].depth == 2 and evs[0].dungeon.staircase() == (4, 5) and evs[0].dungeon.width == 12
+    assert (evs[1].entity_iden, evs[1].depth, evs[1].old_depth, evs[1].posx, evs[1].posy) == (1, 2, 1, 7, 3)
+    assert evs[1].depth_changed and not evs[3].depth_changed
+    assert (evs[2].attacker_iden, evs[2].defender_iden, evs[2].og_damage, evs[2].tags) == (2, 1, 1, {3})

@@ -1,0 +1,76 @@
+"""Pins the C oracle to the LIVE reference (only where /root/reference exists, i.e. the build
+container): same injected draws, every tick compared field by field, events included."""
+import numpy as np
+import pytest
+
+from oracle import ref_harness as rh
+from optimax_rogue_b200 import SimConfig, _abi
+
+import trace_util as tu
+
+pytestmark = pytest.mark.skipif(not rh.reference_available(), reason='reference tree not present')
+
+SEED = 0xBEEF
+
+
+def compare(gid, bots, cfg_kw, ref_kw, npcs=(), episode=0):
+    tr, mv = rh.play_episode(SEED, gid, episode, bots=bots, npcs=npcs, **ref_kw)
+    cfg = SimConfig(seed=SEED, n_npc=len(npcs), **cfg_kw)
+    if episode:
+        pytest.skip('episode offsets are covered by the golden traces')
+    to, mo = tu.oracle_episode(cfg, gid, bots=bots, npcs=npcs)
+    a = [tu.strip(r) for r in tr]
+    assert len(a) == len(to)
+    for i, (x, y) in enumerate(zip(a, to)):
+        assert x == y, f'game {gid} record {i}: reference {x} != oracle {y}'
+    assert mv == mo
+
+
+@pytest.mark.parametrize('bots', [('staircase', 'random'), ('random', 'random'), ('staircase', 'staircase')])
+@pytest.mark.parametrize('despawn', ['unreachable', 'unused'])
+def test_default_room(bots, despawn):
+    for gid in range(100, 106):
+        compare(gid, bots, dict(max_ticks=200, despawn_strat=1 if despawn == 'unreachable' else 2),
+                dict(max_ticks=200, despawn=despawn))
+
+
+def test_small_rooms_and_stats():
+    for gid, (w, h) in enumerate([(4, 4), (5, 5), (4, 9), (7, 4)]):
+        compare(gid, ('random', 'random'),
+                dict(width=w, height=h, max_ticks=150, hp=(3, 5), damage=(3, 2), armor=(1, 0)),
+                dict(width=w, height=h, max_ticks=150, hp=(3, 5), damage=(3, 2), armor=(1, 0)))
+
+
+def test_separated_start():
+    for gid in range(4):
+        compare(gid, ('staircase', 'staircase'),
+                dict(start_kind=_abi.START_SEPARATED, start_depth=(0, 3), max_ticks=200, despawn_strat=1 + gid % 2),
+                dict(start='separated', p_depths=(0, 3), max_ticks=200, despawn=('unreachable', 'unused')[gid % 2]))
+
+
+def test_fixed_map_plugin_generator():
+    from oracle.gen_golden import fixed_map
+    for gid, stairs in enumerate([False, True, True]):
+        tiles = fixed_map(stairs=stairs, seed=gid)
+        compare(gid, ('staircase' if stairs else 'random', 'random'),
+                dict(dgen_kind=_abi.DGEN_FIXED, fixed_tiles=tiles, max_ticks=200),
+                dict(fixed_tiles=tiles.astype('int32'), max_ticks=200))
+
+
+def test_npc_slots():
+    from oracle import cport
+    base = [(0, 3, 3, 2), (0, 5, 2, 1), (1, 2, 2, 3), (0, 2, 4, 1)]
+    for gid in range(6):
+        # an NPC dropped onto a player's spawn tile would corrupt the reference's pos_lookup
+        # (add_entity overwrites the player's key, state.py:78-82): keep the setup legal
+        orc = cport.Oracle(SimConfig(seed=SEED, width=8, height=6, n_npc=4), 1, gid)
+        orc.reset()
+        taken = {(0, int(orc.state.pos[0, 0]), int(orc.state.pos[0, 1])), (0, int(orc.state.pos[0, 2]), int(orc.state.pos[0, 3]))}
+        npcs = []
+        for (d, x, y, hp) in base:
+            while (d, x, y) in taken:
+                x = x % 6 + 1
+            taken.add((d, x, y))
+            npcs.append((d, x, y, hp))
+        compare(gid, ('random', 'staircase'), dict(width=8, height=6, max_ticks=150, hp=(50, 50)),
+                dict(width=8, height=6, max_ticks=150, hp=50), npcs=npcs)
