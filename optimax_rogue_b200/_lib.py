@@ -10,7 +10,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liborx.so')
+LIB_PATH = os.environ.get('ORX_LIB') or os.path.join(_HERE, 'liborx.so')   # ORX_LIB: tuning builds only
 
 
 class OrxError(RuntimeError):

@@ -5,6 +5,7 @@
 
 #include "../../include/orx.h"
 #include "orx_rules.cuh"
+#include "orx_pipe.cuh"
 
 using namespace orx;
 
@@ -222,6 +223,11 @@ k_observe(const __grid_constant__ Params P, int16_t* __restrict__ obs, int radiu
 // ------------------------------------------------------------------ host side
 int cuda_fail(cudaError_t e) { return ORX_ERR_CUDA_BASE - (int)e; }
 
+int launch_done() {
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? ORX_OK : cuda_fail(e);
+}
+
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 int check_common(const OrxConfig* cfg, const OrxState* st, int64_t n)
@@ -286,9 +292,38 @@ int dispatch_dgen_npc(const OrxConfig* c, F&& f)
     return npc ? f.template operator()<ORX_DGEN_FIXED, true>() : f.template operator()<ORX_DGEN_FIXED, false>();
 }
 
-int launch_done() {
-    const cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? ORX_OK : cuda_fail(e);
+
+bool pipe_aligned(const OrxState* st, const void* moves, const void* result)
+{
+    return aligned(st->pos, 16) && aligned(st->hp, 16) && aligned(st->depth, 16) && aligned(st->stairs, 16) &&
+           aligned(st->tick, 16) && aligned(st->episode, 16) && aligned(st->status, 16) && aligned(moves, 16) &&
+           aligned(result, 16);
+}
+
+Params offset_params(const Params& P, int64_t off, int64_t n)
+{
+    Params T = P;
+    T.pos += off; T.hp += off; T.depth += off; T.stairs += off; T.tick += off; T.episode += off; T.status += off;
+    T.n = (unsigned int)n; T.gid_base = P.gid_base + (unsigned long long)off;
+    return T;
+}
+
+template <int DGEN>
+int launch_pipe(const Params& P, const uint16_t* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, cudaStream_t s)
+{
+    const size_t smem = pipe_smem_bytes((int)tiles_bytes);
+    int dev = 0, sms = 148, per_sm = 2;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(k_step_pipe<DGEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_pipe<DGEN>, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    unsigned int grid = (unsigned int)sms * (unsigned int)per_sm;       // persistent: every CTA resident
+    if (grid > n_tiles) grid = n_tiles;
+    k_step_pipe<DGEN><<<grid, kPipeThreads, smem, s>>>(P, mv, result, n_tiles);
+    return launch_done();
 }
 
 }  // namespace
@@ -342,11 +377,25 @@ int orx_step(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uin
     if (n == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, game_id_base);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    const int grid = grid_for(n);
     const size_t smem = tiles_smem(cfg);
     const uint16_t* mv = reinterpret_cast<const uint16_t*>(moves);
     uint2* ev = reinterpret_cast<uint2*>(events);
     const int max_ev = orx_max_events(cfg);
+    // Hot variant (no NPC slots, no event log): persistent TMA-pipelined kernel over the full
+    // 256-game tiles, the simple kernel for a ragged tail (< 256 games).
+    if (ev == nullptr && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
+        const unsigned int n_tiles = (unsigned int)(n / kTile);
+        const int64_t n_body = (int64_t)n_tiles * kTile;
+        int rc2 = cfg->dgen_kind == ORX_DGEN_EMPTY ? launch_pipe<ORX_DGEN_EMPTY>(P, mv, result, n_tiles, 0, s)
+                                                   : launch_pipe<ORX_DGEN_FIXED>(P, mv, result, n_tiles, smem, s);
+        if (rc2 != ORX_OK || n_body == n) return rc2;
+        const Params T = offset_params(P, n_body, n - n_body);
+        const int tgrid = grid_for(n - n_body);
+        if (cfg->dgen_kind == ORX_DGEN_EMPTY) k_step<ORX_DGEN_EMPTY, false, false><<<tgrid, kThreads, 0, s>>>(T, mv + n_body, result + n_body, nullptr, max_ev);
+        else k_step<ORX_DGEN_FIXED, false, false><<<tgrid, kThreads, smem, s>>>(T, mv + n_body, result + n_body, nullptr, max_ev);
+        return launch_done();
+    }
+    const int grid = grid_for(n);
     return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
         if (ev != nullptr) k_step<DGEN, NPC, true><<<grid, kThreads, smem, s>>>(P, mv, result, ev, max_ev);
         else k_step<DGEN, NPC, false><<<grid, kThreads, smem, s>>>(P, mv, result, nullptr, max_ev);

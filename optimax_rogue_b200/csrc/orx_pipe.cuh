@@ -1,0 +1,202 @@
+// Persistent, TMA-fed version of the tick kernel (the hot variant: no NPC slots, no event log).
+//
+// A CTA owns a strided set of 256-game tiles. One producer thread streams each tile's eight
+// plane slices HBM -> shared memory with 1-D bulk copies (cp.async.bulk, completion on an
+// mbarrier), kStages tiles ahead of the eight compute warps; the compute warps pull their game
+// into registers, run tick_lane, write the new planes back into the same stage, and the producer
+// streams the stage shared memory -> HBM with bulk stores before refilling it. Loads therefore
+// stay in flight for the whole life of the CTA instead of only at the start of each thread, and
+// no thread does per-plane 64-bit address arithmetic.
+//
+// Stage life cycle (stage s, tiles s, s+kStages, ...):
+//   producer: wait_group.read (previous bulk stores have drained the stage) -> expect_tx(full[s])
+//             -> 8 bulk loads
+//   consumer: wait full[s] -> smem -> registers -> tick -> registers -> smem (in place)
+//             -> fence.proxy.async -> one arrive per warp on done[s]
+//   producer: wait done[s] -> 8 bulk stores + commit_group
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "orx_rules.cuh"
+
+namespace orx {
+
+constexpr int kTile = 256;            // games per tile = compute threads per CTA
+#ifndef ORX_PIPE_STAGES
+#define ORX_PIPE_STAGES 4
+#endif
+#ifndef ORX_PIPE_MINBLOCKS
+#define ORX_PIPE_MINBLOCKS 4
+#endif
+constexpr int kStages = ORX_PIPE_STAGES;
+constexpr int kPipeThreads = kTile + 32;   // + one producer warp
+
+// byte offsets of the plane slices inside a stage (all multiples of 16)
+constexpr uint32_t OFF_POS = 0, OFF_HP = 1024, OFF_ST = 2048, OFF_TICK = 3072, OFF_EP = 4096,
+                   OFF_DEPTH = 5120, OFF_STATUS = 7168, OFF_MOVES = 7424, OFF_RESULT = 7936,
+                   STAGE_BYTES = 8192;
+constexpr uint32_t LOAD_BYTES = 5 * 1024 + 2048 + 256 + 512;   // per tile, HBM -> smem
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ORX_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ORX_DONE;\n"
+        "bra ORX_WAIT;\n"
+        "ORX_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// n_tiles full tiles of kTile games; the caller handles a ragged tail with the simple kernel.
+template <int DGEN>
+__global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
+k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result,
+            unsigned int n_tiles)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* stages = smem;                                             // kStages * STAGE_BYTES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);   // full[kStages], done[kStages]
+    uint8_t* tiles_sm = smem + kStages * STAGE_BYTES + 2 * kStages * 8;
+    const uint32_t full0 = smem_addr(bars), done0 = smem_addr(bars + kStages);
+    const uint32_t stage0 = smem_addr(stages);
+    const unsigned int tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(done0 + 8 * s, kTile / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint8_t* tiles = nullptr;
+    if (DGEN == ORX_DGEN_FIXED) {
+        const int nt = P.W * P.H;
+        for (int t = tid; t < nt; t += kPipeThreads) tiles_sm[t] = P.tiles[t];
+        tiles = tiles_sm;
+    }
+    __syncthreads();
+
+    // tiles of this CTA: blockIdx.x, + gridDim.x, ...
+    const unsigned int my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid >= kTile) {
+        // ------------------------------------------------------------ producer (one thread)
+        if (tid != kTile) return;
+        auto issue_loads = [&](unsigned int it) {
+            const unsigned int s = it % kStages;
+            const size_t g = ((size_t)blockIdx.x + (size_t)it * gridDim.x) * kTile;     // first game of the tile
+            const uint32_t bar = full0 + 8 * s, base = stage0 + s * STAGE_BYTES;
+            mbar_expect_tx(bar, LOAD_BYTES);
+            bulk_load(base + OFF_POS, P.pos + g, 1024, bar);
+            bulk_load(base + OFF_HP, P.hp + g, 1024, bar);
+            bulk_load(base + OFF_ST, P.stairs + g, 1024, bar);
+            bulk_load(base + OFF_TICK, P.tick + g, 1024, bar);
+            bulk_load(base + OFF_EP, P.episode + g, 1024, bar);
+            bulk_load(base + OFF_DEPTH, P.depth + g, 2048, bar);
+            bulk_load(base + OFF_STATUS, P.status + g, 256, bar);
+            bulk_load(base + OFF_MOVES, moves + g, 512, bar);
+        };
+        const unsigned int pre = my_tiles < (unsigned)kStages ? my_tiles : (unsigned)kStages;
+        for (unsigned int it = 0; it < pre; ++it) issue_loads(it);
+        for (unsigned int it = 0; it < my_tiles; ++it) {
+            const unsigned int s = it % kStages;
+            mbar_wait(done0 + 8 * s, (it / kStages) & 1u);
+            const size_t g = ((size_t)blockIdx.x + (size_t)it * gridDim.x) * kTile;
+            const uint32_t base = stage0 + s * STAGE_BYTES;
+            bulk_store(P.pos + g, base + OFF_POS, 1024);
+            bulk_store(P.hp + g, base + OFF_HP, 1024);
+            bulk_store(P.stairs + g, base + OFF_ST, 1024);
+            bulk_store(P.tick + g, base + OFF_TICK, 1024);
+            bulk_store(P.episode + g, base + OFF_EP, 1024);
+            bulk_store(P.depth + g, base + OFF_DEPTH, 2048);
+            bulk_store(P.status + g, base + OFF_STATUS, 256);
+            bulk_store(result + g, base + OFF_RESULT, 256);
+            bulk_commit();
+            if (it + kStages < my_tiles) {
+                bulk_wait_read_all();              // the stage has been read out: safe to overwrite
+                issue_loads(it + kStages);
+            }
+        }
+        bulk_wait_all();
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers (8 warps)
+    for (unsigned int it = 0; it < my_tiles; ++it) {
+        const unsigned int s = it % kStages;
+        uint8_t* st = stages + s * STAGE_BYTES;
+        mbar_wait(full0 + 8 * s, (it / kStages) & 1u);
+        const uint32_t pos = reinterpret_cast<const uint32_t*>(st + OFF_POS)[tid];
+        const uint32_t hpw = reinterpret_cast<const uint32_t*>(st + OFF_HP)[tid];
+        const uint32_t stw = reinterpret_cast<const uint32_t*>(st + OFF_ST)[tid];
+        const int tick = reinterpret_cast<const int*>(st + OFF_TICK)[tid];
+        const uint32_t ep = reinterpret_cast<const uint32_t*>(st + OFF_EP)[tid];
+        const int2 dep = reinterpret_cast<const int2*>(st + OFF_DEPTH)[tid];
+        const int status = st[OFF_STATUS + tid];
+        const uint32_t mv = reinterpret_cast<const uint16_t*>(st + OFF_MOVES)[tid];
+        const unsigned int lane = (blockIdx.x + it * gridDim.x) * kTile + tid;      // game index in the launch
+        int res = status;
+        if (status == ORX_RESULT_IN_PROGRESS) {          // finished lanes are frozen until reset
+            Lane L;
+            unpack_lane(L, pos, hpw, dep, stw, tick, ep);
+            Stream rs = make_stream(P, lane, ep);
+            const uint4 blk = draw_block(rs, DOM_TICK, SUB_MAIN, (uint32_t)tick);
+            Counters cnt{};
+            EvSink<false> ev{nullptr, 0, 0};
+            res = tick_lane<DGEN, false, false>(P, tiles, L, mv, blk.z, rs, lane, ev, cnt);
+            int new_status = res;
+            if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
+                rs.episode += 1;
+                reset_lane<DGEN, false>(P, L, rs, lane);
+                new_status = ORX_RESULT_IN_PROGRESS;
+            }
+            reinterpret_cast<uint32_t*>(st + OFF_POS)[tid] = L.pos;
+            reinterpret_cast<uint32_t*>(st + OFF_HP)[tid] = ((uint32_t)L.hp1 & 0xFFFFu) | ((uint32_t)L.hp2 << 16);
+            reinterpret_cast<uint32_t*>(st + OFF_ST)[tid] = L.st;
+            reinterpret_cast<int*>(st + OFF_TICK)[tid] = L.tick;
+            reinterpret_cast<uint32_t*>(st + OFF_EP)[tid] = L.episode;
+            reinterpret_cast<int2*>(st + OFF_DEPTH)[tid] = make_int2(L.d1, L.d2);
+            st[OFF_STATUS + tid] = (uint8_t)new_status;
+        }
+        st[OFF_RESULT + tid] = (uint8_t)res;
+        fence_proxy_async();                 // generic-proxy writes -> visible to the bulk-store engine
+        __syncwarp();
+        if ((tid & 31u) == 0) mbar_arrive(done0 + 8 * s);
+    }
+}
+
+constexpr size_t pipe_smem_bytes(int fixed_tiles) { return (size_t)kStages * STAGE_BYTES + 2 * kStages * 8 + (size_t)fixed_tiles; }
+
+}  // namespace orx

@@ -1,0 +1,51 @@
+"""Kernel micro-benchmark used while tuning: k_step alone over rotating batches (> L2), CUDA graph,
+CUDA events. Not the judged benchmark (that is bench.py)."""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from optimax_rogue_b200 import SimConfig
+from optimax_rogue_b200.game.state import BatchedGameState
+from optimax_rogue_b200.logic.updater import BatchedUpdater, reset_games
+from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--games', type=int, nargs='+', default=[1 << 20])
+ap.add_argument('--steps', type=int, default=200)
+ap.add_argument('--reps', type=int, default=3)
+args = ap.parse_args()
+dev = torch.device('cuda')
+for G in args.games:
+    cfg = SimConfig(max_ticks=1000, seed=1, auto_reset=True)
+    nb = max(2, min(64, -(-300_000_000 // (32 * G))))
+    upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, 1000, auto_reset=True)
+    batches = []
+    for b in range(nb):
+        gs = BatchedGameState(cfg, G, dev, game_id_base=b * G)
+        reset_games(gs)
+        upd.rollout(gs, 1, 1, 17 * (b + 1))
+        batches.append(gs)
+    moves = torch.randint(1, 6, (8, G, 2), dtype=torch.uint8, device=dev)
+    res = [torch.empty((G,), dtype=torch.uint8, device=dev) for _ in range(nb)]
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for k in range(4):
+            upd.update(batches[k % nb], moves[k % 8], out=res[k % nb])
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for k in range(args.steps):
+                upd.update(batches[k % nb], moves[k % 8], out=res[k % nb])
+        g.replay()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(args.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st); g.replay(); e1.record(st)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / args.steps)
+    print(f'games={G} batches={nb} us/step={best * 1e3:.2f} ticks/s={G / best * 1e3:.3e} GB/s(61B)={61 * G / best / 1e6:.0f}', flush=True)
