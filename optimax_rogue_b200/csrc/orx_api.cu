@@ -58,8 +58,11 @@ k_step(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, uin
        uint2* __restrict__ events, int max_ev)
 {
     extern __shared__ uint8_t smem[];
+    __shared__ CmdEntry lut[256];
+    build_cmd_lut(P, lut, threadIdx.x, kThreads);
     const uint8_t* tiles = nullptr;
     if (DGEN == ORX_DGEN_FIXED) tiles = stage_tiles(P, smem);
+    else __syncthreads();
     const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= P.n) return;
     // Eight independent loads in flight per thread before the first use (asm volatile keeps ptxas
@@ -81,7 +84,7 @@ k_step(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, uin
     Stream s = make_stream(P, i, ep);
     const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)tick);
     Counters cnt{};
-    int res = tick_lane<DGEN, NPC, EV>(P, tiles, L, mv, blk.z, s, i, ev, cnt);
+    int res = tick_lane<DGEN, NPC, EV>(P, tiles, lut, L, mv, blk.z, s, i, ev, cnt);
     ev.finish();
     result[i] = (uint8_t)res;
     if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
@@ -143,6 +146,8 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
     const uint8_t* tiles = nullptr;
     if (DGEN == ORX_DGEN_FIXED) tiles = stage_tiles(P, smem);
     __shared__ unsigned int s_cnt[7];
+    __shared__ CmdEntry lut[256];
+    build_cmd_lut(P, lut, threadIdx.x, kThreads);
     if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     Counters cnt{};
@@ -158,7 +163,7 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
                 const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
                 const uint32_t m1 = bot_move(bot1, L.pos & 0xFFFFu, L.st & 0xFFFFu, blk.x);
                 const uint32_t m2 = bot_move(bot2, L.pos >> 16, L.st >> 16, blk.y);
-                const int res = tick_lane<DGEN, NPC, false>(P, tiles, L, m1 | (m2 << 8), blk.z, s, i, ev, cnt);
+                const int res = tick_lane<DGEN, NPC, false>(P, tiles, lut, L, m1 | (m2 << 8), blk.z, s, i, ev, cnt);
                 ++cnt.ticks;
                 if (res != ORX_RESULT_IN_PROGRESS) {
                     cnt.p1 += res == ORX_RESULT_PLAYER1_WIN;
@@ -266,15 +271,13 @@ Params make_params(const OrxConfig* c, const OrxState* st, int64_t n, uint64_t g
     P.hp0 = c->hp[0]; P.hp1 = c->hp[1];
     P.dmg0 = c->damage[0] - c->armor[0]; P.dmg1 = c->damage[1] - c->armor[1];
     P.auto_reset = c->auto_reset; P.n_npc = c->n_npc;
-    P.k0 = (uint32_t)c->seed; P.k1 = (uint32_t)(c->seed >> 32);
+    make_round_keys(P.rk, (uint32_t)c->seed, (uint32_t)(c->seed >> 32));
     P.tiles = c->fixed_tiles; P.ground = c->fixed_ground; P.n_ground = c->fixed_n_ground;
     P.fsx = c->fixed_stairs[0]; P.fsy = c->fixed_stairs[1];
     P.pos = reinterpret_cast<uint32_t*>(st->pos); P.hp = reinterpret_cast<uint32_t*>(st->hp);
     P.depth = reinterpret_cast<int2*>(st->depth); P.stairs = reinterpret_cast<uint32_t*>(st->stairs);
     P.tick = st->tick; P.episode = st->episode; P.status = st->status;
     P.npc_pos = st->npc_pos; P.npc_hp = st->npc_hp; P.npc_depth = st->npc_depth;
-    P.lim_lo = 0xFFu | (1u << 8) | ((uint32_t)(c->width - 2) << 16) | ((uint32_t)(c->height - 2) << 24);
-    P.lim_hi = 1u | 0xFFFFFF00u;
     P.n = (unsigned int)n; P.gid_base = gid_base;
     return P;
 }
@@ -322,8 +325,14 @@ int launch_pipe(const Params& P, const uint16_t* mv, uint8_t* result, unsigned i
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_pipe<DGEN>, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     unsigned int grid = (unsigned int)sms * (unsigned int)per_sm;       // persistent: every CTA resident
     if (grid > n_tiles) grid = n_tiles;
-    k_step_pipe<DGEN><<<grid, kPipeThreads, smem, s>>>(P, mv, result, n_tiles);
-    return launch_done();
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kPipeThreads); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL, see k_step_pipe
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = ORX_PIPE_PDL ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&lc, k_step_pipe<DGEN>, P, mv, result, n_tiles);
+    return e == cudaSuccess ? launch_done() : cuda_fail(e);
 }
 
 }  // namespace

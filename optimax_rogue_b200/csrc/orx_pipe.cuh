@@ -27,7 +27,10 @@ constexpr int kTile = 256;            // games per tile = compute threads per CT
 #define ORX_PIPE_STAGES 4
 #endif
 #ifndef ORX_PIPE_MINBLOCKS
-#define ORX_PIPE_MINBLOCKS 4
+#define ORX_PIPE_MINBLOCKS 3
+#endif
+#ifndef ORX_PIPE_PDL
+#define ORX_PIPE_PDL 1
 #endif
 constexpr int kStages = ORX_PIPE_STAGES;
 constexpr int kPipeThreads = kTile + 32;   // + one producer warp
@@ -92,6 +95,10 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
     const uint32_t full0 = smem_addr(bars), done0 = smem_addr(bars + kStages);
     const uint32_t stage0 = smem_addr(stages);
     const unsigned int tid = threadIdx.x;
+    // Programmatic dependent launch: the next kernel in the stream may begin its prologue (barrier
+    // init, map staging) while this grid is still running; its producer waits for this grid to
+    // complete (griddepcontrol.wait) before it touches any plane.
+    if (ORX_PIPE_PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -100,6 +107,8 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __shared__ CmdEntry lut[256];
+    build_cmd_lut(P, lut, tid, kPipeThreads);
     const uint8_t* tiles = nullptr;
     if (DGEN == ORX_DGEN_FIXED) {
         const int nt = P.W * P.H;
@@ -128,6 +137,7 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
             bulk_load(base + OFF_STATUS, P.status + g, 256, bar);
             bulk_load(base + OFF_MOVES, moves + g, 512, bar);
         };
+        if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // all earlier work in the stream is complete and visible
         const unsigned int pre = my_tiles < (unsigned)kStages ? my_tiles : (unsigned)kStages;
         for (unsigned int it = 0; it < pre; ++it) issue_loads(it);
         for (unsigned int it = 0; it < my_tiles; ++it) {
@@ -175,15 +185,16 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
             const uint4 blk = draw_block(rs, DOM_TICK, SUB_MAIN, (uint32_t)tick);
             Counters cnt{};
             EvSink<false> ev{nullptr, 0, 0};
-            res = tick_lane<DGEN, false, false>(P, tiles, L, mv, blk.z, rs, lane, ev, cnt);
+            res = tick_lane<DGEN, false, false>(P, tiles, lut, L, mv, blk.z, rs, lane, ev, cnt);
             int new_status = res;
             if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
                 rs.episode += 1;
                 reset_lane<DGEN, false>(P, L, rs, lane);
                 new_status = ORX_RESULT_IN_PROGRESS;
             }
+            const uint32_t new_hp = ((uint32_t)L.hp1 & 0xFFFFu) | ((uint32_t)L.hp2 << 16);
             reinterpret_cast<uint32_t*>(st + OFF_POS)[tid] = L.pos;
-            reinterpret_cast<uint32_t*>(st + OFF_HP)[tid] = ((uint32_t)L.hp1 & 0xFFFFu) | ((uint32_t)L.hp2 << 16);
+            reinterpret_cast<uint32_t*>(st + OFF_HP)[tid] = new_hp;
             reinterpret_cast<uint32_t*>(st + OFF_ST)[tid] = L.st;
             reinterpret_cast<int*>(st + OFF_TICK)[tid] = L.tick;
             reinterpret_cast<uint32_t*>(st + OFF_EP)[tid] = L.episode;

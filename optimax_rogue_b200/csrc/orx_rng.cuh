@@ -9,25 +9,32 @@ namespace orx {
 enum : uint32_t { DOM_TICK = 0, DOM_LEVEL = 1, DOM_RESET = 2 };
 enum : uint32_t { SUB_MAIN = 0, SUB_NPC = 1, SUB_DESCEND = 64, MAX_TRIES = 256 };
 
+// The ten round keys (seed + r * Weyl constants) are the same for every game of a launch: the host
+// computes them once into the kernel parameter block, so a round is two wide multiplies and two
+// three-input XORs against constant-bank operands.
+struct RoundKeys { uint32_t k[20]; };   // k[2r], k[2r+1]
+
 struct Stream {
-    uint32_t k0, k1;      // Philox key = seed
+    const RoundKeys* rk;
     uint32_t g0, g1;      // global game id (g1 < 2^22)
     uint32_t episode;
 };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1)
+__host__ __device__ inline void make_round_keys(RoundKeys& rk, uint32_t k0, uint32_t k1)
+{
+    for (int r = 0; r < 10; ++r) { rk.k[2 * r] = k0; rk.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RoundKeys& rk)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0;
+        c0 = hi1 ^ c1 ^ rk.k[2 * r];
         c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
+        c2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
         c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -35,7 +42,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ uint4 draw_block(const Stream& s, uint32_t domain, uint32_t sub, uint32_t index)
 {
     const uint32_t c1 = (s.g1 & 0x3FFFFFu) | ((sub & 0xFFu) << 22) | (domain << 30);
-    return philox4x32_10(s.g0, c1, s.episode, index, s.k0, s.k1);
+    return philox4x32_10(s.g0, c1, s.episode, index, *s.rk);
 }
 
 __device__ __forceinline__ uint32_t bounded(uint32_t w, uint32_t n) { return __umulhi(w, n); }

@@ -34,8 +34,7 @@ struct Params {
     int hp0, hp1;
     int dmg0, dmg1;            // damage - armor of the ATTACKER (updater.py:313)
     int auto_reset, n_npc;
-    uint32_t k0, k1;
-    uint32_t lim_lo, lim_hi;   // per-command wall limit of the moved coordinate (EMPTY rooms)
+    RoundKeys rk;              // Philox round keys of the seed
     const uint8_t* tiles;      // DGEN_FIXED: uint8[W*H] x-major
     const uint16_t* ground;    // DGEN_FIXED: Ground tile list
     int n_ground, fsx, fsy;
@@ -183,29 +182,41 @@ __device__ __noinline__ uint2 reset_draw(const Params& P, Stream s)
 }
 
 // ---------------------------------------------------------------- command -> clamped xy delta
-// Returns 0 for Stay, for codes outside Move (logic/moves.py:6-12) and for a move into a Wall or
-// off the map (updater.py:90-98, world.py:41-46), evaluated from the pre-tick position.
-template <int DGEN>
-__device__ __forceinline__ int clamped_delta(const Params& P, const uint8_t* tiles, uint32_t m, uint32_t xy)
+// A 256-entry shared-memory table turns a raw command byte into its xy delta (0 for Stay and for
+// codes outside Move, logic/moves.py:6-12) and, for empty rooms, into a (mask, value) pair such
+// that the move is blocked iff (xy & mask) == value. Inside an empty room only the border blocks
+// (updater.py:90-98, world.py:41-46): Up is blocked iff y == 1, Right iff x == W-2, Down iff
+// y == H-2, Left iff x == 1; Stay/invalid use mask = value = 0, i.e. "always blocked" => delta 0.
+struct CmdEntry { uint32_t maskval; int delta; };
+
+__device__ __forceinline__ void build_cmd_lut(const Params& P, CmdEntry* lut, unsigned int tid, unsigned int nthreads)
 {
-    const bool odd = (m & 1u) != 0;                     // Up(1)/Down(3) move y, Right(2)/Left(4) move x
-    const int dd = odd ? ((int)(m - 2u) << 8) : (int)(3u - m);
-    bool ok = (m - 1u) < 4u;
+    for (unsigned int m = tid; m < 256u; m += nthreads) {
+        CmdEntry e{0u, 0};
+        if (m == ORX_MOVE_UP) e = {0xFF00u | (0x0100u << 16), -256};
+        else if (m == ORX_MOVE_RIGHT) e = {0x00FFu | ((uint32_t)(P.W - 2) << 16), 1};
+        else if (m == ORX_MOVE_DOWN) e = {0xFF00u | ((uint32_t)(P.H - 2) << 24), 256};
+        else if (m == ORX_MOVE_LEFT) e = {0x00FFu | (0x0001u << 16), -1};
+        lut[m] = e;
+    }
+}
+
+// Returns 0 for Stay, for invalid codes and for a move into a Wall or off the map, evaluated from
+// the pre-tick position.
+template <int DGEN>
+__device__ __forceinline__ int clamped_delta(const Params& P, const uint8_t* tiles, const CmdEntry* lut, uint32_t m, uint32_t xy)
+{
+    const CmdEntry e = lut[m];
     if (DGEN == ORX_DGEN_EMPTY) {
-        // Inside an empty room only the border blocks: the moved coordinate must not already sit
-        // next to it. lim bytes (indexed by the command): Up 1, Right W-2, Down H-2, Left 1.
-        const uint32_t c = odd ? (xy >> 8) : (xy & 255u);
-        const uint32_t lim = __byte_perm(P.lim_lo, P.lim_hi, m & 7u) & 255u;
-        ok = ok & (c != lim);
+        return ((xy & e.maskval & 0xFFFFu) == (e.maskval >> 16)) ? 0 : e.delta;
     } else {
+        if (e.delta == 0) return 0;
+        const bool odd = (m & 1u) != 0;
         const int x = (int)(xy & 255u) + (odd ? 0 : (int)(3u - m));
         const int y = (int)(xy >> 8) + (odd ? (int)(m - 2u) : 0);
-        if (ok) {
-            ok = (unsigned)x < (unsigned)P.W && (unsigned)y < (unsigned)P.H;
-            if (ok) ok = tiles[x * P.H + y] != ORX_TILE_WALL;
-        }
+        if ((unsigned)x >= (unsigned)P.W || (unsigned)y >= (unsigned)P.H) return 0;
+        return tiles[x * P.H + y] != ORX_TILE_WALL ? e.delta : 0;
     }
-    return ok ? dd : 0;
 }
 
 template <int DGEN>
@@ -218,12 +229,12 @@ __device__ __forceinline__ bool is_stairs(const Params& P, const uint8_t* tiles,
 // One Updater.update. mv = p1 command | p2 command << 8; w_init is word 2 of the tick's main
 // block. Returns the UpdateResult.
 template <int DGEN, bool NPC, bool EV>
-__device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, Lane& L, uint32_t mv,
+__device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, const CmdEntry* lut, Lane& L, uint32_t mv,
                                          uint32_t w_init, const Stream& s, unsigned int lane,
                                          EvSink<EV>& ev, Counters& cnt)
 {
-    const int dl1 = clamped_delta<DGEN>(P, tiles, mv & 255u, L.pos & 0xFFFFu);
-    const int dl2 = clamped_delta<DGEN>(P, tiles, (mv >> 8) & 255u, L.pos >> 16);
+    const int dl1 = clamped_delta<DGEN>(P, tiles, lut, mv & 255u, L.pos & 0xFFFFu);
+    const int dl2 = clamped_delta<DGEN>(P, tiles, lut, (mv >> 8) & 255u, L.pos >> 16);
     // random.shuffle([p1, p2]) (updater.py:114): j = randbelow(2) = w >> 31; j == 0 swaps => p2 first.
     // Roles: A acts first and lives in the LOW half of pos/st, B acts second in the HIGH half.
     const bool p2_first = (int)w_init >= 0;
@@ -350,7 +361,7 @@ __device__ __forceinline__ Stream make_stream(const Params& P, unsigned int i, u
 {
     const unsigned long long gid = P.gid_base + (unsigned long long)i;
     Stream s;
-    s.k0 = P.k0; s.k1 = P.k1; s.g0 = (uint32_t)gid; s.g1 = (uint32_t)(gid >> 32); s.episode = episode;
+    s.rk = &P.rk; s.g0 = (uint32_t)gid; s.g1 = (uint32_t)(gid >> 32); s.episode = episode;
     return s;
 }
 
