@@ -137,6 +137,7 @@ def cpu_port_run(n_games, seconds, steps=None, game_id_base=0):
     import numpy as np
     from oracle import cport
     cfg = sim_config()
+    cores = cport.set_threads(os.cpu_count())         # torchrun exports OMP_NUM_THREADS=1
     orc = cport.Oracle(cfg, n_games, game_id_base)
     orc.reset()
     stats = np.zeros(8, np.uint64)
@@ -151,7 +152,7 @@ def cpu_port_run(n_games, seconds, steps=None, game_id_base=0):
         if (steps is not None and done >= steps) or (steps is None and el >= seconds):
             break
     el = time.perf_counter() - t0
-    return float(stats[0]) / el, os.cpu_count(), int(stats[0]), el
+    return float(stats[0]) / el, cores, int(stats[0]), el
 
 
 def run_reference(args, rank, world):
@@ -164,6 +165,7 @@ def run_reference(args, rank, world):
     import numpy as np
     from oracle import cport
     cfg = sim_config()
+    cores = cport.set_threads(os.cpu_count())         # torchrun exports OMP_NUM_THREADS=1
     orc = cport.Oracle(cfg, n_sample, 0)
     orc.reset()
     stats = np.zeros(8, np.uint64)
@@ -181,7 +183,7 @@ def run_reference(args, rank, world):
         'steps': steps, 'warmup': max(args.warmup, 1), 'ms_per_step': 1e3 * el / steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
         'data': 'synthetic', 'config': {'workload': WORKLOAD, 'games_per_step': n_sample},
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': f'{steps} steps x {n_sample} games, oracle/orx_oracle.c oro_rollout(1 tick, RandomBot x2), OpenMP'},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'wall_s': time.perf_counter() - t_w0,

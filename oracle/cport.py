@@ -20,6 +20,7 @@ _HDR = os.path.join(_HERE, '..', 'include', 'orx.h')
 
 _PROTOS = {
     'oro_philox': (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'oro_set_threads': (C.c_int, [C.c_int]),
     'oro_reset': (C.c_int, [C.POINTER(_abi.OrxConfig), C.POINTER(_abi.OrxState), C.c_void_p,
                             C.c_int, C.c_int64, C.c_uint64]),
     'oro_step': (C.c_int, [C.POINTER(_abi.OrxConfig), C.POINTER(_abi.OrxState), C.c_void_p,
@@ -55,6 +56,11 @@ def lib():
         build()
         _lib = _abi.bind(C.CDLL(_SO), _PROTOS)
     return _lib
+
+
+def set_threads(n=0):
+    """Sets (n > 0) and returns the OpenMP thread count oro_rollout will use."""
+    return lib().oro_set_threads(int(n))
 
 
 def philox(ctr, key):

@@ -27,6 +27,21 @@
 #include <string.h>
 
 #include "../include/orx.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* threads used by oro_rollout (the CPU baseline); torchrun exports OMP_NUM_THREADS=1 */
+int oro_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 /* ------------------------------------------------------------------ Philox4x32-10 */
 static void philox(uint32_t c[4], uint32_t k0, uint32_t k1)
