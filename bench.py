@@ -10,8 +10,10 @@ streams). Rank r owns games [r*G, (r+1)*G) (weak scaling, no collective on the s
 
 Timed regions (CUDA events on the launching stream, max over ranks):
   value     K steps captured in one CUDA graph, commands already resident in HBM
-  e2e       the public ``BatchedUpdater.update`` call with HOST command/result buffers: pinned H2D
-            copy of the step's commands, the tick, D2H copy of the results, sync -- every step
+  e2e       the public ``BatchedUpdater.update`` call with pinned HOST command/result buffers: the
+            step's commands cross PCIe host->device and its results device->host inside the timed
+            region every step (the tick kernel's TMA producer reads/writes the pinned buffers
+            directly, tile by tile), then a stream sync so the caller can read the results
   rollout   (extra) fused multi-tick kernel with both bots on device
 L2: the timed loop rotates over B independent batches whose combined state exceeds the 126 MB L2.
 
@@ -346,7 +348,7 @@ def run_b200(args, rank, local_rank, world):
                          'games_per_launch': G},
             'e2e': {'value': world * G * k_e2e / (ms_e2e * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': 2 * G, 'd2h_bytes_per_step': G, 'steps': k_e2e,
-                    'api': 'BatchedUpdater.update(state, pinned host uint8[N,2]) -> pinned host uint8[N] (orx_step_host), sync every step'},
+                    'api': 'BatchedUpdater.update(state, pinned host uint8[N,2]) -> pinned host uint8[N] (orx_step_host: commands and results cross PCIe inside the tick kernel), sync every step'},
             'gpu_launches': K,
             'rollout': {'value': roll_ticks_all / (ms_roll * 1e-3), 'unit': UNIT, 'ticks_per_launch': T,
                         'launches': r_launches, 'fused': True,

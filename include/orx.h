@@ -146,9 +146,10 @@ int orx_reset(const OrxConfig* cfg, const OrxState* st, const uint8_t* mask, int
 int orx_step(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uint8_t* result,
              OrxEvent* events, int64_t n, uint64_t game_id_base, void* cuda_stream);
 
-/* orx_step with HOST command/result buffers: H2D copy of moves, the tick, D2H copy of result,
- * all on cuda_stream (pinned host memory makes the copies asynchronous). moves_dev/result_dev
- * are caller-owned device staging buffers of the same shapes. */
+/* orx_step with HOST command/result buffers, all on cuda_stream; results are valid in result_host
+ * once the stream has been synchronised. Pinned (page-locked) buffers are read/written directly by
+ * the tick kernel over PCIe, tile by tile; pageable buffers go through H2D/D2H copies into the
+ * caller-owned device staging buffers moves_dev/result_dev (same shapes). */
 int orx_step_host(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
                   uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
                   uint64_t game_id_base, void* cuda_stream);

@@ -1,6 +1,7 @@
 // liborx.so: kernels + the C ABI declared in include/orx.h. sm_100a only.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/orx.h"
@@ -138,8 +139,11 @@ __device__ __forceinline__ unsigned int warp_sum(unsigned int v)
     return v;
 }
 
+#ifndef ORX_ROLLOUT_MINBLOCKS
+#define ORX_ROLLOUT_MINBLOCKS 3
+#endif
 template <int DGEN, bool NPC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, ORX_ROLLOUT_MINBLOCKS)
 k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, unsigned long long* __restrict__ stats)
 {
     extern __shared__ uint8_t smem[];
@@ -296,6 +300,15 @@ int dispatch_dgen_npc(const OrxConfig* c, F&& f)
 }
 
 
+bool host_mapped(const void* p, void** dev)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+    *dev = a.devicePointer;
+    return true;
+}
+
 bool pipe_aligned(const OrxState* st, const void* moves, const void* result)
 {
     return aligned(st->pos, 16) && aligned(st->hp, 16) && aligned(st->depth, 16) && aligned(st->stairs, 16) &&
@@ -421,6 +434,14 @@ int orx_step_host(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves
     if (rc != ORX_OK) return rc;
     if (n == 0) return ORX_OK;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    // Pinned (page-locked, UVA-mapped) host buffers are read and written by the tick kernel itself:
+    // the TMA producer pulls each tile's commands over PCIe next to its HBM planes and the results
+    // stream back the same way, so there is no separate copy launch and the transfer overlaps the
+    // compute tile by tile. Pageable buffers fall back to staged cudaMemcpyAsync copies.
+    void *mv_map = nullptr, *res_map = nullptr;
+    if (getenv("ORX_HOST_STAGED") == nullptr && host_mapped(moves_host, &mv_map) && host_mapped(result_host, &res_map))
+        return orx_step(cfg, st, static_cast<const uint8_t*>(mv_map), static_cast<uint8_t*>(res_map), nullptr, n,
+                        game_id_base, cuda_stream);
     cudaError_t e = cudaMemcpyAsync(moves_dev, moves_host, (size_t)n * 2, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return cuda_fail(e);
     const int rs = orx_step(cfg, st, moves_dev, result_dev, nullptr, n, game_id_base, cuda_stream);

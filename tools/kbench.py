@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--games', type=int, nargs='+', default=[1 << 20])
 ap.add_argument('--steps', type=int, default=200)
 ap.add_argument('--reps', type=int, default=3)
+ap.add_argument('--rollout', type=int, default=0, help='also time orx_rollout with this many ticks per launch')
 args = ap.parse_args()
 dev = torch.device('cuda')
 for G in args.games:
@@ -48,4 +49,19 @@ for G in args.games:
             e0.record(st); g.replay(); e1.record(st)
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) / args.steps)
+    if args.rollout:
+        stats = torch.zeros(8, dtype=torch.int64, device=dev)
+        with torch.cuda.stream(st):
+            upd.rollout(batches[0], 1, 1, args.rollout, stats)
+            torch.cuda.synchronize()
+            rbest = 1e9
+            for _ in range(args.reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for b in range(min(nb, 4)):
+                    upd.rollout(batches[b], 1, 1, args.rollout, stats)
+                e1.record(st)
+                torch.cuda.synchronize()
+                rbest = min(rbest, e0.elapsed_time(e1) / min(nb, 4))
+        print(f'games={G} rollout T={args.rollout}: {rbest * 1e3:.1f} us/launch, {G * args.rollout / rbest * 1e3:.3e} ticks/s', flush=True)
     print(f'games={G} batches={nb} us/step={best * 1e3:.2f} ticks/s={G / best * 1e3:.3e} GB/s(61B)={61 * G / best / 1e6:.0f}', flush=True)
