@@ -6,6 +6,8 @@ of ``include/orx.h:OrxState``). It replaces the reference's per-game object grap
 have no counterpart. ``GameState`` is the host-side single-game view with the reference's
 attribute names, used for interop with code written against the reference.
 """
+import io
+import json
 import typing
 
 import numpy as np
@@ -45,6 +47,54 @@ class GameState:
         ents = [e for e in self.entities if e.depth == entity.depth]
         return GameState(False, self.tick - 1 if reduce_tick else self.tick,
                          self.player_1_iden, self.player_2_iden, world, ents)
+
+    # -- the reference's binary snapshot (state.py:94-132), byte for byte --------------------------
+    ENTITY_IDEN = 'optimax_rogue.game.entities.entity'     # Serializable.identifier, serializer.py:92-96
+
+    @staticmethod
+    def _entity_bytes(ent: Entity) -> bytes:
+        """ser.serialize(entity): JSON, sorted keys, ASCII (serializer.py:46-52,145-151; the
+        prims are Entity.to_prims, entities.py:76-88; no modifier or item class exists)."""
+        prims = {'iden': ent.iden, 'x': ent.x, 'y': ent.y, 'depth': ent.depth, 'health': ent.health,
+                 'base_max_health': ent.base_max_health, 'base_damage': ent.base_damage,
+                 'base_armor': ent.base_armor, 'modifiers': [], 'items': {}}
+        return json.dumps({'iden': GameState.ENTITY_IDEN, 'prims': prims}, sort_keys=True).encode('ASCII')
+
+    def to_prims(self) -> bytes:
+        arr = io.BytesIO()
+        arr.write((1 if self.is_authoritative else 0).to_bytes(1, 'big', signed=False))
+        arr.write(int(self.tick).to_bytes(4, 'big', signed=False))
+        arr.write(int(self.player_1_iden).to_bytes(4, 'big', signed=False))
+        arr.write(int(self.player_2_iden).to_bytes(4, 'big', signed=False))
+        wserd = self.world.to_prims()
+        arr.write(len(wserd).to_bytes(8, 'big', signed=False))
+        arr.write(wserd)
+        arr.write(len(self.entities).to_bytes(4, 'big', signed=False))
+        for ent in self.entities:
+            eserd = self._entity_bytes(ent)
+            arr.write(len(eserd).to_bytes(4, 'big', signed=False))
+            arr.write(eserd)
+        return arr.getvalue()
+
+    @classmethod
+    def from_prims(cls, prims: bytes) -> 'GameState':
+        arr = io.BytesIO(prims)
+        auth = int.from_bytes(arr.read(1), 'big', signed=False)
+        tick = int.from_bytes(arr.read(4), 'big', signed=False)
+        p1 = int.from_bytes(arr.read(4), 'big', signed=False)
+        p2 = int.from_bytes(arr.read(4), 'big', signed=False)
+        wlen = int.from_bytes(arr.read(8), 'big', signed=False)
+        world = World.from_prims(arr.read(wlen))
+        ents = []
+        for _ in range(int.from_bytes(arr.read(4), 'big', signed=False)):
+            elen = int.from_bytes(arr.read(4), 'big', signed=False)
+            d = json.loads(arr.read(elen).decode('ASCII'))
+            if d['iden'] != cls.ENTITY_IDEN:
+                raise ValueError(f"unexpected serialized type {d['iden']}")
+            q = d['prims']
+            ents.append(Entity(q['iden'], q['depth'], q['x'], q['y'], q['health'], q['base_max_health'],
+                               q['base_damage'], q['base_armor']))
+        return cls(auth == 1, tick, p1, p2, world, ents)
 
 
 def empty_room_tiles(width: int, height: int, stairs: typing.Tuple[int, int]) -> np.ndarray:

@@ -56,6 +56,40 @@ def test_step_parity_separated_start_and_stats():
     gu.run_parity(cfg, 1024, 400, bots=(2, 1), events=True)
 
 
+@pytest.mark.parametrize('n', [1, 31, 255, 256, 257, 1000])
+def test_step_parity_ragged_batch_sizes(n):
+    # < 256 games: simple kernel only; 257 / 1000: TMA-pipelined body + ragged tail
+    cfg = SimConfig(max_ticks=30, seed=21, auto_reset=True, hp=(2, 2))
+    gu.run_parity(cfg, n, 70, bots=(1, 2), events=False, game_id_base=77)
+
+
+def test_events_do_not_change_the_state():
+    # the event-writing kernel variant and the pipelined hot variant must agree
+    cfg = SimConfig(max_ticks=90, seed=8, auto_reset=True)
+    a, upd, _ = gu.make_pair(cfg, 3000)
+    b = a.clone()
+    for t in range(120):
+        mv = upd.bot_moves(a, 2, 1)
+        ra, _ = upd.update(a, mv, want_events=True)
+        rb, _ = upd.update(b, mv, want_events=False)
+        assert torch.equal(ra, rb)
+    for name in gu.PLANES:
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
+def test_checkpoint_resume(tmp_path):
+    cfg = SimConfig(max_ticks=64, seed=5, auto_reset=True)
+    gs, upd, _ = gu.make_pair(cfg, 2048)
+    upd.rollout(gs, 1, 1, 33)
+    torch.save(gs.state_dict(), tmp_path / 'ck.pt')
+    upd.rollout(gs, 1, 1, 50)
+    resumed = BatchedGameState(cfg, 2048, 'cuda')
+    resumed.load_state_dict(torch.load(tmp_path / 'ck.pt'))
+    upd.rollout(resumed, 1, 1, 50)
+    for name in gu.PLANES:
+        assert torch.equal(getattr(gs, name), getattr(resumed, name)), name
+
+
 def test_step_out_of_range_commands_are_stay():
     cfg = SimConfig(max_ticks=0, seed=3)
     rng = np.random.default_rng(0)

@@ -117,3 +117,32 @@ def test_event_decoding():
     assert (evs[1].entity_iden, evs[1].depth, evs[1].old_depth, evs[1].posx, evs[1].posy) == (1, 2, 1, 7, 3)
     assert evs[1].depth_changed and not evs[3].depth_changed
     assert (evs[2].attacker_iden, evs[2].defender_iden, evs[2].og_damage, evs[2].tags) == (2, 1, 1, {3})
+
+
+def _sample_game_state():
+    d0, d3 = Dungeon(empty_room_tiles(60, 10, (17, 4))), Dungeon(empty_room_tiles(60, 10, (2, 2)))
+    ents = [Entity(1, 0, 5, 6, 9, 10, 2, 1), Entity(2, 3, 40, 3, -1, 10, 2, 1), Entity(3, 0, 7, 7, 2, 2, 0, 0)]
+    return GameState(True, 77, 1, 2, World({0: d0, 3: d3}), ents)
+
+
+def test_game_state_snapshot_roundtrip():
+    gs = _sample_game_state()
+    raw = gs.to_prims()
+    assert raw[0] == 1 and raw[1:5] == (77).to_bytes(4, 'big')                      # state.py:96-98
+    back = GameState.from_prims(raw)
+    assert back.tick == 77 and back.world == gs.world and back.entities == gs.entities
+    assert back.to_prims() == raw
+
+
+@pytest.mark.skipif(not rh.reference_available(), reason='reference tree not present')
+def test_game_state_snapshot_is_byte_identical_to_reference():
+    ref = rh.load_reference()
+    ours = _sample_game_state()
+    rd = {d: ref.world.Dungeon(dung.tiles.copy()) for d, dung in ours.world.dungeons.items()}
+    rents = [ref.entities.Entity(e.iden, e.depth, e.x, e.y, e.health, e.base_max_health, e.base_damage,
+                                 e.base_armor, [], dict()) for e in ours.entities]
+    theirs = ref.state.GameState(True, 77, 1, 2, ref.world.World(rd), rents)
+    assert ours.to_prims() == theirs.to_prims()
+    # and the reference can load what we write
+    back = ref.state.GameState.from_prims(ours.to_prims())
+    assert back == theirs
