@@ -307,6 +307,43 @@ def run_b200(args, rank, local_rank, world):
         ms_roll = e4.elapsed_time(e5)
         roll_ticks = int(stats[0].item())
 
+        # ---- ruleset R1 (extra; README-only rules, parity unpinned): configs[2], 65,536 games per GPU
+        from optimax_rogue_b200.r1 import R1GameState
+        G1, nb1, K1 = 1 << 16, 18, 72
+        r1_batches = [R1GameState(G1, max_ticks=MAX_TICKS, auto_reset=True, seed=SEED, device=dev,
+                                  game_id_base=(rank * nb1 + b) * G1).reset() for b in range(nb1)]
+        r1_moves = torch.randint(1, 7, (4, G1, 2), dtype=torch.uint8, device=dev, generator=gen)
+        r1_res = torch.empty((G1,), dtype=torch.uint8, device=dev)
+        for b in range(nb1):
+            r1_batches[b].rollout(64)            # populate with enemies / items, untimed
+        torch.cuda.synchronize(dev)
+        g1 = torch.cuda.CUDAGraph()
+        for k in range(3):
+            r1_batches[k].update(r1_moves[k % 4], out=r1_res)
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(g1, stream=stream):
+            for k in range(K1):
+                r1_batches[k % nb1].update(r1_moves[k % 4], out=r1_res)
+        g1.replay()
+        torch.cuda.synchronize(dev)
+        barrier()
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e6.record(stream)
+        g1.replay()
+        e7.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms_r1 = e6.elapsed_time(e7)
+        r1_stats = torch.zeros((8,), dtype=torch.int64, device=dev)
+        e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e8.record(stream)
+        for b in range(4):
+            r1_batches[b].rollout(64, r1_stats)
+        e9.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms_r1_roll = e8.elapsed_time(e9)
+
     if rank == 0:
         time.sleep(0.15)
         sampler.stop()
@@ -321,6 +358,8 @@ def run_b200(args, rank, local_rank, world):
     ms_total = max_over_ranks(ms_total)
     ms_e2e = max_over_ranks(ms_e2e)
     ms_roll = max_over_ranks(ms_roll)
+    ms_r1 = max_over_ranks(ms_r1)
+    ms_r1_roll = max_over_ranks(ms_r1_roll)
     if world > 1:
         t = torch.tensor([roll_ticks], dtype=torch.int64, device=dev)
         dist.all_reduce(t)          # the optional end-of-rollout stats gather (tiny, off the step path)
@@ -353,6 +392,12 @@ def run_b200(args, rank, local_rank, world):
             'rollout': {'value': roll_ticks_all / (ms_roll * 1e-3), 'unit': UNIT, 'ticks_per_launch': T,
                         'launches': r_launches, 'fused': True,
                         'note': 'orx_rollout: bots + tick fused, state in registers for T ticks'},
+            'r1': {'note': 'ruleset R1 = README-only rules (docs/RULESET_R1.md); PARITY UNPINNED vs the reference, '
+                           'bit-exact vs oracle/orx_r1_oracle.c; configs[2]: 65,536 games per GPU, 8 enemy + 4 item slots',
+                   'value': world * G1 * K1 / (ms_r1 * 1e-3), 'unit': UNIT, 'games_per_gpu': G1, 'steps': K1,
+                   'us_per_step': ms_r1 / K1 * 1e3, 'alg_bytes_per_game_tick': 2 * 241 + 3,
+                   'hbm_frac': (2 * 241 + 3) * G1 / (ms_r1 / K1 * 1e-3) / 1e9 / peak,
+                   'rollout_value': world * 4 * G1 * 64 / (ms_r1_roll * 1e-3)},
             'clocks': sampler.summary(t_wall0, t_wall1),
         }
         if not args.no_cpu_baseline:

@@ -168,6 +168,50 @@ int orx_rollout(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2
 int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stairs_radius,
                 int64_t n, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Ruleset R1: the README-only rules (readme.md:44-48,69-74), specified in docs/RULESET_R1.md.
+ * PARITY UNPINNED -- the reference has no code for them. Separate state and entry points; R0 above
+ * is unaffected. 16 entity lanes per game: 0-1 players, 2-9 enemies, 10-13 ground items.
+ * ------------------------------------------------------------------------------------------- */
+#define ORX_R1_LANES 16
+#define ORX_R1_ENEMIES 8
+#define ORX_R1_ITEMS 4
+#define ORX_MOVE_HEAL 6            /* readme.md:74 */
+#define ORX_R1_STATE_BYTES 241
+
+typedef struct OrxR1Config {
+    uint32_t struct_size;
+    int32_t width, height;
+    int32_t max_ticks;              /* 0 = unlimited */
+    int32_t auto_reset;
+    int32_t wall_density;           /* interior tile is a wall iff mix(x, y, key) & 255 < wall_density */
+    uint64_t seed;
+} OrxR1Config;
+
+typedef struct OrxR1State {
+    uint32_t* ent_loc;     /* [n][16]  x | y<<8 | alive<<16 | item kind<<17 */
+    int32_t* ent_depth;    /* [n][16] */
+    uint32_t* ent_stat;    /* [n][16]  int16 hp | int16 mana (players) << 16 */
+    uint32_t* pl_a;        /* [n][2]   max_hp | max_mana<<16 */
+    uint32_t* pl_b;        /* [n][2]   xp | level<<8 | n_items<<16 | cd<<24 */
+    uint32_t* pl_c;        /* [n][2]   damage | armor<<8 */
+    uint32_t* lvl_stairs;  /* [n]      staircase xy of player 1's level | player 2's << 16 */
+    uint32_t* lvl_key;     /* [n][2]   wall key of each player's level */
+    uint32_t* sep;         /* [n]      ticks since the players separated */
+    int32_t* tick;         /* [n] */
+    uint32_t* episode;     /* [n] */
+    uint8_t* status;       /* [n]      ORX_RESULT_* */
+} OrxR1State;
+
+int orx_r1_reset(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mask, int bump_episode,
+                 int64_t n, uint64_t game_id_base, void* cuda_stream);
+/* moves: device uint8[n][2], codes 1..6; result: device uint8[n] */
+int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* moves, uint8_t* result,
+                int64_t n, uint64_t game_id_base, void* cuda_stream);
+/* n_ticks fused ticks, both players uniform random over the six commands; stats as orx_rollout */
+int orx_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, unsigned long long* stats,
+                   int64_t n, uint64_t game_id_base, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

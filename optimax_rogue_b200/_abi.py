@@ -58,6 +58,26 @@ class OrxEvent(C.Structure):
                 ('depth', C.c_int32)]
 
 
+# ---- ruleset R1 (README-only rules; docs/RULESET_R1.md) ------------------------------------------
+R1_LANES, R1_ENEMIES, R1_ITEMS, MOVE_HEAL, R1_STATE_BYTES = 16, 8, 4, 6, 241
+
+
+class OrxR1Config(C.Structure):
+    _fields_ = [('struct_size', C.c_uint32), ('width', C.c_int32), ('height', C.c_int32),
+                ('max_ticks', C.c_int32), ('auto_reset', C.c_int32), ('wall_density', C.c_int32),
+                ('seed', C.c_uint64)]
+
+
+R1_PLANES = (('ent_loc', 'int32', (16,)), ('ent_depth', 'int32', (16,)), ('ent_stat', 'int32', (16,)),
+             ('pl_a', 'int32', (2,)), ('pl_b', 'int32', (2,)), ('pl_c', 'int32', (2,)),
+             ('lvl_stairs', 'int32', ()), ('lvl_key', 'int32', (2,)), ('sep', 'int32', ()),
+             ('tick', 'int32', ()), ('episode', 'int32', ()), ('status', 'uint8', ()))
+
+
+class OrxR1State(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _, _ in R1_PLANES]
+
+
 # name -> (restype, argtypes); every symbol include/orx.h declares
 PROTOTYPES = {
     'orx_abi_version': (C.c_int, []),
@@ -76,6 +96,12 @@ PROTOTYPES = {
                               C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_observe': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_int,
                               C.c_int64, C.c_void_p]),
+    'orx_r1_reset': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_void_p, C.c_int,
+                               C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_r1_step': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_void_p, C.c_void_p,
+                              C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_r1_rollout': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_int, C.c_void_p,
+                                 C.c_int64, C.c_uint64, C.c_void_p]),
 }
 
 

@@ -16,6 +16,7 @@ from optimax_rogue_b200.config import SimConfig
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, '_build', 'liborx_oracle.so')
 _SRC = os.path.join(_HERE, 'orx_oracle.c')
+_SRC_R1 = os.path.join(_HERE, 'orx_r1_oracle.c')
 _HDR = os.path.join(_HERE, '..', 'include', 'orx.h')
 
 _PROTOS = {
@@ -29,17 +30,23 @@ _PROTOS = {
                                 C.c_int, C.c_void_p, C.c_int64, C.c_uint64]),
     'oro_rollout': (C.c_int, [C.POINTER(_abi.OrxConfig), C.POINTER(_abi.OrxState), C.c_int,
                               C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_uint64]),
+    'oro_r1_reset': (C.c_int, [C.POINTER(_abi.OrxR1Config), C.POINTER(_abi.OrxR1State), C.c_void_p,
+                               C.c_int, C.c_int64, C.c_uint64]),
+    'oro_r1_step': (C.c_int, [C.POINTER(_abi.OrxR1Config), C.POINTER(_abi.OrxR1State), C.c_void_p,
+                              C.c_void_p, C.c_int64, C.c_uint64]),
+    'oro_r1_rollout': (C.c_int, [C.POINTER(_abi.OrxR1Config), C.POINTER(_abi.OrxR1State), C.c_int,
+                                 C.c_void_p, C.c_int64, C.c_uint64]),
 }
 
 
 def build(force=False):
     """gcc build of the oracle into oracle/_build/ (OpenMP when the compiler has it)."""
     stale = (not os.path.exists(_SO)
-             or os.path.getmtime(_SO) < max(os.path.getmtime(_SRC), os.path.getmtime(_HDR)))
+             or os.path.getmtime(_SO) < max(os.path.getmtime(_SRC), os.path.getmtime(_SRC_R1), os.path.getmtime(_HDR)))
     if not (force or stale):
         return _SO
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
-    base = ['gcc', '-O2', '-fPIC', '-std=c11', '-Wall', '-shared', '-o', _SO, _SRC]
+    base = ['gcc', '-O2', '-fPIC', '-std=c11', '-Wall', '-shared', '-o', _SO, _SRC, _SRC_R1]
     for extra in (['-fopenmp'], []):
         r = subprocess.run(base + extra, capture_output=True, text=True)
         if r.returncode == 0:
@@ -159,3 +166,55 @@ def decode_events(events_i32):
     a = ((w0 >> 16) & 0xFF).astype(np.int32)
     b = ((w0 >> 24) & 0xFF).astype(np.int32)
     return np.stack([kind, iden, a, b, events_i32[..., 1].astype(np.int32)], axis=-1)
+
+
+# ---- ruleset R1 (parity unpinned: pins the CUDA kernel to docs/RULESET_R1.md, not to the reference)
+def r1_config(width=60, height=10, max_ticks=0, auto_reset=False, wall_density=26, seed=0):
+    c = _abi.OrxR1Config()
+    c.struct_size = C.sizeof(_abi.OrxR1Config)
+    c.width, c.height, c.max_ticks = width, height, int(max_ticks or 0)
+    c.auto_reset, c.wall_density, c.seed = int(auto_reset), wall_density, seed & 0xFFFFFFFFFFFFFFFF
+    return c
+
+
+class R1HostState:
+    def __init__(self, n):
+        self.n = n
+        for name, dt, shape in _abi.R1_PLANES:
+            arr = np.zeros((n,) + shape, dtype=dt)
+            setattr(self, name, arr)
+        self.status[:] = 1
+
+    def c_struct(self):
+        st = _abi.OrxR1State()
+        for name, _, _ in _abi.R1_PLANES:
+            setattr(st, name, getattr(self, name).ctypes.data)
+        return st
+
+
+class R1Oracle:
+    def __init__(self, n, game_id_base=0, **cfg):
+        self.n, self.game_id_base = n, game_id_base
+        self.c_cfg = r1_config(**cfg)
+        self.state = R1HostState(n)
+
+    def reset(self, mask=None, bump_episode=False):
+        st = self.state.c_struct()
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().oro_r1_reset(C.byref(self.c_cfg), C.byref(st), None if m is None else m.ctypes.data,
+                           int(bump_episode), self.n, self.game_id_base)
+
+    def step(self, moves):
+        moves = np.ascontiguousarray(moves, np.uint8).reshape(self.n, 2)
+        result = np.zeros(self.n, np.uint8)
+        st = self.state.c_struct()
+        lib().oro_r1_step(C.byref(self.c_cfg), C.byref(st), moves.ctypes.data, result.ctypes.data, self.n,
+                          self.game_id_base)
+        return result
+
+    def rollout(self, n_ticks, stats=None):
+        stats = np.zeros(_abi.STAT_COUNT, np.uint64) if stats is None else stats
+        st = self.state.c_struct()
+        lib().oro_r1_rollout(C.byref(self.c_cfg), C.byref(st), n_ticks, stats.ctypes.data, self.n,
+                             self.game_id_base)
+        return stats

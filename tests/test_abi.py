@@ -17,7 +17,7 @@ HEADER = os.path.join(ROOT, 'include', 'orx.h')
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    return sorted(set(re.findall(r'\b(orx_[a-z_]+)\s*\(', src)))
+    return sorted(set(re.findall(r'\b(orx_[a-z0-9_]+)\s*\(', src)))
 
 
 def test_header_and_ctypes_mirror_list_the_same_functions():

@@ -1,0 +1,88 @@
+"""-m gpu: ruleset R1 (README-only rules, docs/RULESET_R1.md). PARITY UNPINNED with respect to the
+reference -- these tests pin the CUDA kernels to the plain-C restatement of the written spec
+(oracle/orx_r1_oracle.c), bit for bit, every plane, every tick."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport
+from optimax_rogue_b200 import _abi
+from optimax_rogue_b200.r1 import R1GameState
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(n, base=0, **cfg):
+    gs = R1GameState(n, game_id_base=base, **cfg).reset()
+    orc = cport.R1Oracle(n, game_id_base=base, **cfg)
+    orc.reset()
+    return gs, orc
+
+
+def assert_equal(gs, orc, where):
+    p = gs.planes_cpu()
+    for name, _, _ in _abi.R1_PLANES:
+        a, b = p[name], getattr(orc.state, name)
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a.reshape(len(a), -1) != b.reshape(len(b), -1))[0]
+            raise AssertionError(f'{where}: plane {name} differs at game {bad[0]} col {bad[1]}: '
+                                 f'cuda={a[bad[0]]} oracle={b[bad[0]]}')
+
+
+@pytest.mark.parametrize('w,h,density', [(60, 10, 26), (12, 8, 0), (9, 9, 40), (30, 6, 90)])
+def test_r1_reset_parity(w, h, density):
+    gs, orc = pair(3001, base=(1 << 33) + 5, width=w, height=h, wall_density=density, seed=11)
+    assert_equal(gs, orc, 'reset')
+
+
+@pytest.mark.parametrize('w,h,density,ticks', [(60, 10, 26, 400), (10, 7, 10, 300), (7, 7, 0, 300), (24, 8, 60, 250)])
+def test_r1_step_parity_random_commands(w, h, density, ticks):
+    n = 2000
+    gs, orc = pair(n, width=w, height=h, wall_density=density, seed=3, max_ticks=150, auto_reset=True)
+    rng = np.random.default_rng(w * 1000 + h)
+    for t in range(ticks):
+        mv = rng.integers(0, 8, size=(n, 2), dtype=np.uint8)        # includes Heal (6) and invalid codes (0, 7)
+        ro = orc.step(mv)
+        rg = gs.update(torch.from_numpy(mv).cuda())
+        assert np.array_equal(rg.cpu().numpy(), ro), f'tick {t}: results differ'
+        if t % 10 == 0 or t == ticks - 1:
+            assert_equal(gs, orc, f'tick {t}')
+
+
+def test_r1_frozen_without_auto_reset():
+    n = 1500
+    gs, orc = pair(n, width=8, height=8, wall_density=0, seed=9, max_ticks=60)
+    rng = np.random.default_rng(1)
+    for t in range(80):
+        mv = rng.integers(1, 7, size=(n, 2), dtype=np.uint8)
+        ro = orc.step(mv)
+        rg = gs.update(torch.from_numpy(mv).cuda())
+        assert np.array_equal(rg.cpu().numpy(), ro)
+    assert_equal(gs, orc, 'end')
+    assert (gs.status != 1).all()
+
+
+def test_r1_rollout_matches_oracle_and_rules_fire():
+    n = 5000
+    gs, orc = pair(n, seed=0x0A11CE, max_ticks=500, auto_reset=True)
+    stats = gs.rollout(400)
+    ostats = orc.rollout(400)
+    assert_equal(gs, orc, 'rollout')
+    assert np.array_equal(stats.cpu().numpy().astype(np.uint64), ostats)
+    p = gs.planes_cpu()
+    alive = (p['ent_loc'] >> 16) & 1
+    assert alive[:, 2:10].sum() > 0, 'enemies spawn'
+    assert ((p['pl_b'] >> 16) & 255).max() > 0, 'items get picked up'
+    assert ((p['pl_b'] >> 8) & 255).max() > 1, 'players level up'
+    assert int(stats[1]) + int(stats[2]) > 0, 'games end by death'
+    assert int(stats[5]) > 0, 'descents happen'
+
+
+def test_r1_shard_invariance():
+    cfg = dict(seed=21, max_ticks=200, auto_reset=True)
+    full = R1GameState(2048, **cfg).reset()
+    full.rollout(150)
+    part = R1GameState(1024, game_id_base=1024, **cfg).reset()
+    part.rollout(150)
+    for name, _, _ in _abi.R1_PLANES:
+        assert torch.equal(getattr(part, name), getattr(full, name)[1024:]), name
