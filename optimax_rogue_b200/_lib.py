@@ -29,6 +29,15 @@ def lib():
     """The bound CDLL; raises RuntimeError (loudly) when the extension is not built."""
     global _lib
     if _lib is None:
+        if 'ORX_LIB' not in os.environ:
+            from . import build as _build
+            if not _build.is_current():
+                # never run kernels that do not match the sources in the tree
+                if _build.have_nvcc():
+                    _build.build()
+                elif os.path.exists(LIB_PATH):
+                    raise RuntimeError(f'{LIB_PATH} is stale (sources changed since it was built) and nvcc is '
+                                       'not available to rebuild it. There is no CPU fallback.')
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f'{LIB_PATH} is missing: the CUDA extension has not been built. '

@@ -1,5 +1,7 @@
 """Builds ``liborx.so`` in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import hashlib
 import os
+import shutil
 import subprocess
 import sys
 
@@ -14,9 +16,33 @@ NVCC_FLAGS = ['-std=c++20', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-shared', '-Xcompiler', '-fPIC', '--cudart', 'shared']
 
 
+HASH_FILE = OUT + '.srchash'
+
+
+def source_hash() -> str:
+    h = hashlib.sha256()
+    for p in sorted(SOURCES + HEADERS):
+        with open(p, 'rb') as f:
+            h.update(f.read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    """True when liborx.so was built from exactly the sources in the tree."""
+    try:
+        with open(HASH_FILE) as f:
+            return os.path.exists(OUT) and f.read().strip() == source_hash()
+    except OSError:
+        return False
+
+
+def have_nvcc() -> bool:
+    return shutil.which(os.environ.get('NVCC', 'nvcc')) is not None
+
+
 def build(force=False, verbose=False):
-    newest = max(os.path.getmtime(p) for p in SOURCES + HEADERS)
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
+    if not force and is_current():
         return OUT
     nvcc = os.environ.get('NVCC', 'nvcc')
     cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT] + SOURCES
@@ -25,6 +51,8 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
+    with open(HASH_FILE, 'w') as f:
+        f.write(source_hash())
     return OUT
 
 

@@ -231,3 +231,38 @@ def test_bad_arguments_fail_loudly():
     # n == 0 is a no-op
     c = gs.c_config()
     assert lib.orx_reset(C.byref(c), C.byref(st), None, 0, 0, 0, None) == 0
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json size (2^20 games): the oracle cannot replay a million games in seconds, so the
+    checks are size-independent properties -- fused rollout == tick-by-tick loop on every lane, and
+    four 1024-game windows of the batch equal the oracle run on just those global game ids."""
+    n, ticks = 1 << 20, 48
+    cfg = SimConfig(max_ticks=40, seed=SEED, auto_reset=True, hp=(3, 3))
+    gs = BatchedGameState(cfg, n, 'cuda')
+    reset_games(gs)
+    from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
+    upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, 40, auto_reset=True)
+    twin = gs.clone()
+    stats = upd.rollout(gs, 1, 2, ticks)
+    moves = torch.empty((n, 2), dtype=torch.uint8, device='cuda')
+    wins = torch.zeros(5, dtype=torch.int64, device='cuda')
+    for _ in range(ticks):
+        upd.bot_moves(twin, 1, 2, out=moves)
+        res, _ = upd.update(twin, moves)
+        wins += torch.bincount(res.to(torch.int64), minlength=5)
+    for name in gu.PLANES:
+        assert torch.equal(getattr(gs, name), getattr(twin, name)), name
+    assert int(stats[0]) == n * ticks
+    assert [int(stats[1]), int(stats[2]), int(stats[3])] == [int(wins[2]), int(wins[3]), int(wins[4])]
+    p = gs.planes_cpu()
+    from oracle import cport
+    for start in (0, 123 * 1024, 700 * 1024 + 1, n - 1024):
+        orc = cport.Oracle(cfg, 1024, game_id_base=start)
+        orc.reset()
+        orc.rollout(1, 2, ticks)
+        for name in gu.PLANES:
+            a = p[name][start:start + 1024]
+            if name == 'episode':
+                a = a.view(np.uint32)
+            assert np.array_equal(a, getattr(orc.state, name)), (start, name)
