@@ -195,10 +195,12 @@ __device__ __forceinline__ int r1_tick(const R1Params& P, const Grp g, R1Lane& L
     if (victim >= 0) { const int full = max(0, my_dmg - v_arm); dealt = amount == 2 ? full / 2 : full; }
     // gather: what do I take, and which players damaged me
     int taken = 0, credit = 0;
-#pragma unroll
-    for (int j = 0; j < NM; ++j) {
+    uint32_t attackers = g.ballot(victim >= 0 && dealt > 0);
+    while (attackers) {                       // usually empty: most ticks have no combat
+        const int j = __ffs(attackers) - 1;
+        attackers &= attackers - 1;
         const int vj = g.bc(victim, j), aj = g.bc(dealt, j);
-        if (vj == l) { taken += aj; if (j < 2 && aj > 0) credit |= 1 << j; }
+        if (vj == l) { taken += aj; if (j < 2) credit |= 1 << j; }
     }
     // 5. apply
     if (l < 2 && spend) L.aux -= min(L.aux, L.max_mana / 3);
@@ -229,6 +231,7 @@ __device__ __forceinline__ int r1_tick(const R1Params& P, const Grp g, R1Lane& L
         if (!can) continue;
         const int px = g.bc(L.x, p), py = g.bc(L.y, p), pd = g.bc(L.depth, p);
         const bool here = l >= NM && l < NM + ORX_R1_ITEMS && L.alive && L.depth == pd && L.x == px && L.y == py;
+        if (g.ballot(here) == 0) continue;
 #pragma unroll
         for (int i = NM; i < NM + ORX_R1_ITEMS; ++i) {
             const bool hit = g.bc((int)here, i) != 0;
@@ -265,11 +268,12 @@ __device__ __forceinline__ int r1_tick(const R1Params& P, const Grp g, R1Lane& L
     {
         const int d0 = g.bc(L.depth, 0), d1 = g.bc(L.depth, 1);
         if (l >= 2 && L.alive && L.depth != d0 && L.depth != d1) L.alive = 0;
+        uint4 sb = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+        if ((L.tick & 3) == 0) sb = draw_block(s, DOM_TICK, SUB_SPAWN, (uint32_t)L.tick);   // spawn roll every 4th tick
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             if (p == 1 && d1 == d0) continue;
-            const uint4 b = draw_block(s, DOM_TICK, SUB_SPAWN + (uint32_t)p, (uint32_t)L.tick);
-            if (b.x >= (1u << 28)) continue;
+            if ((p == 0 ? sb.x : sb.y) >= (1u << 30)) continue;
             const uint32_t freee = g.ballot(l >= 2 && mover && !L.alive);
             if (freee == 0) continue;
             const int slot = __ffs(freee) - 1;
@@ -381,7 +385,10 @@ k_r1_reset(const __grid_constant__ R1Params P, const uint8_t* __restrict__ mask,
     store_group(P, g, game, L, ORX_RESULT_IN_PROGRESS);
 }
 
-__global__ void __launch_bounds__(kThreadsR1)
+#ifndef ORX_R1_MINBLOCKS
+#define ORX_R1_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kThreadsR1, ORX_R1_MINBLOCKS)
 k_r1_step(const __grid_constant__ R1Params P, const uint8_t* __restrict__ moves, uint8_t* __restrict__ result)
 {
     const Grp g = make_group();
@@ -411,7 +418,7 @@ __device__ __forceinline__ unsigned int warp_sum(unsigned int v)
     return v;
 }
 
-__global__ void __launch_bounds__(kThreadsR1)
+__global__ void __launch_bounds__(kThreadsR1, ORX_R1_MINBLOCKS)
 k_r1_rollout(const __grid_constant__ R1Params P, int n_ticks, unsigned long long* __restrict__ stats)
 {
     __shared__ unsigned int s_cnt[ORX_STAT_COUNT];

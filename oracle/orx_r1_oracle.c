@@ -259,11 +259,11 @@ static int r1_tick(G* g, int c1, int c2)
     /* 7. vanish + spawn */
     for (int l = 2; l < NM + ORX_R1_ITEMS; ++l)
         if (g->e[l].alive && g->e[l].depth != g->e[0].depth && g->e[l].depth != g->e[1].depth) g->e[l].alive = 0;
+    uint32_t sw[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0 };
+    if (g->tick % 4 == 0) draw_block(&g->rng, DOM_TICK, SUB_SPAWN, (uint32_t)g->tick, sw);
     for (int p = 0; p < 2; ++p) {
         if (p == 1 && g->e[1].depth == g->e[0].depth) continue;
-        uint32_t w[4];
-        draw_block(&g->rng, DOM_TICK, SUB_SPAWN + p, (uint32_t)g->tick, w);
-        if (w[0] >= (1u << 28)) continue;
+        if (sw[p] >= (1u << 30)) continue;
         int slot = -1;
         for (int m = 2; m < NM; ++m) if (!g->e[m].alive) { slot = m; break; }
         if (slot < 0) continue;
