@@ -133,6 +133,17 @@ def sim_config(auto_reset=True):
 
 
 # ------------------------------------------------------------------------------------------ CPU side
+def cpu_port_run_isolated(n_games, seconds):
+    """cpu_port_run in a child process whose environment lets OpenMP use every host core (launchers
+    such as torchrun export OMP_NUM_THREADS=1, which libgomp honours even after omp_set_num_threads
+    once it has been initialised that way inside a Python process)."""
+    env = {k: v for k, v in os.environ.items() if not k.startswith('OMP_') and k != 'GOMP_CPU_AFFINITY'}
+    code = ('import json, sys; sys.path.insert(0, %r); import bench; '
+            'print(json.dumps(bench.cpu_port_run(%d, %f)))' % (ROOT, n_games, seconds))
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, check=True).stdout
+    return tuple(json.loads(out.strip().splitlines()[-1]))
+
+
 def cpu_port_run(n_games, seconds, steps=None, game_id_base=0):
     """Times the C restatement (OpenMP, all cores) ticking ``n_games`` games with RandomBot commands.
     Returns (ticks_per_s, cores, ticks_done, elapsed)."""
@@ -208,6 +219,7 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     G, K, W = args.games_per_gpu, args.steps, args.warmup
@@ -400,8 +412,8 @@ def run_b200(args, rank, local_rank, world):
                    'rollout_value': world * 4 * G1 * 64 / (ms_r1_roll * 1e-3)},
             'clocks': sampler.summary(t_wall0, t_wall1),
         }
-        if not args.no_cpu_baseline:
-            v, cores, ticks, el = cpu_port_run(1 << 18, args.cpu_seconds)
+        if not args.no_cpu_baseline and world == 1:     # CPU baseline: rank 0 at N=1 only (other ranks would spin on host cores)
+            v, cores, ticks, el = cpu_port_run_isolated(1 << 18, args.cpu_seconds)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': f'{ticks} game-ticks in {el:.1f} s: 2^18 games, same config, oracle/orx_oracle.c oro_rollout (RandomBot x2), OpenMP over all host cores'}
         print(json.dumps(line), flush=True)
@@ -421,6 +433,11 @@ def main():
                '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
     if args.impl == 'reference':
+        if rank == 0 and any(k.startswith('OMP_') for k in os.environ) and '_ORX_BENCH_CHILD' not in os.environ:
+            # torchrun exports OMP_NUM_THREADS=1: re-run rank 0's measurement with every host core
+            env = {k: v for k, v in os.environ.items() if not k.startswith('OMP_')}
+            env['_ORX_BENCH_CHILD'] = '1'
+            sys.exit(subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env))
         run_reference(args, rank, world)
     else:
         run_b200(args, rank, local_rank, world)
