@@ -286,15 +286,17 @@ def run_b200(args, rank, local_rank, world):
             hm.copy_(moves[0].cpu())
         host_res = torch.empty((G,), dtype=torch.uint8, pin_memory=True)
         k_e2e = max(10, min(K, 200))
+        # one bound stepper per (batch, command buffer): BatchedUpdater.host_stepper is the public call for
+        # host-side loops; each step() = H2D commands + tick + D2H results + stream sync
+        steppers = [upd.host_stepper(batches[k % n_batches], host_moves[k % 4], host_res)
+                    for k in range(min(k_e2e, 4 * n_batches))]
         for k in range(3):
-            upd.update(batches[k % n_batches], host_moves[k % 4], out=host_res)
-            stream.synchronize()
+            steppers[k % len(steppers)]()
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record(stream)
         for k in range(k_e2e):
-            upd.update(batches[k % n_batches], host_moves[k % 4], out=host_res)
-            stream.synchronize()          # the caller reads host_res here
+            steppers[k % len(steppers)]()  # synchronous: the caller can read host_res after each call
         e3.record(stream)
         torch.cuda.synchronize(dev)
         barrier()
@@ -399,7 +401,7 @@ def run_b200(args, rank, local_rank, world):
                          'games_per_launch': G},
             'e2e': {'value': world * G * k_e2e / (ms_e2e * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': 2 * G, 'd2h_bytes_per_step': G, 'steps': k_e2e,
-                    'api': 'BatchedUpdater.update(state, pinned host uint8[N,2]) -> pinned host uint8[N] (orx_step_host: commands and results cross PCIe inside the tick kernel), sync every step'},
+                    'api': 'BatchedUpdater.host_stepper(state, pinned host uint8[N,2], pinned host uint8[N])() = orx_step_host_sync: commands and results cross PCIe inside the tick kernel, stream sync every step'},
             'gpu_launches': K,
             'rollout': {'value': roll_ticks_all / (ms_roll * 1e-3), 'unit': UNIT, 'ticks_per_launch': T,
                         'launches': r_launches, 'fused': True,

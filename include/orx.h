@@ -21,7 +21,8 @@
  *                   StaircaseBot.move  optimax_rogue_bots/staircasebot.py:9-20
  *   orx_rollout     the tick loop  optimax_rogue/server/main.py:110-113 with both bots inlined
  *   orx_observe     GameState.view_for  optimax_rogue/game/state.py:53-58
- *   orx_step_host   orx_step with host command/result buffers (what a remote caller holds)
+ *   orx_step_host   orx_step with host command/result buffers (what a remote caller holds);
+ *   orx_step_host_sync  the same plus a stream synchronisation (Server.update returns the result, server.py:132-138)
  *
  * Integer codes are the reference's enum values and must not change.
  */
@@ -153,6 +154,13 @@ int orx_step(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uin
 int orx_step_host(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
                   uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
                   uint64_t game_id_base, void* cuda_stream);
+
+/* orx_step_host followed by a synchronisation of cuda_stream: on return result_host holds this
+ * tick's results. One call per tick for a host-side loop that needs the results before it can
+ * choose the next commands. */
+int orx_step_host_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
+                       uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
+                       uint64_t game_id_base, void* cuda_stream);
 
 /* Command generation for scripted bots; ORX_BOT_NONE leaves that player's byte untouched. */
 int orx_bot_moves(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2,

@@ -90,6 +90,8 @@ PROTOTYPES = {
                            C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_step_host': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step_host_sync': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_bot_moves': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_int, C.c_int,
                                 C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_rollout': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_int, C.c_int, C.c_int,

@@ -328,14 +328,24 @@ template <int DGEN>
 int launch_pipe(const Params& P, const uint16_t* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, cudaStream_t s)
 {
     const size_t smem = pipe_smem_bytes((int)tiles_bytes);
-    int dev = 0, sms = 148, per_sm = 2;
+    // Launch geometry depends only on (device, kernel, smem): look it up once per process, the
+    // occupancy query costs more than the launch itself. (A cache of device properties, not state.)
+    static int cache_sms[64] = {0}, cache_per_sm[64][2] = {{0}};
+    static size_t cache_smem[64][2] = {{0}};
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (smem > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(k_step_pipe<DGEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e);
+    const int slot = dev & 63, kd = DGEN == ORX_DGEN_EMPTY ? 0 : 1;
+    if (cache_sms[slot] == 0 || cache_smem[slot][kd] != smem || cache_per_sm[slot][kd] == 0) {
+        int sms = 148, per_sm = 2;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (smem > 48 * 1024) {
+            const cudaError_t e = cudaFuncSetAttribute(k_step_pipe<DGEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e);
+        }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_pipe<DGEN>, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cache_per_sm[slot][kd] = per_sm; cache_smem[slot][kd] = smem; cache_sms[slot] = sms;
     }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_pipe<DGEN>, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int sms = cache_sms[slot], per_sm = cache_per_sm[slot][kd];
     unsigned int grid = (unsigned int)sms * (unsigned int)per_sm;       // persistent: every CTA resident
     if (grid > n_tiles) grid = n_tiles;
     cudaLaunchConfig_t lc = {};
@@ -447,6 +457,16 @@ int orx_step_host(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves
     const int rs = orx_step(cfg, st, moves_dev, result_dev, nullptr, n, game_id_base, cuda_stream);
     if (rs != ORX_OK) return rs;
     e = cudaMemcpyAsync(result_host, result_dev, (size_t)n, cudaMemcpyDeviceToHost, s);
+    return e == cudaSuccess ? ORX_OK : cuda_fail(e);
+}
+
+int orx_step_host_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
+                       uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
+                       uint64_t game_id_base, void* cuda_stream)
+{
+    const int rc = orx_step_host(cfg, st, moves_host, result_host, moves_dev, result_dev, n, game_id_base, cuda_stream);
+    if (rc != ORX_OK) return rc;
+    const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
     return e == cudaSuccess ? ORX_OK : cuda_fail(e);
 }
 

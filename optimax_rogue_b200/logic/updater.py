@@ -31,6 +31,22 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _on_device:
+    """``torch.cuda.device(dev)`` only when dev is not already current (the context manager costs
+    several microseconds per call, which matters for the per-step host path)."""
+
+    def __init__(self, device):
+        self.ctx = None if torch.cuda.current_device() == (device.index or 0) else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
 def _require_cuda(gs: BatchedGameState):
     if gs.device.type != 'cuda':
         raise RuntimeError('BatchedGameState must live on a CUDA device: there is no CPU fallback')
@@ -46,7 +62,7 @@ def reset_games(gs: BatchedGameState, mask: typing.Optional[torch.Tensor] = None
     if mask is not None:
         mask = mask.to(device=gs.device, dtype=torch.uint8).contiguous()
         mptr = mask.data_ptr()
-    with torch.cuda.device(gs.device):
+    with _on_device(gs.device):
         rc = _lib.lib().orx_reset(C.byref(cfg), C.byref(st), mptr, int(bump_episode), gs.n,
                                   gs.game_id_base, _stream_ptr(gs.device))
     _lib.check(rc, 'orx_reset')
@@ -86,6 +102,10 @@ class BatchedUpdater:
 
     @staticmethod
     def _as_moves(gs, player1_move, player2_move):
+        if (player2_move is None and isinstance(player1_move, torch.Tensor) and player1_move.dtype == torch.uint8
+                and player1_move.dim() == 2 and player1_move.shape[0] == gs.n and player1_move.shape[1] == 2
+                and player1_move.is_contiguous()):
+            return player1_move                       # fast path: already a uint8[N,2] command block
         if player2_move is None:
             mv = player1_move
         else:
@@ -121,7 +141,7 @@ class BatchedUpdater:
         if want_events:
             events = torch.empty((gs.n, _abi.MAX_EVENTS_BASE + gs.cfg.n_npc, 2), dtype=torch.int32,
                                  device=gs.device)
-        with torch.cuda.device(gs.device):
+        with _on_device(gs.device):
             rc = _lib.lib().orx_step(C.byref(cfg), C.byref(st), mv.data_ptr(), result.data_ptr(),
                                      events.data_ptr() if events is not None else None, gs.n,
                                      gs.game_id_base, _stream_ptr(gs.device))
@@ -136,13 +156,44 @@ class BatchedUpdater:
             self._stage = (torch.empty((gs.n, 2), dtype=torch.uint8, device=gs.device),
                            torch.empty((gs.n,), dtype=torch.uint8, device=gs.device))
         result_host = out if out is not None else torch.empty((gs.n,), dtype=torch.uint8, pin_memory=True)
-        with torch.cuda.device(gs.device):
+        with _on_device(gs.device):
             rc = _lib.lib().orx_step_host(C.byref(cfg), C.byref(st), moves_host.data_ptr(),
                                           result_host.data_ptr(), self._stage[0].data_ptr(),
                                           self._stage[1].data_ptr(), gs.n, gs.game_id_base,
                                           _stream_ptr(gs.device))
         _lib.check(rc, 'orx_step_host')
         return result_host
+
+    def host_stepper(self, game_state: BatchedGameState, moves_host: torch.Tensor, result_host: torch.Tensor):
+        """Binds one game state and a pair of HOST buffers (pin them: ``pin_memory()``) and returns
+        ``step()``: one call = one tick with the commands currently in ``moves_host``; when it returns,
+        ``result_host`` holds the tick's UpdateResult codes (``orx_step_host_sync``). This is
+        ``update(gs, moves_host, out=result_host)`` + stream synchronise with the per-call argument
+        marshalling done once, for host loops that tick every few tens of microseconds."""
+        gs = game_state
+        _require_cuda(gs)
+        if (moves_host.is_cuda or result_host.is_cuda or moves_host.dtype != torch.uint8 or result_host.dtype != torch.uint8
+                or tuple(moves_host.shape) != (gs.n, 2) or tuple(result_host.shape) != (gs.n,)
+                or not moves_host.is_contiguous() or not result_host.is_contiguous()):
+            raise ValueError(f'need contiguous CPU uint8 tensors of shape ({gs.n}, 2) and ({gs.n},)')
+        cfg, st = self._cfg(gs)
+        stage = (torch.empty((gs.n, 2), dtype=torch.uint8, device=gs.device),
+                 torch.empty((gs.n,), dtype=torch.uint8, device=gs.device))
+        fn = _lib.lib().orx_step_host_sync
+        args = (C.byref(cfg), C.byref(st), C.c_void_p(moves_host.data_ptr()), C.c_void_p(result_host.data_ptr()),
+                C.c_void_p(stage[0].data_ptr()), C.c_void_p(stage[1].data_ptr()), C.c_int64(gs.n),
+                C.c_uint64(gs.game_id_base), C.c_void_p(_stream_ptr(gs.device)))
+        keep = (cfg, st, stage, moves_host, result_host, gs)
+        dev_index = gs.device.index or 0
+
+        def step():
+            if torch.cuda.current_device() != dev_index:
+                torch.cuda.set_device(dev_index)
+            rc = fn(*args)
+            if rc != 0:
+                _lib.check(rc, 'orx_step_host_sync')
+            return keep[4]
+        return step
 
     def _advance_order(self, gs, events):
         if self.current_update_order is None:
@@ -161,7 +212,7 @@ class BatchedUpdater:
         _require_cuda(gs)
         cfg, st = self._cfg(gs)
         moves = out if out is not None else torch.full((gs.n, 2), 5, dtype=torch.uint8, device=gs.device)
-        with torch.cuda.device(gs.device):
+        with _on_device(gs.device):
             rc = _lib.lib().orx_bot_moves(C.byref(cfg), C.byref(st), int(bot_p1), int(bot_p2),
                                           moves.data_ptr(), gs.n, gs.game_id_base, _stream_ptr(gs.device))
         _lib.check(rc, 'orx_bot_moves')
@@ -176,7 +227,7 @@ class BatchedUpdater:
         cfg, st = self._cfg(gs)
         if stats is None:
             stats = torch.zeros((_abi.STAT_COUNT,), dtype=torch.int64, device=gs.device)
-        with torch.cuda.device(gs.device):
+        with _on_device(gs.device):
             rc = _lib.lib().orx_rollout(C.byref(cfg), C.byref(st), int(bot_p1), int(bot_p2), int(n_ticks),
                                         stats.data_ptr(), gs.n, gs.game_id_base, _stream_ptr(gs.device))
         _lib.check(rc, 'orx_rollout')
@@ -190,7 +241,7 @@ class BatchedUpdater:
         _require_cuda(gs)
         cfg, st = self._cfg(gs)
         obs = out if out is not None else torch.empty((gs.n, 2, _abi.OBS_LEN), dtype=torch.int16, device=gs.device)
-        with torch.cuda.device(gs.device):
+        with _on_device(gs.device):
             rc = _lib.lib().orx_observe(C.byref(cfg), C.byref(st), obs.data_ptr(), int(stairs_radius),
                                         gs.n, _stream_ptr(gs.device))
         _lib.check(rc, 'orx_observe')

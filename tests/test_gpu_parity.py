@@ -189,6 +189,29 @@ def test_step_host_buffers():
     gu.assert_state_equal(gs, orc, 'host path')
 
 
+def test_host_stepper_matches_oracle():
+    cfg = SimConfig(max_ticks=50, seed=6, auto_reset=True)
+    gs, upd, orc = gu.make_pair(cfg, 2500)
+    host_moves = torch.empty((2500, 2), dtype=torch.uint8, pin_memory=True)
+    host_res = torch.empty((2500,), dtype=torch.uint8, pin_memory=True)
+    step = upd.host_stepper(gs, host_moves, host_res)
+    for t in range(70):
+        mv = orc.bot_moves(2, 1)
+        host_moves.copy_(torch.from_numpy(mv))
+        res = step()                                  # synchronous: results are on the host on return
+        res_o, _ = orc.step(mv)
+        assert np.array_equal(res.numpy(), res_o)
+    gu.assert_state_equal(gs, orc, 'host stepper')
+    # pageable buffers take the staged-copy path and must agree as well
+    pm, pr = torch.empty((2500, 2), dtype=torch.uint8), torch.empty((2500,), dtype=torch.uint8)
+    step2 = upd.host_stepper(gs, pm, pr)
+    for t in range(20):
+        mv = orc.bot_moves(1, 1)
+        pm.copy_(torch.from_numpy(mv))
+        assert np.array_equal(step2().numpy(), orc.step(mv)[0])
+    gu.assert_state_equal(gs, orc, 'host stepper, pageable')
+
+
 def test_observe():
     cfg = SimConfig(max_ticks=0, seed=4)
     gs, upd, orc = gu.make_pair(cfg, 2000)
