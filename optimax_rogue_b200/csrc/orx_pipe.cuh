@@ -22,7 +22,10 @@
 
 namespace orx {
 
-constexpr int kTile = 256;            // games per tile = compute threads per CTA
+#ifndef ORX_PIPE_TILE
+#define ORX_PIPE_TILE 256
+#endif
+constexpr int kTile = ORX_PIPE_TILE;  // games per tile = compute threads per CTA
 #ifndef ORX_PIPE_STAGES
 #define ORX_PIPE_STAGES 4
 #endif
@@ -36,10 +39,12 @@ constexpr int kStages = ORX_PIPE_STAGES;
 constexpr int kPipeThreads = kTile + 32;   // + one producer warp
 
 // byte offsets of the plane slices inside a stage (all multiples of 16)
-constexpr uint32_t OFF_POS = 0, OFF_HP = 1024, OFF_ST = 2048, OFF_TICK = 3072, OFF_EP = 4096,
-                   OFF_DEPTH = 5120, OFF_STATUS = 7168, OFF_MOVES = 7424, OFF_RESULT = 7936,
-                   STAGE_BYTES = 8192;
-constexpr uint32_t LOAD_BYTES = 5 * 1024 + 2048 + 256 + 512;   // per tile, HBM -> smem
+constexpr uint32_t T4 = 4u * kTile, T8 = 8u * kTile, T2 = 2u * kTile, T1 = kTile;   // slice sizes in bytes
+constexpr uint32_t OFF_POS = 0, OFF_HP = T4, OFF_ST = 2 * T4, OFF_TICK = 3 * T4, OFF_EP = 4 * T4,
+                   OFF_DEPTH = 5 * T4, OFF_STATUS = 5 * T4 + T8, OFF_MOVES = OFF_STATUS + T1, OFF_RESULT = OFF_MOVES + T2,
+                   STAGE_BYTES = OFF_RESULT + T1;
+constexpr uint32_t LOAD_BYTES = 5 * T4 + T8 + T1 + T2;          // per tile, HBM -> smem
+static_assert(kTile % 32 == 0 && (T1 % 16) == 0, "bulk copies move multiples of 16 bytes");
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -128,14 +133,14 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
             const size_t g = ((size_t)blockIdx.x + (size_t)it * gridDim.x) * kTile;     // first game of the tile
             const uint32_t bar = full0 + 8 * s, base = stage0 + s * STAGE_BYTES;
             mbar_expect_tx(bar, LOAD_BYTES);
-            bulk_load(base + OFF_POS, P.pos + g, 1024, bar);
-            bulk_load(base + OFF_HP, P.hp + g, 1024, bar);
-            bulk_load(base + OFF_ST, P.stairs + g, 1024, bar);
-            bulk_load(base + OFF_TICK, P.tick + g, 1024, bar);
-            bulk_load(base + OFF_EP, P.episode + g, 1024, bar);
-            bulk_load(base + OFF_DEPTH, P.depth + g, 2048, bar);
-            bulk_load(base + OFF_STATUS, P.status + g, 256, bar);
-            bulk_load(base + OFF_MOVES, moves + g, 512, bar);
+            bulk_load(base + OFF_POS, P.pos + g, T4, bar);
+            bulk_load(base + OFF_HP, P.hp + g, T4, bar);
+            bulk_load(base + OFF_ST, P.stairs + g, T4, bar);
+            bulk_load(base + OFF_TICK, P.tick + g, T4, bar);
+            bulk_load(base + OFF_EP, P.episode + g, T4, bar);
+            bulk_load(base + OFF_DEPTH, P.depth + g, T8, bar);
+            bulk_load(base + OFF_STATUS, P.status + g, T1, bar);
+            bulk_load(base + OFF_MOVES, moves + g, T2, bar);
         };
         if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // all earlier work in the stream is complete and visible
         const unsigned int pre = my_tiles < (unsigned)kStages ? my_tiles : (unsigned)kStages;
@@ -145,14 +150,14 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
             mbar_wait(done0 + 8 * s, (it / kStages) & 1u);
             const size_t g = ((size_t)blockIdx.x + (size_t)it * gridDim.x) * kTile;
             const uint32_t base = stage0 + s * STAGE_BYTES;
-            bulk_store(P.pos + g, base + OFF_POS, 1024);
-            bulk_store(P.hp + g, base + OFF_HP, 1024);
-            bulk_store(P.stairs + g, base + OFF_ST, 1024);
-            bulk_store(P.tick + g, base + OFF_TICK, 1024);
-            bulk_store(P.episode + g, base + OFF_EP, 1024);
-            bulk_store(P.depth + g, base + OFF_DEPTH, 2048);
-            bulk_store(P.status + g, base + OFF_STATUS, 256);
-            bulk_store(result + g, base + OFF_RESULT, 256);
+            bulk_store(P.pos + g, base + OFF_POS, T4);
+            bulk_store(P.hp + g, base + OFF_HP, T4);
+            bulk_store(P.stairs + g, base + OFF_ST, T4);
+            bulk_store(P.tick + g, base + OFF_TICK, T4);
+            bulk_store(P.episode + g, base + OFF_EP, T4);
+            bulk_store(P.depth + g, base + OFF_DEPTH, T8);
+            bulk_store(P.status + g, base + OFF_STATUS, T1);
+            bulk_store(result + g, base + OFF_RESULT, T1);
             bulk_commit();
             if (it + kStages < my_tiles) {
                 bulk_wait_read_all();              // the stage has been read out: safe to overwrite

@@ -310,25 +310,35 @@ __device__ __forceinline__ int r1_tick(const R1Params& P, const Grp g, R1Lane& L
     return res;
 }
 
+__device__ __forceinline__ uint32_t ldg32(const void* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// All of a lane's loads are issued back to back (asm volatile keeps ptxas from sinking them below
+// the first use), so one DRAM round trip covers the whole group state.
 __device__ __forceinline__ void load_group(const R1Params& P, const Grp g, unsigned int game, R1Lane& L)
 {
     const size_t e = (size_t)game * 16 + g.l;
-    const uint32_t loc = P.ent_loc[e], stat = P.ent_stat[e];
-    L.x = loc & 255; L.y = (loc >> 8) & 255; L.alive = (loc >> 16) & 1; L.depth = P.ent_depth[e];
+    const size_t q = (size_t)game * 2 + (g.l & 1);          // lanes >= 2 read a valid word and drop it
+    const uint32_t loc = ldg32(P.ent_loc + e), stat = ldg32(P.ent_stat + e), dep = ldg32(P.ent_depth + e);
+    const uint32_t a = ldg32(P.pl_a + q), b = ldg32(P.pl_b + q), c = ldg32(P.pl_c + q);
+    const uint32_t sw = ldg32(P.lvl_stairs + game), k0 = ldg32(P.lvl_key + (size_t)game * 2), k1 = ldg32(P.lvl_key + (size_t)game * 2 + 1);
+    const uint32_t sep = ldg32(P.sep + game), tick = ldg32(P.tick + game), ep = ldg32(P.episode + game);
+    L.x = loc & 255; L.y = (loc >> 8) & 255; L.alive = (loc >> 16) & 1; L.depth = (int)dep;
     L.hp = (int)(int16_t)(stat & 0xFFFF);
     L.aux = g.l >= NM ? (int)((loc >> 17) & 3) : (int)(int16_t)(stat >> 16);
     L.max_hp = L.max_mana = L.xp = L.level = L.n_items = L.cd = L.damage = L.armor = 0;
     if (g.l < 2) {
-        const size_t q = (size_t)game * 2 + g.l;
-        const uint32_t a = P.pl_a[q], b = P.pl_b[q], c = P.pl_c[q];
         L.max_hp = (int)(int16_t)(a & 0xFFFF); L.max_mana = (int)(int16_t)(a >> 16);
         L.xp = b & 255; L.level = (b >> 8) & 255; L.n_items = (b >> 16) & 255; L.cd = b >> 24;
         L.damage = c & 255; L.armor = (c >> 8) & 255;
     }
-    const uint32_t sw = P.lvl_stairs[game];
     L.sx0 = sw & 255; L.sy0 = (sw >> 8) & 255; L.sx1 = (sw >> 16) & 255; L.sy1 = sw >> 24;
-    L.key0 = P.lvl_key[(size_t)game * 2]; L.key1 = P.lvl_key[(size_t)game * 2 + 1];
-    L.sep = (int)P.sep[game]; L.tick = P.tick[game]; L.episode = P.episode[game];
+    L.key0 = k0; L.key1 = k1;
+    L.sep = (int)sep; L.tick = (int)tick; L.episode = ep;
 }
 
 __device__ __forceinline__ void store_group(const R1Params& P, const Grp g, unsigned int game, const R1Lane& L, int status)
@@ -394,13 +404,15 @@ k_r1_step(const __grid_constant__ R1Params P, const uint8_t* __restrict__ moves,
     const Grp g = make_group();
     const unsigned int game = (blockIdx.x * kThreadsR1 + threadIdx.x) >> 4;
     if (game >= P.n) return;
-    const int status = P.status[game];
-    if (status != ORX_RESULT_IN_PROGRESS) { if (g.l == 0) result[game] = (uint8_t)status; return; }
     R1Lane L;
     load_group(P, g, game, L);
+    uint32_t mvw, status;
+    asm volatile("ld.global.u16 %0, [%1];" : "=r"(mvw) : "l"(moves + 2 * (size_t)game));
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(status) : "l"(P.status + game));
+    if (status != ORX_RESULT_IN_PROGRESS) { if (g.l == 0) result[game] = (uint8_t)status; return; }
     Stream s = make_stream(P, game, L.episode);
     R1Counters cnt{};
-    int res = r1_tick(P, g, L, s, moves[2 * (size_t)game], moves[2 * (size_t)game + 1], cnt);
+    int res = r1_tick(P, g, L, s, (int)(mvw & 255u), (int)(mvw >> 8), cnt);
     if (g.l == 0) result[game] = (uint8_t)res;
     if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
         L.episode += 1;
