@@ -54,3 +54,36 @@ def test_ten_thousand_replayed_episodes_bit_exact(suite, fused_bots):
     assert len(bad) == 0, f'{len(bad)} of {n} episodes differ from the reference, first {bad[:5]}'
     hist = {str(k): int((p['status'] == k).sum()) for k in (2, 3, 4)}
     assert hist == kw['result_hist']
+
+
+def test_truth_table_through_the_cuda_path():
+    """The 400-row two-player resolution table recorded from the live reference (8 placements x 25
+    command pairs x 2 initiative orders): positions, health and the ordered events."""
+    from optimax_rogue_b200 import _abi
+    from optimax_rogue_b200.logic.worldgen import FixedDungeonGenerator
+    from optimax_rogue_b200.logic.updates import unpack_events
+    rows = json.load(open(os.path.join(GOLD, 'truth_table.json')))
+    tiles = np.full((9, 9), 1, np.uint8)
+    tiles[[0, -1], :] = 2
+    tiles[:, [0, -1]] = 2
+    cfg = SimConfig(width=9, height=9, dgen_kind=_abi.DGEN_FIXED, fixed_tiles=tiles, seed=0x0A11CE)
+    upd = BatchedUpdater(FixedDungeonGenerator(tiles), 1, None)
+    by_gid = {}
+    for row in rows:
+        by_gid.setdefault(row['gid'], []).append(row)
+    assert len(by_gid) == 2
+    for gid, group in by_gid.items():
+        for row in group:
+            gs = BatchedGameState(cfg, 1, 'cuda', game_id_base=gid)
+            reset_games(gs)
+            dx, dy = row['placement']
+            gs.pos.copy_(torch.tensor([[4, 4, 4 + dx, 4 + dy]], dtype=torch.uint8))
+            mv = torch.tensor([[row['m1'], row['m2']]], dtype=torch.uint8, device='cuda')
+            res, ev = upd.update(gs, mv, want_events=True)
+            p = gs.planes_cpu()
+            ent = [[int(p['pos'][0, 0]), int(p['pos'][0, 1]), int(p['depth'][0, 0]), int(p['hp'][0, 0])],
+                   [int(p['pos'][0, 2]), int(p['pos'][0, 3]), int(p['depth'][0, 1]), int(p['hp'][0, 1])]]
+            assert ent == row['ent'], row
+            assert int(res[0]) == row['result']
+            evs = [list(map(int, e)) for e in unpack_events(ev)[0] if e[0] != 0]
+            assert evs == row['events'], (row, evs)

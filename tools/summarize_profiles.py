@@ -91,8 +91,20 @@ def main():
     with open(os.path.join(PROF, 'roofline_traffic.json'), 'w') as f:
         json.dump(traffic, f, indent=1)
     print(traffic)
-    if len(sys.argv) > 4:
-        summarize_report(sys.argv[4], tag, 'k_rollout')
+    for extra in sys.argv[4:]:
+        name = os.path.basename(extra).replace('.ncu-rep', '').replace('prof_', '').replace('_' + tag, '')
+        rep = summarize_report(extra, tag, name)
+        if 'step16m' in name:
+            rd16 = [to_bytes(*l['dram__bytes_read.sum']) for l in rep]
+            wr16 = [to_bytes(*l['dram__bytes_write.sum']) for l in rep]
+            traffic['large_batch_check'] = {
+                'games_per_launch': 1 << 24, 'dram_bytes_read_per_launch': sum(rd16) / len(rd16),
+                'dram_bytes_write_per_launch': sum(wr16) / len(wr16),
+                'bytes_per_game': (sum(rd16) + sum(wr16)) / len(rd16) / (1 << 24),
+                'note': '2^24 games per launch (512 MB of planes, 4x the L2): written planes must spill to DRAM '
+                        'inside the profiled window, so read+write per game can be compared with the 61 B algorithmic figure'}
+            with open(os.path.join(PROF, 'roofline_traffic.json'), 'w') as f:
+                json.dump(traffic, f, indent=1)
 
 
 if __name__ == '__main__':
