@@ -85,6 +85,13 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int2 lds_s32x2(uint32_t a) { int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32x2(uint32_t a, int x, int y) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // n_tiles full tiles of kTile games; the caller handles a ragged tail with the simple kernel.
@@ -169,19 +176,23 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
     }
 
     // ---------------------------------------------------------------- consumers (8 warps)
-    for (unsigned int it = 0; it < my_tiles; ++it) {
+    // Shared-memory addresses are formed once, as 32-bit shared-window offsets, and pinned with an
+    // empty asm so ptxas keeps them in registers instead of re-deriving them (S2R + LEA chains)
+    // every tile.
+    uint32_t a4 = stage0 + tid * 4u;            // this thread's slot in the 4-byte slices of stage 0
+    uint32_t lane = blockIdx.x * kTile + tid;   // game index inside the launch
+    uint32_t lane_step = gridDim.x * kTile;
+    asm volatile("" : "+r"(a4), "+r"(lane), "+r"(lane_step));
+    for (unsigned int it = 0; it < my_tiles; ++it, lane += lane_step) {
         const unsigned int s = it % kStages;
-        uint8_t* st = stages + s * STAGE_BYTES;
+        const uint32_t b4 = a4 + s * STAGE_BYTES, b8 = b4 + tid * 4u, b1 = b4 - tid * 3u, b2 = b4 - tid * 2u;
         mbar_wait(full0 + 8 * s, (it / kStages) & 1u);
-        const uint32_t pos = reinterpret_cast<const uint32_t*>(st + OFF_POS)[tid];
-        const uint32_t hpw = reinterpret_cast<const uint32_t*>(st + OFF_HP)[tid];
-        const uint32_t stw = reinterpret_cast<const uint32_t*>(st + OFF_ST)[tid];
-        const int tick = reinterpret_cast<const int*>(st + OFF_TICK)[tid];
-        const uint32_t ep = reinterpret_cast<const uint32_t*>(st + OFF_EP)[tid];
-        const int2 dep = reinterpret_cast<const int2*>(st + OFF_DEPTH)[tid];
-        const int status = st[OFF_STATUS + tid];
-        const uint32_t mv = reinterpret_cast<const uint16_t*>(st + OFF_MOVES)[tid];
-        const unsigned int lane = (blockIdx.x + it * gridDim.x) * kTile + tid;      // game index in the launch
+        const uint32_t pos = lds_u32(b4 + OFF_POS), hpw = lds_u32(b4 + OFF_HP), stw = lds_u32(b4 + OFF_ST);
+        const int tick = (int)lds_u32(b4 + OFF_TICK);
+        const uint32_t ep = lds_u32(b4 + OFF_EP);
+        const int2 dep = lds_s32x2(b8 + OFF_DEPTH);
+        const int status = (int)lds_u8(b1 + OFF_STATUS);
+        const uint32_t mv = lds_u16(b2 + OFF_MOVES);
         int res = status;
         if (status == ORX_RESULT_IN_PROGRESS) {          // finished lanes are frozen until reset
             Lane L;
@@ -197,16 +208,15 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
                 reset_lane<DGEN, false>(P, L, rs, lane);
                 new_status = ORX_RESULT_IN_PROGRESS;
             }
-            const uint32_t new_hp = ((uint32_t)L.hp1 & 0xFFFFu) | ((uint32_t)L.hp2 << 16);
-            reinterpret_cast<uint32_t*>(st + OFF_POS)[tid] = L.pos;
-            reinterpret_cast<uint32_t*>(st + OFF_HP)[tid] = new_hp;
-            reinterpret_cast<uint32_t*>(st + OFF_ST)[tid] = L.st;
-            reinterpret_cast<int*>(st + OFF_TICK)[tid] = L.tick;
-            reinterpret_cast<uint32_t*>(st + OFF_EP)[tid] = L.episode;
-            reinterpret_cast<int2*>(st + OFF_DEPTH)[tid] = make_int2(L.d1, L.d2);
-            st[OFF_STATUS + tid] = (uint8_t)new_status;
+            sts_u32(b4 + OFF_POS, L.pos);
+            sts_u32(b4 + OFF_HP, ((uint32_t)L.hp1 & 0xFFFFu) | ((uint32_t)L.hp2 << 16));
+            sts_u32(b4 + OFF_ST, L.st);
+            sts_u32(b4 + OFF_TICK, (uint32_t)L.tick);
+            sts_u32(b4 + OFF_EP, L.episode);
+            sts_s32x2(b8 + OFF_DEPTH, L.d1, L.d2);
+            sts_u8(b1 + OFF_STATUS, (uint32_t)new_status);
         }
-        st[OFF_RESULT + tid] = (uint8_t)res;
+        sts_u8(b1 + OFF_RESULT, (uint32_t)res);
         fence_proxy_async();                 // generic-proxy writes -> visible to the bulk-store engine
         __syncwarp();
         if ((tid & 31u) == 0) mbar_arrive(done0 + 8 * s);
