@@ -220,6 +220,19 @@ int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mov
 int orx_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, unsigned long long* stats,
                    int64_t n, uint64_t game_id_base, void* cuda_stream);
 
+/* Per-player observation for ruleset R1: obs int16[n][2][ORX_R1_OBS_LEN] (GameState.view_for,
+ * game/state.py:53-58, widened to the R1 state; "a ladder ... becomes visible when an agent gets
+ * near it", readme.md:44 -> stairs_radius, Chebyshev, < 0 = always visible).
+ *   0..7   x y depth hp mana cd damage armor        8..15  max_hp max_mana level xp n_items sep tick status
+ *   16..19 opponent: on_my_depth x y hp (else 0 -1 -1 0)        20..22 stairs: visible x y (else 0 -1 -1)
+ *   23..46 enemies 8 x (x y hp) on my depth (else -1 -1 0)      47..58 items 4 x (x y kind) on my depth (else -1)
+ *   59..62 walls of the 7x7 window centred on the player, row-major (dy, dx = -3..3), bit k of word k/16;
+ *          tiles off the map count as walls                       63 reserved (0)
+ * depth, sep and tick saturate at 32767. */
+#define ORX_R1_OBS_LEN 64
+int orx_r1_observe(const OrxR1Config* cfg, const OrxR1State* st, int16_t* obs, int stairs_radius,
+                   int64_t n, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

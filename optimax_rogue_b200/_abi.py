@@ -59,7 +59,7 @@ class OrxEvent(C.Structure):
 
 
 # ---- ruleset R1 (README-only rules; docs/RULESET_R1.md) ------------------------------------------
-R1_LANES, R1_ENEMIES, R1_ITEMS, MOVE_HEAL, R1_STATE_BYTES = 16, 8, 4, 6, 241
+R1_LANES, R1_ENEMIES, R1_ITEMS, MOVE_HEAL, R1_STATE_BYTES, R1_OBS_LEN = 16, 8, 4, 6, 241, 64
 
 
 class OrxR1Config(C.Structure):
@@ -104,6 +104,8 @@ PROTOTYPES = {
                               C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_r1_rollout': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_int, C.c_void_p,
                                  C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_r1_observe': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_void_p, C.c_int,
+                                 C.c_int64, C.c_void_p]),
 }
 
 

@@ -473,6 +473,55 @@ k_r1_rollout(const __grid_constant__ R1Params P, int n_ticks, unsigned long long
     }
 }
 
+// Observation: lanes 0/1 write the scalar block of their player, every entity lane writes its own
+// triple into both players' rows, and the 7x7 wall window is hashed 16 tiles at a time by the
+// whole group -- one ballot is one output word.
+__global__ void __launch_bounds__(kThreadsR1)
+k_r1_observe(const __grid_constant__ R1Params P, int16_t* __restrict__ obs, int radius)
+{
+    const Grp g = make_group();
+    const unsigned int game = (blockIdx.x * kThreadsR1 + threadIdx.x) >> 4;
+    if (game >= P.n) return;
+    R1Lane L;
+    load_group(P, g, game, L);
+    const int status = P.status[game];
+    const int l = g.l;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        int16_t* o = obs + ((size_t)game * 2 + p) * ORX_R1_OBS_LEN;
+        const int mx = g.bc(L.x, p), my = g.bc(L.y, p), md = g.bc(L.depth, p);
+        const int ox = g.bc(L.x, 1 - p), oy = g.bc(L.y, 1 - p), od = g.bc(L.depth, 1 - p), oh = g.bc(L.hp, 1 - p);
+        const int sx = p == 0 ? L.sx0 : L.sx1, sy = p == 0 ? L.sy0 : L.sy1;
+        const uint32_t key = p == 0 ? L.key0 : L.key1;
+        if (l == p) {
+            o[0] = (int16_t)L.x; o[1] = (int16_t)L.y; o[2] = (int16_t)min(L.depth, 32767); o[3] = (int16_t)L.hp;
+            o[4] = (int16_t)L.aux; o[5] = (int16_t)L.cd; o[6] = (int16_t)L.damage; o[7] = (int16_t)L.armor;
+            o[8] = (int16_t)L.max_hp; o[9] = (int16_t)L.max_mana; o[10] = (int16_t)L.level; o[11] = (int16_t)L.xp;
+            o[12] = (int16_t)L.n_items; o[13] = (int16_t)min(L.sep, 32767); o[14] = (int16_t)min(L.tick, 32767); o[15] = (int16_t)status;
+            const bool same = od == md;
+            o[16] = (int16_t)same; o[17] = (int16_t)(same ? ox : -1); o[18] = (int16_t)(same ? oy : -1); o[19] = (int16_t)(same ? oh : 0);
+            const bool vis = radius < 0 || max(abs(sx - mx), abs(sy - my)) <= radius;
+            o[20] = (int16_t)vis; o[21] = (int16_t)(vis ? sx : -1); o[22] = (int16_t)(vis ? sy : -1);
+            o[63] = 0;
+        }
+        const bool here = L.alive && L.depth == md;
+        if (l >= 2 && l < NM) {
+            int16_t* e = o + 23 + 3 * (l - 2);
+            e[0] = (int16_t)(here ? L.x : -1); e[1] = (int16_t)(here ? L.y : -1); e[2] = (int16_t)(here ? L.hp : 0);
+        } else if (l >= NM && l < NM + ORX_R1_ITEMS) {
+            int16_t* e = o + 47 + 3 * (l - NM);
+            e[0] = (int16_t)(here ? L.x : -1); e[1] = (int16_t)(here ? L.y : -1); e[2] = (int16_t)(here ? L.aux : -1);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int t = 16 * r + l;
+            const bool w = t < 49 && is_wall(P, key, sx, sy, mx + t % 7 - 3, my + t / 7 - 3);
+            const uint32_t bits = g.ballot(w);
+            if (l == 0) o[59 + r] = (int16_t)bits;
+        }
+    }
+}
+
 int r1_check(const OrxR1Config* c, const OrxR1State* st, int64_t n)
 {
     if (c == nullptr || st == nullptr || n < 0) return ORX_ERR_BAD_ARG;
@@ -540,6 +589,17 @@ int orx_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, un
     if (n_ticks < 0) return ORX_ERR_BAD_ARG;
     if (n == 0 || n_ticks == 0) return ORX_OK;
     k_r1_rollout<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), n_ticks, stats);
+    return r1_done();
+}
+
+int orx_r1_observe(const OrxR1Config* cfg, const OrxR1State* st, int16_t* obs, int stairs_radius,
+                   int64_t n, void* cuda_stream)
+{
+    const int rc = r1_check(cfg, st, n);
+    if (rc != ORX_OK) return rc;
+    if (obs == nullptr) return ORX_ERR_BAD_ARG;
+    if (n == 0) return ORX_OK;
+    k_r1_observe<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, 0), obs, stairs_radius);
     return r1_done();
 }
 

@@ -69,5 +69,15 @@ class R1GameState:
         _lib.check(rc, 'orx_r1_rollout')
         return stats
 
+    def observe(self, stairs_radius: int = 4, out: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Per-player observation int16[N,2,R1_OBS_LEN] (layout: include/orx.h:orx_r1_observe); the
+        staircase is reported only within ``stairs_radius`` (Chebyshev; < 0 = always)."""
+        obs = out if out is not None else torch.empty((self.n, 2, _abi.R1_OBS_LEN), dtype=torch.int16, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().orx_r1_observe(C.byref(self.cfg), C.byref(self._st), obs.data_ptr(), int(stairs_radius),
+                                           self.n, self._stream())
+        _lib.check(rc, 'orx_r1_observe')
+        return obs
+
     def planes_cpu(self):
         return {name: getattr(self, name).cpu().numpy() for name, _, _ in _abi.R1_PLANES}

@@ -36,6 +36,8 @@ _PROTOS = {
                               C.c_void_p, C.c_int64, C.c_uint64]),
     'oro_r1_rollout': (C.c_int, [C.POINTER(_abi.OrxR1Config), C.POINTER(_abi.OrxR1State), C.c_int,
                                  C.c_void_p, C.c_int64, C.c_uint64]),
+    'oro_r1_observe': (C.c_int, [C.POINTER(_abi.OrxR1Config), C.POINTER(_abi.OrxR1State), C.c_void_p, C.c_int,
+                                 C.c_int64]),
 }
 
 
@@ -211,6 +213,12 @@ class R1Oracle:
         lib().oro_r1_step(C.byref(self.c_cfg), C.byref(st), moves.ctypes.data, result.ctypes.data, self.n,
                           self.game_id_base)
         return result
+
+    def observe(self, radius=4):
+        obs = np.zeros((self.n, 2, _abi.R1_OBS_LEN), np.int16)
+        st = self.state.c_struct()
+        lib().oro_r1_observe(C.byref(self.c_cfg), C.byref(st), obs.ctypes.data, radius, self.n)
+        return obs
 
     def rollout(self, n_ticks, stats=None):
         stats = np.zeros(_abi.STAT_COUNT, np.uint64) if stats is None else stats

@@ -391,3 +391,39 @@ int oro_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, un
     if (stats) for (int k = 0; k < ORX_STAT_COUNT; ++k) stats[k] += total[k];
     return 0;
 }
+
+/* docs/RULESET_R1.md "Observation"; layout in include/orx.h (orx_r1_observe) */
+int oro_r1_observe(const OrxR1Config* cfg, const OrxR1State* st, int16_t* obs, int radius, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        G g; load_game(&g, cfg, st, i, 0);
+        for (int p = 0; p < 2; ++p) {
+            int16_t* o = obs + (i * 2 + p) * ORX_R1_OBS_LEN;
+            const Ent* me = &g.e[p]; const Ent* ot = &g.e[1 - p]; const Pl* q = &g.p[p];
+            memset(o, 0, sizeof(int16_t) * ORX_R1_OBS_LEN);
+            o[0] = (int16_t)me->x; o[1] = (int16_t)me->y; o[2] = (int16_t)imin(me->depth, 32767); o[3] = (int16_t)me->hp;
+            o[4] = (int16_t)me->aux; o[5] = (int16_t)q->cd; o[6] = (int16_t)q->damage; o[7] = (int16_t)q->armor;
+            o[8] = (int16_t)q->max_hp; o[9] = (int16_t)q->max_mana; o[10] = (int16_t)q->level; o[11] = (int16_t)q->xp;
+            o[12] = (int16_t)q->n_items; o[13] = (int16_t)imin(g.sep, 32767); o[14] = (int16_t)imin(g.tick, 32767); o[15] = (int16_t)g.status;
+            int same = ot->depth == me->depth;
+            o[16] = (int16_t)same; o[17] = (int16_t)(same ? ot->x : -1); o[18] = (int16_t)(same ? ot->y : -1); o[19] = (int16_t)(same ? ot->hp : 0);
+            int vis = radius < 0 || imax(abs(g.sx[p] - me->x), abs(g.sy[p] - me->y)) <= radius;
+            o[20] = (int16_t)vis; o[21] = (int16_t)(vis ? g.sx[p] : -1); o[22] = (int16_t)(vis ? g.sy[p] : -1);
+            for (int k = 0; k < ORX_R1_ENEMIES; ++k) {
+                const Ent* e = &g.e[2 + k];
+                int here = e->alive && e->depth == me->depth;
+                o[23 + 3 * k] = (int16_t)(here ? e->x : -1); o[24 + 3 * k] = (int16_t)(here ? e->y : -1); o[25 + 3 * k] = (int16_t)(here ? e->hp : 0);
+            }
+            for (int k = 0; k < ORX_R1_ITEMS; ++k) {
+                const Ent* e = &g.e[NM + k];
+                int here = e->alive && e->depth == me->depth;
+                o[47 + 3 * k] = (int16_t)(here ? e->x : -1); o[48 + 3 * k] = (int16_t)(here ? e->y : -1); o[49 + 3 * k] = (int16_t)(here ? e->aux : -1);
+            }
+            for (int t = 0; t < 49; ++t) {
+                int x = me->x + t % 7 - 3, y = me->y + t / 7 - 3;
+                if (is_wall(&g, g.key[p], g.sx[p], g.sy[p], x, y)) o[59 + t / 16] = (int16_t)((uint16_t)o[59 + t / 16] | (1u << (t % 16)));
+            }
+        }
+    }
+    return 0;
+}

@@ -86,3 +86,17 @@ def test_r1_shard_invariance():
     part.rollout(150)
     for name, _, _ in _abi.R1_PLANES:
         assert torch.equal(getattr(part, name), getattr(full, name)[1024:]), name
+
+
+@pytest.mark.parametrize('radius', [-1, 0, 4])
+def test_r1_observation_parity(radius):
+    gs, orc = pair(3000, width=24, height=9, wall_density=50, seed=17, max_ticks=300, auto_reset=True)
+    gs.rollout(120)
+    orc.rollout(120)
+    assert_equal(gs, orc, 'before observe')
+    got = gs.observe(radius).cpu().numpy()
+    want = orc.observe(radius)
+    assert np.array_equal(got, want)
+    assert (got[:, :, 23:47:3] >= 0).any(), 'some enemy is visible'
+    if radius == 0:
+        assert (got[:, :, 20] == 0).all()      # nobody ever stands on the staircase

@@ -180,3 +180,26 @@ def test_walls_are_a_pure_function_of_the_level_key():
     big.reset()
     st = big.rollout(200)
     assert int(st[0]) == 500 * 200 and (big.state.status == 1).all()
+
+
+def test_observation_layout_and_ladder_visibility():
+    o, s = game(wall_density=0)
+    put(s, 0, 3, 3); put(s, 1, 8, 5, hp=7)
+    put(s, 2, 4, 4, hp=2, aux=0); put(s, 10, 2, 2, kind=1)
+    s.lvl_stairs[0] = 6 | (3 << 8) | (6 << 16) | (3 << 24)
+    obs = o.observe(radius=3)
+    a, b = obs[0, 0], obs[0, 1]
+    assert a[:5].tolist() == [3, 3, 0, 10, 9] and a[16:20].tolist() == [1, 8, 5, 7]
+    assert a[20:23].tolist() == [1, 6, 3]                 # staircase 3 tiles away: visible (readme.md:44)
+    assert b[20:23].tolist() == [1, 6, 3]                 # Chebyshev distance max(2, 2) = 2
+    assert o.observe(radius=1)[0, 0, 20:23].tolist() == [0, -1, -1]
+    assert a[23:26].tolist() == [4, 4, 2] and a[26:29].tolist() == [-1, -1, 0]
+    assert a[47:50].tolist() == [2, 2, 1]
+    # 7x7 wall window of player 1 at (3, 3): column x = 0 is the border wall => bit 0 of every row
+    bits = int(a[59]) & 0xFFFF | (int(a[60]) & 0xFFFF) << 16 | (int(a[61]) & 0xFFFF) << 32 | (int(a[62]) & 0xFFFF) << 48
+    for row in range(7):
+        y = 3 + row - 3
+        for col in range(7):
+            x = 3 + col - 3
+            wall = x <= 0 or y <= 0 or x >= 11 or y >= 7
+            assert (bits >> (row * 7 + col)) & 1 == int(wall), (row, col)
