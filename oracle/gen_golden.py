@@ -27,12 +27,17 @@ SEED = 0x0A11CE
 SUITES = {
     'stair_vs_random': dict(bots=('staircase', 'random'), max_ticks=512, despawn='unreachable'),
     'random_vs_random': dict(bots=('random', 'random'), max_ticks=1000, despawn='unreachable'),
+    # both players descend all the time: double descents, DungeonCreated under Unused, spawn retries
+    'stair_vs_stair_unused': dict(bots=('staircase', 'staircase'), max_ticks=256, despawn='unused', episodes=4000),
+    # SeparatedGameStartGenerator (worldgen.py:91-135): player 1 climbs down towards player 2's level
+    'separated_stair_vs_random': dict(bots=('staircase', 'random'), max_ticks=256, despawn='unreachable',
+                                      start='separated', p_depths=(0, 6), episodes=3000),
 }
 
 
 def _digest_job(args):
     name, gid = args
-    kw = SUITES[name]
+    kw = {k: v for k, v in SUITES[name].items() if k != 'episodes'}
     trace, _ = rh.play_episode(SEED, gid, **kw)
     return gid, rh.digest(trace), len(trace) - 1, trace[-1]['result'], trace[-1]['ent'][0][2], trace[-1]['ent'][1][2]
 
@@ -118,22 +123,32 @@ def truth_table():
 
 def main():
     quick = '--quick' in sys.argv
+    only_new = '--only-new' in sys.argv        # keep committed suites, add the missing ones
     os.makedirs(OUT, exist_ok=True)
     n_ep = 200 if quick else 10000
     meta = {'seed': SEED, 'episodes': n_ep, 'suites': {}}
+    meta_path = os.path.join(OUT, 'digests_meta.json')
+    if only_new and os.path.exists(meta_path):
+        meta = json.load(open(meta_path))
     with mp.Pool(os.cpu_count()) as pool:
         for name, kw in SUITES.items():
-            res = pool.map(_digest_job, [(name, g) for g in range(n_ep)], chunksize=16)
+            if only_new and name in meta['suites'] and os.path.exists(os.path.join(OUT, f'digests_{name}.npy')):
+                continue
+            n_suite = min(n_ep, kw.get('episodes', n_ep))
+            res = pool.map(_digest_job, [(name, g) for g in range(n_suite)], chunksize=16)
             res.sort()
             dig = np.array([r[1] for r in res], dtype=np.uint64)
             np.save(os.path.join(OUT, f'digests_{name}.npy'), dig)
             ticks = [r[2] for r in res]
             hist = {str(k): int(sum(1 for r in res if r[3] == k)) for k in (2, 3, 4)}
-            meta['suites'][name] = dict(kw, bots=list(kw['bots']), total_ticks=int(sum(ticks)),
+            meta['suites'][name] = dict({k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()},
+                                        bots=list(kw['bots']), episodes=n_suite, total_ticks=int(sum(ticks)),
                                         result_hist=hist, max_depth=int(max(max(r[4], r[5]) for r in res)))
             print(name, meta['suites'][name], flush=True)
-    with open(os.path.join(OUT, 'digests_meta.json'), 'w') as f:
+    with open(meta_path, 'w') as f:
         json.dump(meta, f, indent=1)
+    if only_new:
+        return
 
     cases = trace_cases()
     arrays = {}

@@ -19,17 +19,23 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-@pytest.mark.parametrize('suite', ['stair_vs_random', 'random_vs_random'])
+SUITES = sorted(json.load(open(os.path.join(GOLD, 'digests_meta.json')))['suites'])
+
+
+@pytest.mark.parametrize('suite', SUITES)
 @pytest.mark.parametrize('fused_bots', [False, True])
-def test_ten_thousand_replayed_episodes_bit_exact(suite, fused_bots):
+def test_replayed_episodes_bit_exact(suite, fused_bots):
+    """Up to 10,000 episodes per suite replayed on the GPU against digests recorded from the live
+    reference (StaircaseBot / RandomBot pairings, both despawn strategies, separated starts)."""
+    from test_oracle_golden import suite_config
     meta = json.load(open(os.path.join(GOLD, 'digests_meta.json')))
     want = np.load(os.path.join(GOLD, f'digests_{suite}.npy'))
     kw = meta['suites'][suite]
     n = len(want)
-    cfg = SimConfig(max_ticks=kw['max_ticks'], seed=meta['seed'])
+    cfg = suite_config(meta, kw)
     gs = BatchedGameState(cfg, n, 'cuda')
     reset_games(gs)
-    upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, kw['max_ticks'])
+    upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), cfg.despawn_strat, kw['max_ticks'])
     bots = [tu.BOT_CODES[b] for b in kw['bots']]
     dg = tu.BatchDigest(n)
     active = np.ones(n, bool)

@@ -112,12 +112,25 @@ def batch_digests(cfg, bots, n, max_steps, chunk=2000):
     return out
 
 
-@pytest.mark.parametrize('suite', ['stair_vs_random', 'random_vs_random'])
-def test_ten_thousand_episode_digests(suite):
+SUITES = sorted(json.load(open(os.path.join(GOLD, 'digests_meta.json')))['suites'])
+
+
+def suite_config(meta, kw):
+    extra = {}
+    if kw.get('despawn') == 'unused':
+        extra['despawn_strat'] = 2
+    if kw.get('start') == 'separated':
+        extra['start_kind'] = _abi.START_SEPARATED
+        extra['start_depth'] = tuple(kw['p_depths'])
+    return SimConfig(max_ticks=kw['max_ticks'], seed=meta['seed'], **extra)
+
+
+@pytest.mark.parametrize('suite', SUITES)
+def test_replayed_episode_digests(suite):
     meta = json.load(open(os.path.join(GOLD, 'digests_meta.json')))
     want = np.load(os.path.join(GOLD, f'digests_{suite}.npy'))
     kw = meta['suites'][suite]
-    cfg = SimConfig(max_ticks=kw['max_ticks'], seed=meta['seed'])
+    cfg = suite_config(meta, kw)
     bots = [tu.BOT_CODES[b] for b in kw['bots']]
     got = batch_digests(cfg, bots, len(want), kw['max_ticks'])
     bad = np.flatnonzero(got != want)
