@@ -8,7 +8,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = [os.path.join(_HERE, 'csrc', 'orx_api.cu'), os.path.join(_HERE, 'csrc', 'orx_r1.cu')]
 HEADERS = [os.path.join(_HERE, 'csrc', 'orx_rng.cuh'), os.path.join(_HERE, 'csrc', 'orx_rules.cuh'),
-           os.path.join(_HERE, 'csrc', 'orx_pipe.cuh'),
+           os.path.join(_HERE, 'csrc', 'orx_pipe.cuh'), os.path.join(_HERE, 'csrc', 'orx_r1t.cuh'),
            os.path.join(_HERE, '..', 'include', 'orx.h')]
 OUT = os.path.join(_HERE, 'liborx.so')
 

@@ -11,6 +11,7 @@
 // (x, y, level key), the key and the staircase come from the Philox LEVEL block.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/orx.h"
@@ -473,6 +474,14 @@ k_r1_rollout(const __grid_constant__ R1Params P, int n_ticks, unsigned long long
     }
 }
 
+}  // namespace
+
+namespace {
+#include "orx_r1t.cuh"
+}  // namespace
+
+namespace {
+
 // Observation: lanes 0/1 write the scalar block of their player, every entity lane writes its own
 // triple into both players' rows, and the 7x7 wall window is hashed 16 tiles at a time by the
 // whole group -- one ballot is one output word.
@@ -575,9 +584,15 @@ int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mov
 {
     const int rc = r1_check(cfg, st, n);
     if (rc != ORX_OK) return rc;
-    if (moves == nullptr || result == nullptr) return ORX_ERR_BAD_ARG;
+    if (moves == nullptr || result == nullptr || (reinterpret_cast<uintptr_t>(moves) & 1)) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
-    k_r1_step<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), moves, result);
+    // Default: one thread per game (orx_r1t.cuh). ORX_R1_HALFWARP=1 selects the sixteen-lanes-per-game
+    // kernels instead (same results; kept as the warp-primitive formulation and as a cross-check).
+    if (getenv("ORX_R1_HALFWARP") != nullptr)
+        k_r1_step<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), moves, result);
+    else
+        r1t::k_step<<<(unsigned)((n + r1t::kThreads - 1) / r1t::kThreads), r1t::kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+            r1_params(cfg, st, n, game_id_base), reinterpret_cast<const uint16_t*>(moves), result);
     return r1_done();
 }
 
@@ -588,7 +603,11 @@ int orx_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, un
     if (rc != ORX_OK) return rc;
     if (n_ticks < 0) return ORX_ERR_BAD_ARG;
     if (n == 0 || n_ticks == 0) return ORX_OK;
-    k_r1_rollout<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), n_ticks, stats);
+    if (getenv("ORX_R1_HALFWARP") != nullptr)
+        k_r1_rollout<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), n_ticks, stats);
+    else
+        r1t::k_rollout<<<(unsigned)((n + r1t::kThreads - 1) / r1t::kThreads), r1t::kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+            r1_params(cfg, st, n, game_id_base), n_ticks, stats);
     return r1_done();
 }
 

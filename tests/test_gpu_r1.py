@@ -12,6 +12,17 @@ from optimax_rogue_b200.r1 import R1GameState
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['thread_per_game', 'half_warp'], autouse=True)
+def r1_kernel_flavour(request, monkeypatch):
+    """Both device formulations of the R1 tick (orx_r1t.cuh: one thread per game, the default;
+    orx_r1.cu: sixteen lanes per game with warp primitives) must match the oracle bit for bit."""
+    if request.param == 'half_warp':
+        monkeypatch.setenv('ORX_R1_HALFWARP', '1')
+    else:
+        monkeypatch.delenv('ORX_R1_HALFWARP', raising=False)
+    yield request.param
+
+
 def pair(n, base=0, **cfg):
     gs = R1GameState(n, game_id_base=base, **cfg).reset()
     orc = cport.R1Oracle(n, game_id_base=base, **cfg)

@@ -2,14 +2,16 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from optimax_rogue_b200.r1 import R1GameState
-G, nb, K = 1 << 16, 18, 72
+G = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 16
+nb = max(2, min(18, (300_000_000 // (244 * G)) + 1))
+K = 4 * nb
 bs = [R1GameState(G, max_ticks=1000, auto_reset=True, seed=3, game_id_base=b * G).reset() for b in range(nb)]
 mv = torch.randint(1, 7, (4, G, 2), dtype=torch.uint8, device='cuda')
 res = torch.empty((G,), dtype=torch.uint8, device='cuda')
 for b in bs: b.rollout(64)
 st = torch.cuda.Stream()
 with torch.cuda.stream(st):
-    for k in range(3): bs[k].update(mv[k % 4], out=res)
+    for k in range(3): bs[k % nb].update(mv[k % 4], out=res)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=st):
@@ -23,6 +25,6 @@ with torch.cuda.stream(st):
     stats = torch.zeros(8, dtype=torch.int64, device='cuda')
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
-    for b in range(4): bs[b].rollout(64, stats)
+    for b in range(4): bs[b % nb].rollout(64, stats)
     e1.record(st); torch.cuda.synchronize()
-print(f'R1 step: {best * 1e3:.1f} us/step, {G / best * 1e3:.3e} ticks/s; rollout {4 * G * 64 / e0.elapsed_time(e1) * 1e3:.3e} ticks/s', flush=True)
+print(f'G={G} nb={nb} R1 step: {best * 1e3:.1f} us/step, {G / best * 1e3:.3e} ticks/s; rollout {4 * G * 64 / e0.elapsed_time(e1) * 1e3:.3e} ticks/s', flush=True)
