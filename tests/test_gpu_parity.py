@@ -289,3 +289,12 @@ def test_full_size_batch_properties():
             if name == 'episode':
                 a = a.view(np.uint32)
             assert np.array_equal(a, getattr(orc.state, name)), (start, name)
+
+
+def test_selfplay_example_runs():
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'examples', 'selfplay_loop.py'), '--games', '4096', '--ticks', '20'],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert 'game-ticks/s' in out.stdout
