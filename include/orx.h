@@ -20,6 +20,7 @@
  *   orx_bot_moves   RandomBot.move     optimax_rogue_bots/randombot.py:20-21
  *                   StaircaseBot.move  optimax_rogue_bots/staircasebot.py:9-20
  *   orx_rollout     the tick loop  optimax_rogue/server/main.py:110-113 with both bots inlined
+ *   orx_replay      the same loop with both players' commands queued in advance
  *   orx_observe     GameState.view_for  optimax_rogue/game/state.py:53-58
  *   orx_step_host   orx_step with host command/result buffers (what a remote caller holds);
  *   orx_step_host_sync  the same plus a stream synchronisation (Server.update returns the result, server.py:132-138)
@@ -170,6 +171,12 @@ int orx_bot_moves(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_
  * stats: device uint64[ORX_STAT_COUNT], accumulated (not cleared). */
 int orx_rollout(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2, int n_ticks,
                 unsigned long long* stats, int64_t n, uint64_t game_id_base, void* cuda_stream);
+
+/* n_ticks ticks of QUEUED commands in one launch: moves device uint8[n_ticks][n][2], results device
+ * uint8[n_ticks][n]; identical to n_ticks calls of orx_step, with the state held in registers between
+ * ticks (replaying recorded command streams, open-loop evaluation). */
+int orx_replay(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uint8_t* results, int n_ticks,
+               int64_t n, uint64_t game_id_base, void* cuda_stream);
 
 /* Per-player observation (state.py:53-58): obs int16[n][2][ORX_OBS_LEN]. */
 #define ORX_OBS_LEN 12

@@ -199,6 +199,40 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
     }
 }
 
+// ------------------------------------------------------------------ replay: T ticks of queued commands
+template <int DGEN, bool NPC>
+__global__ void __launch_bounds__(kThreads, ORX_ROLLOUT_MINBLOCKS)
+k_replay(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ results, int n_ticks)
+{
+    extern __shared__ uint8_t smem[];
+    __shared__ CmdEntry lut[256];
+    build_cmd_lut(P, lut, threadIdx.x, kThreads);
+    const uint8_t* tiles = nullptr;
+    if (DGEN == ORX_DGEN_FIXED) tiles = stage_tiles(P, smem);
+    else __syncthreads();
+    const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P.n) return;
+    int status = P.status[i];
+    Lane L;
+    load_lane(P, i, L);
+    Stream s = make_stream(P, i, L.episode);
+    EvSink<false> ev{nullptr, 0, 0};
+    Counters cnt{};
+    for (int t = 0; t < n_ticks; ++t) {
+        const size_t at = (size_t)t * P.n + i;
+        if (status != ORX_RESULT_IN_PROGRESS) { results[at] = (uint8_t)status; continue; }   // frozen lane
+        const uint32_t mv = moves[at];
+        const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
+        const int res = tick_lane<DGEN, NPC, false>(P, tiles, lut, L, mv, blk.z, s, i, ev, cnt);
+        results[at] = (uint8_t)res;
+        if (res != ORX_RESULT_IN_PROGRESS) {
+            if (P.auto_reset) { s.episode += 1; reset_lane<DGEN, NPC>(P, L, s, i); }
+            else status = res;
+        }
+    }
+    store_lane(P, i, L, status);
+}
+
 // ------------------------------------------------------------------ observations (state.py:53-58)
 // obs[i][p] = { x, y, depth (saturated), hp, other_visible, other_x, other_y, other_hp,
 //               stairs_visible, stairs_x, stairs_y, tick (saturated) }
@@ -497,6 +531,24 @@ int orx_rollout(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2
     const size_t smem = tiles_smem(cfg);
     return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
         k_rollout<DGEN, NPC><<<grid, kThreads, smem, s>>>(P, bot_p1, bot_p2, n_ticks, stats);
+        return launch_done();
+    });
+}
+
+int orx_replay(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uint8_t* results, int n_ticks,
+               int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    const int rc = check_common(cfg, st, n);
+    if (rc != ORX_OK) return rc;
+    if (moves == nullptr || results == nullptr || !aligned(moves, 2) || n_ticks < 0) return ORX_ERR_BAD_ARG;
+    if (n == 0 || n_ticks == 0) return ORX_OK;
+    const Params P = make_params(cfg, st, n, game_id_base);
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const int grid = grid_for(n);
+    const size_t smem = tiles_smem(cfg);
+    const uint16_t* mv = reinterpret_cast<const uint16_t*>(moves);
+    return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
+        k_replay<DGEN, NPC><<<grid, kThreads, smem, s>>>(P, mv, results, n_ticks);
         return launch_done();
     });
 }

@@ -233,6 +233,23 @@ class BatchedUpdater:
         _lib.check(rc, 'orx_rollout')
         return stats
 
+    def replay(self, game_state: BatchedGameState, moves: torch.Tensor,
+               out: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Plays ``T`` ticks of queued commands in one launch: ``moves`` uint8[T,N,2] on the device,
+        returns uint8[T,N] results. Same outcome as T ``update`` calls (``orx_replay``)."""
+        gs = game_state
+        _require_cuda(gs)
+        if moves.dim() != 3 or tuple(moves.shape[1:]) != (gs.n, 2) or moves.dtype != torch.uint8 or not moves.is_cuda:
+            raise ValueError(f'moves must be a CUDA uint8 tensor of shape (T, {gs.n}, 2)')
+        moves = moves.contiguous()
+        cfg, st = self._cfg(gs)
+        results = out if out is not None else torch.empty((moves.shape[0], gs.n), dtype=torch.uint8, device=gs.device)
+        with _on_device(gs.device):
+            rc = _lib.lib().orx_replay(C.byref(cfg), C.byref(st), moves.data_ptr(), results.data_ptr(),
+                                       int(moves.shape[0]), gs.n, gs.game_id_base, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_replay')
+        return results
+
     def observe(self, game_state: BatchedGameState, stairs_radius: int = -1,
                 out: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
         """Per-player observation int16[N,2,OBS_LEN] (GameState.view_for, state.py:53-58, plus the

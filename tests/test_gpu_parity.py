@@ -161,6 +161,25 @@ def test_rollout_equals_step_loop():
         assert torch.equal(getattr(gs, name), getattr(gs2, name)), name
 
 
+@pytest.mark.parametrize('auto_reset', [True, False])
+def test_replay_equals_update_loop(auto_reset):
+    cfg = SimConfig(max_ticks=40, seed=12, auto_reset=auto_reset, hp=(2, 2))
+    gs, upd, orc = gu.make_pair(cfg, 3000, game_id_base=99)
+    twin = gs.clone()
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(3)
+    moves = torch.randint(0, 7, (70, 3000, 2), dtype=torch.uint8, device='cuda', generator=gen)
+    results = upd.replay(gs, moves)
+    for t in range(70):
+        r, _ = upd.update(twin, moves[t])
+        assert torch.equal(r, results[t]), t
+        ro, _ = orc.step(moves[t].cpu().numpy())
+        assert np.array_equal(ro, results[t].cpu().numpy()), t
+    for name in gu.PLANES:
+        assert torch.equal(getattr(gs, name), getattr(twin, name)), name
+    gu.assert_state_equal(gs, orc, 'replay')
+
+
 def test_shard_invariance():
     """Game g gives the same trajectory whichever shard (game_id_base) holds it."""
     cfg = SimConfig(max_ticks=80, seed=SEED, auto_reset=True)
