@@ -74,3 +74,27 @@ def test_npc_slots():
             npcs.append((d, x, y, hp))
         compare(gid, ('random', 'staircase'), dict(width=8, height=6, max_ticks=150, hp=(50, 50)),
                 dict(width=8, height=6, max_ticks=150, hp=50), npcs=npcs)
+
+
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=40, deadline=None)
+@given(gid=st.integers(0, 2**53), seed=st.integers(0, 2**64 - 1), w=st.integers(4, 30), h=st.integers(4, 12),
+       hp1=st.integers(1, 12), hp2=st.integers(1, 12), dmg=st.integers(0, 4), arm=st.integers(0, 3),
+       despawn=st.sampled_from([1, 2]), separated=st.booleans(), d2=st.integers(1, 5),
+       bots=st.sampled_from([('random', 'random'), ('staircase', 'random'), ('random', 'staircase'), ('staircase', 'staircase')]))
+def test_fuzzed_configurations_against_live_reference(gid, seed, w, h, hp1, hp2, dmg, arm, despawn, separated, d2, bots):
+    """Random room sizes, stats, start generators, despawn strategies, bot pairings, 64-bit seeds and
+    53-bit game ids: the C oracle must reproduce the live reference tick by tick, events included."""
+    ref_kw = dict(width=w, height=h, max_ticks=90, hp=(hp1, hp2), damage=(dmg, dmg + 1), armor=(arm, 0),
+                  despawn='unreachable' if despawn == 1 else 'unused')
+    cfg_kw = dict(width=w, height=h, max_ticks=90, hp=(hp1, hp2), damage=(dmg, dmg + 1), armor=(arm, 0),
+                  despawn_strat=despawn)
+    if separated:
+        ref_kw.update(start='separated', p_depths=(0, d2))
+        cfg_kw.update(start_kind=_abi.START_SEPARATED, start_depth=(0, d2))
+    tr, mv = rh.play_episode(seed, gid, bots=bots, **ref_kw)
+    to, mo = tu.oracle_episode(SimConfig(seed=seed, **cfg_kw), gid, bots=bots)
+    assert [tu.strip(r) for r in tr] == to
+    assert mv == mo

@@ -83,3 +83,24 @@ def test_cuda_invariants_at_scale():
             mv = upd.bot_moves(gs, 2, 2)      # drive descents as well
         res, _ = upd.update(gs, mv)
         assert bool(((res >= 1) & (res <= 4)).all())
+
+
+@pytest.mark.gpu
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 2**64 - 1), base=st.integers(0, 2**53), w=st.integers(4, 64), h=st.integers(4, 20),
+       hp=st.tuples(st.integers(1, 9), st.integers(1, 9)), dmg=st.tuples(st.integers(0, 4), st.integers(0, 4)),
+       arm=st.tuples(st.integers(0, 2), st.integers(0, 2)), despawn=st.sampled_from([1, 2]),
+       separated=st.booleans(), d2=st.integers(1, 4), max_ticks=st.integers(0, 70), auto_reset=st.booleans(),
+       n=st.integers(1, 700), bots=st.tuples(st.sampled_from([1, 2]), st.sampled_from([1, 2])))
+def test_cuda_matches_oracle_on_fuzzed_configurations(seed, base, w, h, hp, dmg, arm, despawn, separated, d2,
+                                                      max_ticks, auto_reset, n, bots):
+    """Random room sizes, stats, generators, despawn strategies, batch sizes (pipelined body + ragged
+    tail), 64-bit seeds and 53-bit game ids: CUDA == oracle on every plane, result and event, every tick."""
+    from optimax_rogue_b200 import _abi
+    import gpu_util as gu
+    kw = dict(width=w, height=h, hp=hp, damage=dmg, armor=arm, despawn_strat=despawn, max_ticks=max_ticks,
+              auto_reset=auto_reset, seed=seed)
+    if separated:
+        kw.update(start_kind=_abi.START_SEPARATED, start_depth=(0, d2))
+    cfg = SimConfig(**kw)
+    gu.run_parity(cfg, n, 40, bots=bots, events=bool(seed & 1), game_id_base=base)
