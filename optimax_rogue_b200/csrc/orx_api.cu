@@ -1,6 +1,5 @@
 // liborx.so: kernels + the C ABI declared in include/orx.h. sm_100a only.
 #include <cuda_runtime.h>
-#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
