@@ -171,8 +171,8 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
                 issue_loads(it + kStages);
             }
         }
-        bulk_wait_all();
-        return;
+        bulk_wait_read_all();     // shared memory may be released once the last stores have read it; the
+        return;                   // writes themselves complete with the grid (as CUTLASS epilogues do)
     }
 
     // ---------------------------------------------------------------- consumers (8 warps)

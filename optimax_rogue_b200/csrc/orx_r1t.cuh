@@ -357,9 +357,15 @@ __device__ __forceinline__ void store_game(const R1Params& P, unsigned int game,
     P.sep[game] = (uint32_t)G.sep; P.tick[game] = G.tick; P.episode[game] = G.episode; P.status[game] = (uint8_t)status;
 }
 
-constexpr int kThreads = 128;
+#ifndef ORX_R1T_THREADS
+#define ORX_R1T_THREADS 128
+#endif
+#ifndef ORX_R1T_MINBLOCKS
+#define ORX_R1T_MINBLOCKS 1
+#endif
+constexpr int kThreads = ORX_R1T_THREADS;
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, ORX_R1T_MINBLOCKS)
 k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result)
 {
     const unsigned int game = blockIdx.x * kThreads + threadIdx.x;
@@ -383,7 +389,7 @@ k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, u
     store_game(P, game, G, res);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, ORX_R1T_MINBLOCKS)
 k_rollout(const __grid_constant__ R1Params P, int n_ticks, unsigned long long* __restrict__ stats)
 {
     __shared__ unsigned int s_cnt[ORX_STAT_COUNT];
