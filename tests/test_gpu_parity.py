@@ -317,3 +317,57 @@ def test_selfplay_example_runs():
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert 'game-ticks/s' in out.stdout
+
+
+def test_single_game_interop_and_event_decoding():
+    """Lane <-> host GameState conversion (reference attribute names, reference wire format) and
+    decoding of the device event records into GameStateUpdate objects with running orders."""
+    from optimax_rogue_b200.game.state import GameState
+    from optimax_rogue_b200.logic import updates
+    cfg = SimConfig(max_ticks=0, seed=31)
+    gs, upd, orc = gu.make_pair(cfg, 64)
+    order = 0
+    seen = set()
+    for t in range(120):
+        mv = upd.bot_moves(gs, 2, 2)
+        before = gs.planes_cpu()
+        res, ev = upd.update(gs, mv, want_events=True)
+        orc.step(mv.cpu().numpy())
+        recs = updates.unpack_events(ev)
+        after = gs.planes_cpu()
+        evs = updates.decode_events(recs[0], first_order=order)
+        order += len(evs)
+        for e in evs:
+            seen.add(type(e).__name__)
+            if isinstance(e, updates.EntityPositionUpdate):
+                k = e.entity_iden - 1
+                assert (e.posx, e.posy, e.depth) == (int(after['pos'][0, 2 * k]), int(after['pos'][0, 2 * k + 1]), int(after['depth'][0, k])) \
+                    or len([x for x in evs if isinstance(x, updates.EntityPositionUpdate) and x.entity_iden == e.entity_iden]) > 1
+                assert e.old_depth == int(before['depth'][0, k])
+            if isinstance(e, updates.DungeonCreatedUpdate):
+                assert e.dungeon.width == 60 and e.dungeon.height == 10 and (e.dungeon.tiles == 3).sum() == 1
+    assert {'EntityPositionUpdate', 'DungeonCreatedUpdate'} <= seen
+    assert int(upd.get_incr_upd_order()[0]) == order                       # Updater.get_incr_upd_order, updater.py:71-74
+    # lane -> GameState -> bytes -> GameState -> lane
+    host = gs.to_game_state(5)
+    p = gs.planes_cpu()
+    assert (host.player_1.x, host.player_1.y, host.player_1.depth, host.player_1.health) == \
+        (int(p['pos'][5, 0]), int(p['pos'][5, 1]), int(p['depth'][5, 0]), int(p['hp'][5, 0]))
+    assert host.tick == int(p['tick'][5]) and host.world.dungeons[host.player_2.depth].staircase() == \
+        (int(p['stairs'][5, 2]), int(p['stairs'][5, 3]))
+    back = GameState.from_prims(host.to_prims())
+    other = BatchedGameState(cfg, 8, 'cuda', game_id_base=gs.game_id_base + 5)   # lane 0 of `other` has the same global id
+    reset_games(other)
+    other.load_game_state(0, back)
+    q = other.planes_cpu()
+    for name in ('pos', 'hp', 'depth', 'stairs', 'tick'):
+        assert np.array_equal(q[name][0], p[name][5]), name
+    # and the transplanted lane keeps playing exactly like the original (same global game id, same episode)
+    mv = upd.bot_moves(gs, 1, 1)
+    upd.update(gs, mv)
+    upd2 = BatchedUpdater(upd.dgen, 1, None)
+    mv2 = upd2.bot_moves(other, 1, 1)
+    assert torch.equal(mv2[0], mv[5])
+    upd2.update(other, mv2)
+    for name in ('pos', 'hp', 'depth', 'stairs', 'tick'):
+        assert torch.equal(getattr(other, name)[0], getattr(gs, name)[5]), name
