@@ -41,6 +41,12 @@ class GameState:
     def player_2(self) -> Entity:
         return self.iden_lookup[self.player_2_iden]
 
+    def move_entity(self, entity, newdepth, newx, newy):
+        """state.py:64-76"""
+        del self.pos_lookup[(entity.depth, entity.x, entity.y)]
+        entity.depth, entity.x, entity.y = newdepth, newx, newy
+        self.pos_lookup[(newdepth, newx, newy)] = entity
+
     def view_for(self, entity: Entity, reduce_tick: bool = False) -> 'GameState':
         """state.py:53-58: only the viewer's depth is kept."""
         world = World({entity.depth: self.world.dungeons[entity.depth]})

@@ -371,3 +371,53 @@ def test_single_game_interop_and_event_decoding():
     upd2.update(other, mv2)
     for name in ('pos', 'hp', 'depth', 'stairs', 'tick'):
         assert torch.equal(getattr(other, name)[0], getattr(gs, name)[5]), name
+
+
+@pytest.mark.parametrize('despawn', [1, 2])
+def test_single_game_updater_is_a_drop_in_for_the_reference_updater(despawn):
+    """SingleGameUpdater mutates a host GameState in place like Updater.update (updater.py:76-162):
+    after every tick the host object equals the device lane, the world holds exactly the levels the
+    reference's despawn strategy would keep, and the update orders run without gaps."""
+    from optimax_rogue_b200.logic.compat import SingleGameUpdater
+    from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator, TogetherGameStartGenerator
+    from optimax_rogue_b200.logic import updates
+    dgen = EmptyDungeonGenerator(20, 8)
+    seed_state = TogetherGameStartGenerator(dgen).setup_game(1, seed=77, game_id_base=1234)
+    host = seed_state.to_game_state(0)
+    upd = SingleGameUpdater(dgen, despawn, max_ticks=400, seed=77, game_id=1234)
+    orc = cport_oracle_for(dgen, despawn, 400, 77, 1234)
+    rng = np.random.default_rng(despawn)
+    expect_order = 0
+    for t in range(300):
+        p1 = host.player_1
+        sx, sy = host.world.dungeons[p1.depth].staircase()                        # StaircaseBot, staircasebot.py:9-20
+        dx, dy = sx - p1.x, sy - p1.y
+        m1 = (2 if dx > 0 else 4) if abs(dx) > abs(dy) else (3 if dy > 0 else 1)
+        m2 = int(rng.integers(1, 6)) if t % 3 else m1
+        res, evs = upd.update(host, m1, m2)
+        ro, _ = orc.step(np.array([[m1, m2]], np.uint8))
+        assert int(res) == int(ro[0])
+        assert [e.order for e in evs] == list(range(expect_order, expect_order + len(evs)))
+        expect_order += len(evs)
+        s = orc.state
+        assert (host.player_1.x, host.player_1.y, host.player_1.depth, host.player_1.health) == \
+            (int(s.pos[0, 0]), int(s.pos[0, 1]), int(s.depth[0, 0]), int(s.hp[0, 0]))
+        assert (host.player_2.x, host.player_2.y, host.player_2.depth, host.player_2.health) == \
+            (int(s.pos[0, 2]), int(s.pos[0, 3]), int(s.depth[0, 1]), int(s.hp[0, 1]))
+        assert host.tick == int(s.tick[0])
+        d1, d2 = host.player_1.depth, host.player_2.depth
+        want_levels = set(range(min(d1, d2), max(d1, d2) + 1)) if despawn == 1 else {d1, d2}
+        assert set(host.world.dungeons) == want_levels
+        assert host.world.dungeons[d1].staircase() == (int(s.stairs[0, 0]), int(s.stairs[0, 1]))
+        assert (d1, host.player_1.x, host.player_1.y) in host.pos_lookup
+        if int(res) != 1:
+            break
+    assert host.player_1.depth > 3
+
+
+def cport_oracle_for(dgen, despawn, max_ticks, seed, gid):
+    from oracle import cport
+    cfg = SimConfig(width=dgen.width, height=dgen.height, despawn_strat=despawn, max_ticks=max_ticks, seed=seed)
+    orc = cport.Oracle(cfg, 1, game_id_base=gid)
+    orc.reset()
+    return orc
