@@ -272,6 +272,8 @@ int launch_done() {
 
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
+bool ids_ok(uint64_t base, int64_t n) { return (base >> 54) == 0 && ((base + (uint64_t)(n > 0 ? n : 0)) >> 54) == 0; }   // Philox counter holds 54 id bits
+
 int check_common(const OrxConfig* cfg, const OrxState* st, int64_t n)
 {
     if (cfg == nullptr || st == nullptr || n < 0) return ORX_ERR_BAD_ARG;
@@ -423,6 +425,7 @@ int orx_reset(const OrxConfig* cfg, const OrxState* st, const uint8_t* mask, int
 {
     const int rc = check_common(cfg, st, n);
     if (rc != ORX_OK) return rc;
+    if (!ids_ok(game_id_base, n)) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, game_id_base);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
@@ -438,6 +441,7 @@ int orx_step(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uin
 {
     const int rc = check_common(cfg, st, n);
     if (rc != ORX_OK) return rc;
+    if (!ids_ok(game_id_base, n)) return ORX_ERR_BAD_ARG;
     if (moves == nullptr || result == nullptr || !aligned(moves, 2) || (events && !aligned(events, 8))) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, game_id_base);
@@ -508,6 +512,7 @@ int orx_bot_moves(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_
 {
     const int rc = check_common(cfg, st, n);
     if (rc != ORX_OK) return rc;
+    if (!ids_ok(game_id_base, n)) return ORX_ERR_BAD_ARG;
     if (moves == nullptr || !aligned(moves, 2)) return ORX_ERR_BAD_ARG;
     if (bot_p1 < ORX_BOT_NONE || bot_p1 > ORX_BOT_STAIRCASE || bot_p2 < ORX_BOT_NONE || bot_p2 > ORX_BOT_STAIRCASE) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
@@ -521,6 +526,7 @@ int orx_rollout(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2
 {
     const int rc = check_common(cfg, st, n);
     if (rc != ORX_OK) return rc;
+    if (!ids_ok(game_id_base, n)) return ORX_ERR_BAD_ARG;
     if (n_ticks < 0 || (stats && !aligned(stats, 8))) return ORX_ERR_BAD_ARG;
     if (bot_p1 < ORX_BOT_NONE || bot_p1 > ORX_BOT_STAIRCASE || bot_p2 < ORX_BOT_NONE || bot_p2 > ORX_BOT_STAIRCASE) return ORX_ERR_BAD_ARG;
     if (n == 0 || n_ticks == 0) return ORX_OK;
@@ -539,6 +545,7 @@ int orx_replay(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, u
 {
     const int rc = check_common(cfg, st, n);
     if (rc != ORX_OK) return rc;
+    if (!ids_ok(game_id_base, n)) return ORX_ERR_BAD_ARG;
     if (moves == nullptr || results == nullptr || !aligned(moves, 2) || n_ticks < 0) return ORX_ERR_BAD_ARG;
     if (n == 0 || n_ticks == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, game_id_base);

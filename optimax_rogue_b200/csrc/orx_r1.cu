@@ -574,6 +574,7 @@ int orx_r1_reset(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* ma
 {
     const int rc = r1_check(cfg, st, n);
     if (rc != ORX_OK) return rc;
+    if ((game_id_base >> 54) != 0 || ((game_id_base + (uint64_t)n) >> 54) != 0) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
     k_r1_reset<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), mask, bump_episode);
     return r1_done();
@@ -584,6 +585,7 @@ int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mov
 {
     const int rc = r1_check(cfg, st, n);
     if (rc != ORX_OK) return rc;
+    if ((game_id_base >> 54) != 0 || ((game_id_base + (uint64_t)n) >> 54) != 0) return ORX_ERR_BAD_ARG;
     if (moves == nullptr || result == nullptr || (reinterpret_cast<uintptr_t>(moves) & 1)) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
     // Default: one thread per game (orx_r1t.cuh). ORX_R1_HALFWARP=1 selects the sixteen-lanes-per-game
@@ -601,6 +603,7 @@ int orx_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, un
 {
     const int rc = r1_check(cfg, st, n);
     if (rc != ORX_OK) return rc;
+    if ((game_id_base >> 54) != 0 || ((game_id_base + (uint64_t)n) >> 54) != 0) return ORX_ERR_BAD_ARG;
     if (n_ticks < 0) return ORX_ERR_BAD_ARG;
     if (n == 0 || n_ticks == 0) return ORX_OK;
     if (getenv("ORX_R1_HALFWARP") != nullptr)

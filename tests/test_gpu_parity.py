@@ -270,6 +270,8 @@ def test_bad_arguments_fail_loudly():
     assert lib.orx_reset(C.byref(c), C.byref(st), None, 0, 16, 0, None) == _abi.ERR_BAD_ARG
     with pytest.raises(RuntimeError):
         _lib.check(_abi.ERR_BAD_ARG, 'x')
+    # game ids must fit the 54 bits the Philox counter reserves for them
+    assert lib.orx_reset(C.byref(gs.c_config()), C.byref(st), None, 0, 16, 1 << 54, None) == _abi.ERR_BAD_ARG
     # n == 0 is a no-op
     c = gs.c_config()
     assert lib.orx_reset(C.byref(c), C.byref(st), None, 0, 0, 0, None) == 0
