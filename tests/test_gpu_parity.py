@@ -50,6 +50,13 @@ def test_step_parity_small_rooms_fight():
         gu.run_parity(cfg, 1024, 200, bots=(1, 1), events=True)
 
 
+@pytest.mark.parametrize('w,h', [(255, 255), (255, 4), (4, 255)])
+def test_step_parity_extreme_room_sizes(w, h):
+    # coordinates are uint8 and the command table packs W-2 / H-2 into bytes: exercise the limits
+    cfg = SimConfig(width=w, height=h, max_ticks=120, seed=123, auto_reset=True, hp=(2, 2))
+    gu.run_parity(cfg, 1500, 150, bots=(2, 2), events=True)
+
+
 def test_step_parity_separated_start_and_stats():
     cfg = SimConfig(start_kind=_abi.START_SEPARATED, start_depth=(3, 5), max_ticks=300, seed=5,
                     auto_reset=True, hp=(4, 7), damage=(3, 2), armor=(1, 0))
