@@ -430,3 +430,28 @@ def cport_oracle_for(dgen, despawn, max_ticks, seed, gid):
     orc = cport.Oracle(cfg, 1, game_id_base=gid)
     orc.reset()
     return orc
+
+
+def test_long_horizon_soak():
+    """2^20 games x 4096 fused ticks (several episodes per lane, depths in the hundreds for the
+    StaircaseBot): windows of the batch must equal the oracle run on the same global game ids."""
+    from oracle import cport
+    n, ticks = 1 << 20, 4096
+    cfg = SimConfig(max_ticks=1500, seed=0xC0FFEE, auto_reset=True)
+    gs = BatchedGameState(cfg, n, 'cuda', game_id_base=1 << 33)
+    reset_games(gs)
+    from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
+    upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, 1500, auto_reset=True)
+    stats = upd.rollout(gs, 2, 1, ticks)
+    assert int(stats[0]) == n * ticks
+    p = gs.planes_cpu()
+    assert p['depth'].max() > 50 and p['episode'].view(np.uint32).min() >= 2
+    for start in (0, 555_555, n - 256):
+        orc = cport.Oracle(cfg, 256, game_id_base=(1 << 33) + start)
+        orc.reset()
+        orc.rollout(2, 1, ticks)
+        for name in gu.PLANES:
+            a = p[name][start:start + 256]
+            if name == 'episode':
+                a = a.view(np.uint32)
+            assert np.array_equal(a, getattr(orc.state, name)), (start, name)
