@@ -206,6 +206,11 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------------------------------ GPU side
 def run_b200(args, rank, local_rank, world):
+    # Rank 0 must print exactly ONE line on stdout. Libraries (NCCL's version banner, for one) write to
+    # file descriptor 1 directly, so point fd 1 at stderr for the duration and keep the real stdout aside.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from optimax_rogue_b200 import _lib
@@ -219,7 +224,6 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
 
     G, K, W = args.games_per_gpu, args.steps, args.warmup
@@ -418,7 +422,8 @@ def run_b200(args, rank, local_rank, world):
             v, cores, ticks, el = cpu_port_run_isolated(1 << 18, args.cpu_seconds)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': f'{ticks} game-ticks in {el:.1f} s: 2^18 games, same config, oracle/orx_oracle.c oro_rollout (RandomBot x2), OpenMP over all host cores'}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
