@@ -239,6 +239,21 @@ class BatchedGameState:
                                    hpv, hpv, 0, 0))
         return GameState(True, int(p['tick'][i]), 1, 2, World(dungeons), ents)
 
+    def render(self, i: int, player: int = 1, planes=None) -> str:
+        """Text dump of the level ``player`` (1 or 2) of game ``i`` stands on, with the glyphs of the
+        reference's curses spectator (optimax_rogue_cmdspec/map.py:14-24): '.' ground, '#' wall,
+        '\\' staircase, 'o' player 1, 'x' player 2, 'e' NPC."""
+        gs = self.to_game_state(i, planes)
+        me = gs.player_1 if player == 1 else gs.player_2
+        tiles = gs.world.dungeons[me.depth].tiles
+        glyph = {int(Tile.Ground): '.', int(Tile.Wall): '#', int(Tile.StaircaseDown): '\\'}
+        rows = [[glyph[int(tiles[x, y])] for x in range(tiles.shape[0])] for y in range(tiles.shape[1])]
+        for ent in gs.entities:
+            if ent.depth == me.depth:
+                rows[ent.y][ent.x] = 'o' if ent.iden == 1 else 'x' if ent.iden == 2 else 'e'
+        head = f'game {self.game_id_base + i} tick {gs.tick} depth {me.depth} hp {gs.player_1.health}/{gs.player_2.health}'
+        return head + '\n' + '\n'.join(''.join(r) for r in rows)
+
     def load_game_state(self, i: int, gs: GameState):
         """Writes a host GameState into lane ``i`` (players + their levels' staircases)."""
         for k, ent in enumerate((gs.player_1, gs.player_2)):

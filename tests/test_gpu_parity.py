@@ -357,6 +357,8 @@ def test_single_game_interop_and_event_decoding():
                 assert e.dungeon.width == 60 and e.dungeon.height == 10 and (e.dungeon.tiles == 3).sum() == 1
     assert {'EntityPositionUpdate', 'DungeonCreatedUpdate'} <= seen
     assert int(upd.get_incr_upd_order()[0]) == order                       # Updater.get_incr_upd_order, updater.py:71-74
+    art = gs.render(5).splitlines()
+    assert len(art) == 11 and all(len(r) == 60 for r in art[1:]) and art[1] == '#' * 60 and 'o' in ''.join(art[1:])
     # lane -> GameState -> bytes -> GameState -> lane
     host = gs.to_game_state(5)
     p = gs.planes_cpu()
