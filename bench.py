@@ -10,10 +10,12 @@ streams). Rank r owns games [r*G, (r+1)*G) (weak scaling, no collective on the s
 
 Timed regions (CUDA events on the launching stream, max over ranks):
   value     K steps captured in one CUDA graph, commands already resident in HBM
-  e2e       the public ``BatchedUpdater.update`` call with pinned HOST command/result buffers: the
+  e2e       the public ``BatchedUpdater.host_stepper`` call with pinned HOST command/result buffers: the
             step's commands cross PCIe host->device and its results device->host inside the timed
             region every step (the tick kernel's TMA producer reads/writes the pinned buffers
-            directly, tile by tile), then a stream sync so the caller can read the results
+            directly, tile by tile), then a stream sync so the caller can read the results. Headline:
+            nibble-packed commands (1 B per game in, 1 B out); ``unpacked`` = uint8[N,2] commands;
+            ``pipelined`` = two independent batches in flight, no per-step stream sync
   rollout   (extra) fused multi-tick kernel with both bots on device
 L2: the timed loop rotates over B independent batches whose combined state exceeds the 126 MB L2.
 
@@ -285,26 +287,48 @@ def run_b200(args, rank, local_rank, world):
         ms_total = e0.elapsed_time(e1)
 
         # ---- e2e: public API with host buffers, every step H2D + tick + D2H + sync
+        from optimax_rogue_b200.logic.moves import pack_moves
         host_moves = [torch.empty((G, 2), dtype=torch.uint8, pin_memory=True) for _ in range(4)]
-        for hm in host_moves:
-            hm.copy_(moves[0].cpu())
-        host_res = torch.empty((G,), dtype=torch.uint8, pin_memory=True)
+        host_cmds = [torch.empty((G,), dtype=torch.uint8, pin_memory=True) for _ in range(4)]     # nibble-packed
+        for hm, hc in zip(host_moves, host_cmds):
+            m = moves[0].cpu()
+            hm.copy_(m)
+            hc.copy_(pack_moves(m[:, 0], m[:, 1]))
+        host_res = [torch.empty((G,), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
         k_e2e = max(10, min(K, 200))
-        # one bound stepper per (batch, command buffer): BatchedUpdater.host_stepper is the public call for
-        # host-side loops; each step() = H2D commands + tick + D2H results + stream sync
-        steppers = [upd.host_stepper(batches[k % n_batches], host_moves[k % 4], host_res)
-                    for k in range(min(k_e2e, 4 * n_batches))]
-        for k in range(3):
-            steppers[k % len(steppers)]()
-        barrier()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record(stream)
-        for k in range(k_e2e):
-            steppers[k % len(steppers)]()  # synchronous: the caller can read host_res after each call
-        e3.record(stream)
-        torch.cuda.synchronize(dev)
-        barrier()
-        ms_e2e = e2.elapsed_time(e3)
+
+        def time_host_loop(cmd_bufs, sync):
+            # one bound stepper per (batch, command buffer): BatchedUpdater.host_stepper is the public call for
+            # host-side loops; each step() = H2D commands + tick + D2H results (+ stream sync when sync=True)
+            steppers = [upd.host_stepper(batches[k % n_batches], cmd_bufs[k % 4], host_res[k % 2], sync=sync)
+                        for k in range(min(k_e2e, 4 * n_batches))]
+            evs = [torch.cuda.Event(), torch.cuda.Event()]
+            for k in range(3):
+                steppers[k % len(steppers)]()
+            torch.cuda.synchronize(dev)
+            barrier()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            if sync:
+                for k in range(k_e2e):
+                    steppers[k % len(steppers)]()  # synchronous: the caller can read host_res after each call
+            else:
+                # two independent batches in flight: step k is enqueued, then the host waits for step k-1's
+                # results (its own result buffer) -- every step's results still reach the host
+                for k in range(k_e2e):
+                    steppers[k % len(steppers)]()
+                    evs[k & 1].record(stream)
+                    if k:
+                        evs[(k - 1) & 1].synchronize()
+                evs[(k_e2e - 1) & 1].synchronize()
+            eb.record(stream)
+            torch.cuda.synchronize(dev)
+            barrier()
+            return ea.elapsed_time(eb)
+
+        ms_e2e_unpacked = time_host_loop(host_moves, True)
+        ms_e2e = time_host_loop(host_cmds, True)
+        ms_e2e_pipelined = time_host_loop(host_cmds, False)
 
         # ---- rollout (extra): fused T-tick kernel, both bots on device
         T = args.rollout_ticks
@@ -375,6 +399,8 @@ def run_b200(args, rank, local_rank, world):
 
     ms_total = max_over_ranks(ms_total)
     ms_e2e = max_over_ranks(ms_e2e)
+    ms_e2e_unpacked = max_over_ranks(ms_e2e_unpacked)
+    ms_e2e_pipelined = max_over_ranks(ms_e2e_pipelined)
     ms_roll = max_over_ranks(ms_roll)
     ms_r1 = max_over_ranks(ms_r1)
     ms_r1_roll = max_over_ranks(ms_r1_roll)
@@ -401,11 +427,18 @@ def run_b200(args, rank, local_rank, world):
                        'launch': 'K steps captured in one CUDA graph'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (tr or {}).get('dram_bytes_per_launch'), 'peak_source': peak_src,
-                         'kernel': 'k_step<EMPTY,false,false>', 'alg_bytes_per_game_tick': B_ALG,
+                         'kernel': 'k_step_pipe<EMPTY,CMD_BYTES>', 'alg_bytes_per_game_tick': B_ALG,
                          'games_per_launch': G},
             'e2e': {'value': world * G * k_e2e / (ms_e2e * 1e-3), 'unit': UNIT,
-                    'h2d_bytes_per_step': 2 * G, 'd2h_bytes_per_step': G, 'steps': k_e2e,
-                    'api': 'BatchedUpdater.host_stepper(state, pinned host uint8[N,2], pinned host uint8[N])() = orx_step_host_sync: commands and results cross PCIe inside the tick kernel, stream sync every step'},
+                    'h2d_bytes_per_step': G, 'd2h_bytes_per_step': G, 'steps': k_e2e,
+                    'api': 'BatchedUpdater.host_stepper(state, pinned host uint8[N] commands p1|p2<<4, pinned host uint8[N] results)() '
+                           '= orx_step_host_packed_sync: commands and results cross PCIe inside the tick kernel, stream sync every step',
+                    'unpacked': {'value': world * G * k_e2e / (ms_e2e_unpacked * 1e-3), 'h2d_bytes_per_step': 2 * G,
+                                 'd2h_bytes_per_step': G, 'api': 'same call with uint8[N,2] commands (orx_step_host_sync)'},
+                    'pipelined': {'value': world * G * k_e2e / (ms_e2e_pipelined * 1e-3), 'h2d_bytes_per_step': G,
+                                  'd2h_bytes_per_step': G,
+                                  'api': 'host_stepper(..., sync=False) = orx_step_host_packed on two independent batches in flight; '
+                                         'the host waits on step k-1\'s event after enqueueing step k'}},
             'gpu_launches': K,
             'rollout': {'value': roll_ticks_all / (ms_roll * 1e-3), 'unit': UNIT, 'ticks_per_launch': T,
                         'launches': r_launches, 'fused': True,

@@ -22,7 +22,9 @@
  *   orx_rollout     the tick loop  optimax_rogue/server/main.py:110-113 with both bots inlined
  *   orx_replay      the same loop with both players' commands queued in advance
  *   orx_observe     GameState.view_for  optimax_rogue/game/state.py:53-58
+ *   orx_step_packed the same tick with both players' commands of a game in one byte (p1 | p2 << 4)
  *   orx_step_host   orx_step with host command/result buffers (what a remote caller holds);
+ *   orx_step_host_packed(_sync)  the host-buffer tick with nibble-packed commands (half the PCIe bytes)
  *   orx_step_host_sync  the same plus a stream synchronisation (Server.update returns the result, server.py:132-138)
  *
  * Integer codes are the reference's enum values and must not change.
@@ -162,6 +164,19 @@ int orx_step_host(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves
 int orx_step_host_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
                        uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
                        uint64_t game_id_base, void* cuda_stream);
+
+/* Nibble-packed commands: cmds uint8[n], game i's byte = p1_move | (p2_move << 4); nibbles outside
+ * 1..5 are Stay. Everything else is orx_step / orx_step_host / orx_step_host_sync: same kernels,
+ * same results, half the command bytes (the command stream is what bounds the host-buffer path).
+ * cmds_dev/result_dev are only used for pageable host buffers and may be NULL for pinned ones. */
+int orx_step_packed(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmds, uint8_t* result,
+                    OrxEvent* events, int64_t n, uint64_t game_id_base, void* cuda_stream);
+int orx_step_host_packed(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmds_host,
+                         uint8_t* result_host, uint8_t* cmds_dev, uint8_t* result_dev, int64_t n,
+                         uint64_t game_id_base, void* cuda_stream);
+int orx_step_host_packed_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmds_host,
+                              uint8_t* result_host, uint8_t* cmds_dev, uint8_t* result_dev, int64_t n,
+                              uint64_t game_id_base, void* cuda_stream);
 
 /* Command generation for scripted bots; ORX_BOT_NONE leaves that player's byte untouched. */
 int orx_bot_moves(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2,

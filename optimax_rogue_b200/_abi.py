@@ -88,6 +88,12 @@ PROTOTYPES = {
                             C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_step': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step_packed': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step_host_packed': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step_host_packed_sync': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_step_host': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_step_host_sync': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,

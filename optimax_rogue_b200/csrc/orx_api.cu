@@ -54,8 +54,8 @@ __device__ __forceinline__ const uint8_t* stage_tiles(const Params& P, uint8_t* 
 // per-game traffic is 29 B of planes in, 29 B out, 2 B of commands in, 1 B of result out.
 template <int DGEN, bool NPC, bool EV>
 __global__ void __launch_bounds__(kThreads, 4)
-k_step(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result,
-       uint2* __restrict__ events, int max_ev)
+k_step(const __grid_constant__ Params P, const void* __restrict__ moves, uint8_t* __restrict__ result,
+       uint2* __restrict__ events, int max_ev, int packed)
 {
     extern __shared__ uint8_t smem[];
     __shared__ CmdEntry lut[256];
@@ -72,7 +72,13 @@ k_step(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, uin
     const int tick = (int)ldg_u32(reinterpret_cast<const uint32_t*>(P.tick) + i);
     const int2 dep = ldg_s32x2(P.depth + i);
     const int status = (int)ldg_u8(P.status + i);
-    const uint32_t mv = ldg_u16(moves + i);
+    uint32_t mv;
+    if (packed) {     // one byte per game: p1 in the low nibble, p2 in the high nibble
+        const uint32_t c = ldg_u8(static_cast<const uint8_t*>(moves) + i);
+        mv = (c & 15u) | ((c >> 4) << 8);
+    } else {
+        mv = ldg_u16(static_cast<const uint16_t*>(moves) + i);
+    }
     EvSink<EV> ev{EV ? events + (size_t)i * max_ev : nullptr, 0, max_ev};
     if (status != ORX_RESULT_IN_PROGRESS) {   // finished lanes are frozen until reset
         result[i] = (uint8_t)status;
@@ -359,25 +365,25 @@ Params offset_params(const Params& P, int64_t off, int64_t n)
     return T;
 }
 
-template <int DGEN>
-int launch_pipe(const Params& P, const uint16_t* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, cudaStream_t s)
+template <int DGEN, int CMD>
+int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, cudaStream_t s)
 {
     const size_t smem = pipe_smem_bytes((int)tiles_bytes);
     // Launch geometry depends only on (device, kernel, smem): look it up once per process, the
     // occupancy query costs more than the launch itself. (A cache of device properties, not state.)
-    static int cache_sms[64] = {0}, cache_per_sm[64][2] = {{0}};
-    static size_t cache_smem[64][2] = {{0}};
+    static int cache_sms[64] = {0}, cache_per_sm[64][4] = {{0}};
+    static size_t cache_smem[64][4] = {{0}};
     int dev = 0;
     cudaGetDevice(&dev);
-    const int slot = dev & 63, kd = DGEN == ORX_DGEN_EMPTY ? 0 : 1;
+    const int slot = dev & 63, kd = (DGEN == ORX_DGEN_EMPTY ? 0 : 1) + 2 * CMD;
     if (cache_sms[slot] == 0 || cache_smem[slot][kd] != smem || cache_per_sm[slot][kd] == 0) {
         int sms = 148, per_sm = 2;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (smem > 48 * 1024) {
-            const cudaError_t e = cudaFuncSetAttribute(k_step_pipe<DGEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const cudaError_t e = cudaFuncSetAttribute(k_step_pipe<DGEN, CMD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e);
         }
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_pipe<DGEN>, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_pipe<DGEN, CMD>, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         cache_per_sm[slot][kd] = per_sm; cache_smem[slot][kd] = smem; cache_sms[slot] = sms;
     }
     const int sms = cache_sms[slot], per_sm = cache_per_sm[slot][kd];
@@ -389,8 +395,76 @@ int launch_pipe(const Params& P, const uint16_t* mv, uint8_t* result, unsigned i
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL, see k_step_pipe
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at; lc.numAttrs = ORX_PIPE_PDL ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, k_step_pipe<DGEN>, P, mv, result, n_tiles);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, k_step_pipe<DGEN, CMD>, P, mv, result, n_tiles);
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
+}
+
+// One tick; packed = 0: moves uint8[n][2], packed = 1: uint8[n] with p1 | p2 << 4.
+int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uint8_t* result,
+              OrxEvent* events, int64_t n, uint64_t game_id_base, void* cuda_stream, int packed)
+{
+    const int rc = check_common(cfg, st, n);
+    if (rc != ORX_OK) return rc;
+    if (!ids_ok(game_id_base, n)) return ORX_ERR_BAD_ARG;
+    if (moves == nullptr || result == nullptr || (!packed && !aligned(moves, 2)) || (events && !aligned(events, 8))) return ORX_ERR_BAD_ARG;
+    if (n == 0) return ORX_OK;
+    const Params P = make_params(cfg, st, n, game_id_base);
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const size_t smem = tiles_smem(cfg);
+    const size_t mv_stride = packed ? 1 : 2;        // command bytes per game
+    uint2* ev = reinterpret_cast<uint2*>(events);
+    const int max_ev = orx_max_events(cfg);
+    // Hot variant (no NPC slots, no event log): persistent TMA-pipelined kernel over the full
+    // 256-game tiles, the simple kernel for a ragged tail (< 256 games).
+    if (ev == nullptr && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
+        const unsigned int n_tiles = (unsigned int)(n / kTile);
+        const int64_t n_body = (int64_t)n_tiles * kTile;
+        const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
+        int rc2;
+        if (packed) rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES>(P, moves, result, n_tiles, 0, s)
+                                : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES>(P, moves, result, n_tiles, smem, s);
+        else rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES>(P, moves, result, n_tiles, 0, s)
+                         : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES>(P, moves, result, n_tiles, smem, s);
+        if (rc2 != ORX_OK || n_body == n) return rc2;
+        const Params T = offset_params(P, n_body, n - n_body);
+        const int tgrid = grid_for(n - n_body);
+        const uint8_t* tail = moves + (size_t)n_body * mv_stride;
+        if (empty) k_step<ORX_DGEN_EMPTY, false, false><<<tgrid, kThreads, 0, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
+        else k_step<ORX_DGEN_FIXED, false, false><<<tgrid, kThreads, smem, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
+        return launch_done();
+    }
+    const int grid = grid_for(n);
+    return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
+        if (ev != nullptr) k_step<DGEN, NPC, true><<<grid, kThreads, smem, s>>>(P, moves, result, ev, max_ev, packed);
+        else k_step<DGEN, NPC, false><<<grid, kThreads, smem, s>>>(P, moves, result, nullptr, max_ev, packed);
+        return launch_done();
+    });
+}
+
+int step_host_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
+                   uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
+                   uint64_t game_id_base, void* cuda_stream, int packed)
+{
+    if (moves_host == nullptr || result_host == nullptr) return ORX_ERR_BAD_ARG;
+    const int rc = check_common(cfg, st, n);
+    if (rc != ORX_OK) return rc;
+    if (n == 0) return ORX_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    // Pinned (page-locked, UVA-mapped) host buffers are read and written by the tick kernel itself:
+    // the TMA producer pulls each tile's commands over PCIe next to its HBM planes and the results
+    // stream back the same way, so there is no separate copy launch and the transfer overlaps the
+    // compute tile by tile. Pageable buffers fall back to staged cudaMemcpyAsync copies.
+    void *mv_map = nullptr, *res_map = nullptr;
+    if (getenv("ORX_HOST_STAGED") == nullptr && host_mapped(moves_host, &mv_map) && host_mapped(result_host, &res_map))
+        return step_impl(cfg, st, static_cast<const uint8_t*>(mv_map), static_cast<uint8_t*>(res_map), nullptr, n,
+                         game_id_base, cuda_stream, packed);
+    if (moves_dev == nullptr || result_dev == nullptr) return ORX_ERR_BAD_ARG;
+    cudaError_t e = cudaMemcpyAsync(moves_dev, moves_host, (size_t)n * (packed ? 1 : 2), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return cuda_fail(e);
+    const int rs = step_impl(cfg, st, moves_dev, result_dev, nullptr, n, game_id_base, cuda_stream, packed);
+    if (rs != ORX_OK) return rs;
+    e = cudaMemcpyAsync(result_host, result_dev, (size_t)n, cudaMemcpyDeviceToHost, s);
+    return e == cudaSuccess ? ORX_OK : cuda_fail(e);
 }
 
 }  // namespace
@@ -439,69 +513,44 @@ int orx_reset(const OrxConfig* cfg, const OrxState* st, const uint8_t* mask, int
 int orx_step(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uint8_t* result,
              OrxEvent* events, int64_t n, uint64_t game_id_base, void* cuda_stream)
 {
-    const int rc = check_common(cfg, st, n);
-    if (rc != ORX_OK) return rc;
-    if (!ids_ok(game_id_base, n)) return ORX_ERR_BAD_ARG;
-    if (moves == nullptr || result == nullptr || !aligned(moves, 2) || (events && !aligned(events, 8))) return ORX_ERR_BAD_ARG;
-    if (n == 0) return ORX_OK;
-    const Params P = make_params(cfg, st, n, game_id_base);
-    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    const size_t smem = tiles_smem(cfg);
-    const uint16_t* mv = reinterpret_cast<const uint16_t*>(moves);
-    uint2* ev = reinterpret_cast<uint2*>(events);
-    const int max_ev = orx_max_events(cfg);
-    // Hot variant (no NPC slots, no event log): persistent TMA-pipelined kernel over the full
-    // 256-game tiles, the simple kernel for a ragged tail (< 256 games).
-    if (ev == nullptr && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
-        const unsigned int n_tiles = (unsigned int)(n / kTile);
-        const int64_t n_body = (int64_t)n_tiles * kTile;
-        int rc2 = cfg->dgen_kind == ORX_DGEN_EMPTY ? launch_pipe<ORX_DGEN_EMPTY>(P, mv, result, n_tiles, 0, s)
-                                                   : launch_pipe<ORX_DGEN_FIXED>(P, mv, result, n_tiles, smem, s);
-        if (rc2 != ORX_OK || n_body == n) return rc2;
-        const Params T = offset_params(P, n_body, n - n_body);
-        const int tgrid = grid_for(n - n_body);
-        if (cfg->dgen_kind == ORX_DGEN_EMPTY) k_step<ORX_DGEN_EMPTY, false, false><<<tgrid, kThreads, 0, s>>>(T, mv + n_body, result + n_body, nullptr, max_ev);
-        else k_step<ORX_DGEN_FIXED, false, false><<<tgrid, kThreads, smem, s>>>(T, mv + n_body, result + n_body, nullptr, max_ev);
-        return launch_done();
-    }
-    const int grid = grid_for(n);
-    return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
-        if (ev != nullptr) k_step<DGEN, NPC, true><<<grid, kThreads, smem, s>>>(P, mv, result, ev, max_ev);
-        else k_step<DGEN, NPC, false><<<grid, kThreads, smem, s>>>(P, mv, result, nullptr, max_ev);
-        return launch_done();
-    });
+    return step_impl(cfg, st, moves, result, events, n, game_id_base, cuda_stream, 0);
+}
+
+int orx_step_packed(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmds, uint8_t* result,
+                    OrxEvent* events, int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    return step_impl(cfg, st, cmds, result, events, n, game_id_base, cuda_stream, 1);
 }
 
 int orx_step_host(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
                   uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
                   uint64_t game_id_base, void* cuda_stream)
 {
-    if (moves_host == nullptr || result_host == nullptr || moves_dev == nullptr || result_dev == nullptr) return ORX_ERR_BAD_ARG;
-    const int rc = check_common(cfg, st, n);
-    if (rc != ORX_OK) return rc;
-    if (n == 0) return ORX_OK;
-    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    // Pinned (page-locked, UVA-mapped) host buffers are read and written by the tick kernel itself:
-    // the TMA producer pulls each tile's commands over PCIe next to its HBM planes and the results
-    // stream back the same way, so there is no separate copy launch and the transfer overlaps the
-    // compute tile by tile. Pageable buffers fall back to staged cudaMemcpyAsync copies.
-    void *mv_map = nullptr, *res_map = nullptr;
-    if (getenv("ORX_HOST_STAGED") == nullptr && host_mapped(moves_host, &mv_map) && host_mapped(result_host, &res_map))
-        return orx_step(cfg, st, static_cast<const uint8_t*>(mv_map), static_cast<uint8_t*>(res_map), nullptr, n,
-                        game_id_base, cuda_stream);
-    cudaError_t e = cudaMemcpyAsync(moves_dev, moves_host, (size_t)n * 2, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return cuda_fail(e);
-    const int rs = orx_step(cfg, st, moves_dev, result_dev, nullptr, n, game_id_base, cuda_stream);
-    if (rs != ORX_OK) return rs;
-    e = cudaMemcpyAsync(result_host, result_dev, (size_t)n, cudaMemcpyDeviceToHost, s);
-    return e == cudaSuccess ? ORX_OK : cuda_fail(e);
+    return step_host_impl(cfg, st, moves_host, result_host, moves_dev, result_dev, n, game_id_base, cuda_stream, 0);
 }
 
 int orx_step_host_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
                        uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
                        uint64_t game_id_base, void* cuda_stream)
 {
-    const int rc = orx_step_host(cfg, st, moves_host, result_host, moves_dev, result_dev, n, game_id_base, cuda_stream);
+    const int rc = step_host_impl(cfg, st, moves_host, result_host, moves_dev, result_dev, n, game_id_base, cuda_stream, 0);
+    if (rc != ORX_OK) return rc;
+    const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
+    return e == cudaSuccess ? ORX_OK : cuda_fail(e);
+}
+
+int orx_step_host_packed(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmds_host,
+                         uint8_t* result_host, uint8_t* cmds_dev, uint8_t* result_dev, int64_t n,
+                         uint64_t game_id_base, void* cuda_stream)
+{
+    return step_host_impl(cfg, st, cmds_host, result_host, cmds_dev, result_dev, n, game_id_base, cuda_stream, 1);
+}
+
+int orx_step_host_packed_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmds_host,
+                              uint8_t* result_host, uint8_t* cmds_dev, uint8_t* result_dev, int64_t n,
+                              uint64_t game_id_base, void* cuda_stream)
+{
+    const int rc = step_host_impl(cfg, st, cmds_host, result_host, cmds_dev, result_dev, n, game_id_base, cuda_stream, 1);
     if (rc != ORX_OK) return rc;
     const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
     return e == cudaSuccess ? ORX_OK : cuda_fail(e);

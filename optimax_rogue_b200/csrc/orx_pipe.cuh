@@ -43,7 +43,10 @@ constexpr uint32_t T4 = 4u * kTile, T8 = 8u * kTile, T2 = 2u * kTile, T1 = kTile
 constexpr uint32_t OFF_POS = 0, OFF_HP = T4, OFF_ST = 2 * T4, OFF_TICK = 3 * T4, OFF_EP = 4 * T4,
                    OFF_DEPTH = 5 * T4, OFF_STATUS = 5 * T4 + T8, OFF_MOVES = OFF_STATUS + T1, OFF_RESULT = OFF_MOVES + T2,
                    STAGE_BYTES = OFF_RESULT + T1;
-constexpr uint32_t LOAD_BYTES = 5 * T4 + T8 + T1 + T2;          // per tile, HBM -> smem
+constexpr uint32_t PLANE_LOAD_BYTES = 5 * T4 + T8 + T1;         // per tile, HBM -> smem, without the commands
+// Command formats: CMD_BYTES = uint8[n][2] (p1, p2); CMD_NIBBLES = uint8[n], p1 in the low nibble,
+// p2 in the high nibble (halves the command traffic when the commands come over PCIe).
+constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1;
 static_assert(kTile % 32 == 0 && (T1 % 16) == 0, "bulk copies move multiples of 16 bytes");
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,11 +98,13 @@ __device__ __forceinline__ void sts_s32x2(uint32_t a, int x, int y) { asm volati
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // n_tiles full tiles of kTile games; the caller handles a ragged tail with the simple kernel.
-template <int DGEN>
+template <int DGEN, int CMD>
 __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
-k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result,
+k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, uint8_t* __restrict__ result,
             unsigned int n_tiles)
 {
+    constexpr uint32_t MV_BYTES = CMD == CMD_NIBBLES ? T1 : T2, LOAD_BYTES = PLANE_LOAD_BYTES + MV_BYTES;
+    const uint8_t* moves = static_cast<const uint8_t*>(moves_v);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stages = smem;                                             // kStages * STAGE_BYTES
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);   // full[kStages], done[kStages]
@@ -147,7 +152,7 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
             bulk_load(base + OFF_EP, P.episode + g, T4, bar);
             bulk_load(base + OFF_DEPTH, P.depth + g, T8, bar);
             bulk_load(base + OFF_STATUS, P.status + g, T1, bar);
-            bulk_load(base + OFF_MOVES, moves + g, T2, bar);
+            bulk_load(base + OFF_MOVES, moves + g * (MV_BYTES / kTile), MV_BYTES, bar);
         };
         if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // all earlier work in the stream is complete and visible
         const unsigned int pre = my_tiles < (unsigned)kStages ? my_tiles : (unsigned)kStages;
@@ -192,7 +197,13 @@ k_step_pipe(const __grid_constant__ Params P, const uint16_t* __restrict__ moves
         const uint32_t ep = lds_u32(b4 + OFF_EP);
         const int2 dep = lds_s32x2(b8 + OFF_DEPTH);
         const int status = (int)lds_u8(b1 + OFF_STATUS);
-        const uint32_t mv = lds_u16(b2 + OFF_MOVES);
+        uint32_t mv;
+        if (CMD == CMD_NIBBLES) {
+            const uint32_t c = lds_u8(b1 + OFF_MOVES);
+            mv = (c & 15u) | ((c >> 4) << 8);
+        } else {
+            mv = lds_u16(b2 + OFF_MOVES);
+        }
         int res = status;
         if (status == ORX_RESULT_IN_PROGRESS) {          // finished lanes are frozen until reset
             Lane L;

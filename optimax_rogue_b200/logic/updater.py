@@ -118,7 +118,7 @@ class BatchedUpdater:
 
     # -- the tick --------------------------------------------------------------------------------
     def update(self, game_state: BatchedGameState, player1_move, player2_move=None, *,
-               want_events: bool = False, out: typing.Optional[torch.Tensor] = None):
+               want_events: bool = False, out: typing.Optional[torch.Tensor] = None, packed: bool = False):
         """One tick for every game (updater.py:76-162).
 
         ``player1_move``/``player2_move``: uint8[N] Move codes, or pass a single uint8[N,2]
@@ -127,59 +127,77 @@ class BatchedUpdater:
         back in a CPU tensor. Returns ``(result uint8[N] of UpdateResult codes, events)`` where
         events is None or an int32[N, max_events, 2] tensor of raw OrxEvent records
         (see logic/updates.py:decode_events).
+
+        ``packed=True``: ``player1_move`` is one uint8[N] tensor holding both commands of a game,
+        ``p1 | p2 << 4`` (``logic.moves.pack_moves``); same tick, half the command bytes.
         """
         gs = game_state
         _require_cuda(gs)
-        mv = self._as_moves(gs, player1_move, player2_move)
+        if packed:
+            mv = player1_move
+            if (player2_move is not None or not isinstance(mv, torch.Tensor) or mv.dtype != torch.uint8
+                    or tuple(mv.shape) != (gs.n,) or not mv.is_contiguous()):
+                raise ValueError(f'packed commands must be one contiguous uint8 tensor of shape ({gs.n},)')
+        else:
+            mv = self._as_moves(gs, player1_move, player2_move)
         if not mv.is_cuda:
             if want_events:
                 raise ValueError('events are only produced for device-resident moves')
-            return self._update_host(gs, mv, out), None
+            return self._update_host(gs, mv, out, packed), None
         cfg, st = self._cfg(gs)
         result = out if out is not None else torch.empty((gs.n,), dtype=torch.uint8, device=gs.device)
         events = None
         if want_events:
             events = torch.empty((gs.n, _abi.MAX_EVENTS_BASE + gs.cfg.n_npc, 2), dtype=torch.int32,
                                  device=gs.device)
+        fn = _lib.lib().orx_step_packed if packed else _lib.lib().orx_step
         with _on_device(gs.device):
-            rc = _lib.lib().orx_step(C.byref(cfg), C.byref(st), mv.data_ptr(), result.data_ptr(),
-                                     events.data_ptr() if events is not None else None, gs.n,
-                                     gs.game_id_base, _stream_ptr(gs.device))
-        _lib.check(rc, 'orx_step')
+            rc = fn(C.byref(cfg), C.byref(st), mv.data_ptr(), result.data_ptr(),
+                    events.data_ptr() if events is not None else None, gs.n,
+                    gs.game_id_base, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_step_packed' if packed else 'orx_step')
         if events is not None:
             self._advance_order(gs, events)
         return result, events
 
-    def _update_host(self, gs, moves_host, out):
+    def _update_host(self, gs, moves_host, out, packed=False):
         cfg, st = self._cfg(gs)
         if not hasattr(self, '_stage') or self._stage[0].shape[0] != gs.n or self._stage[0].device != gs.device:
             self._stage = (torch.empty((gs.n, 2), dtype=torch.uint8, device=gs.device),
                            torch.empty((gs.n,), dtype=torch.uint8, device=gs.device))
         result_host = out if out is not None else torch.empty((gs.n,), dtype=torch.uint8, pin_memory=True)
+        fn = _lib.lib().orx_step_host_packed if packed else _lib.lib().orx_step_host
         with _on_device(gs.device):
-            rc = _lib.lib().orx_step_host(C.byref(cfg), C.byref(st), moves_host.data_ptr(),
-                                          result_host.data_ptr(), self._stage[0].data_ptr(),
-                                          self._stage[1].data_ptr(), gs.n, gs.game_id_base,
-                                          _stream_ptr(gs.device))
-        _lib.check(rc, 'orx_step_host')
+            rc = fn(C.byref(cfg), C.byref(st), moves_host.data_ptr(), result_host.data_ptr(),
+                    self._stage[0].data_ptr(), self._stage[1].data_ptr(), gs.n, gs.game_id_base,
+                    _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_step_host_packed' if packed else 'orx_step_host')
         return result_host
 
-    def host_stepper(self, game_state: BatchedGameState, moves_host: torch.Tensor, result_host: torch.Tensor):
+    def host_stepper(self, game_state: BatchedGameState, moves_host: torch.Tensor, result_host: torch.Tensor,
+                     sync: bool = True):
         """Binds one game state and a pair of HOST buffers (pin them: ``pin_memory()``) and returns
         ``step()``: one call = one tick with the commands currently in ``moves_host``; when it returns,
         ``result_host`` holds the tick's UpdateResult codes (``orx_step_host_sync``). This is
         ``update(gs, moves_host, out=result_host)`` + stream synchronise with the per-call argument
-        marshalling done once, for host loops that tick every few tens of microseconds."""
+        marshalling done once, for host loops that tick every few tens of microseconds.
+
+        ``moves_host`` is uint8[N,2] (p1, p2) or, nibble-packed, uint8[N] with ``p1 | p2 << 4``
+        (``orx_step_host_packed_sync``: half the PCIe bytes). ``sync=False`` only enqueues the tick
+        (``orx_step_host`` / ``orx_step_host_packed``): the caller synchronises, e.g. with an event,
+        before it reads ``result_host`` -- for loops that keep several independent batches in flight."""
         gs = game_state
         _require_cuda(gs)
+        packed = moves_host.dim() == 1
         if (moves_host.is_cuda or result_host.is_cuda or moves_host.dtype != torch.uint8 or result_host.dtype != torch.uint8
-                or tuple(moves_host.shape) != (gs.n, 2) or tuple(result_host.shape) != (gs.n,)
+                or tuple(moves_host.shape) not in ((gs.n, 2), (gs.n,)) or tuple(result_host.shape) != (gs.n,)
                 or not moves_host.is_contiguous() or not result_host.is_contiguous()):
-            raise ValueError(f'need contiguous CPU uint8 tensors of shape ({gs.n}, 2) and ({gs.n},)')
+            raise ValueError(f'need contiguous CPU uint8 tensors of shape ({gs.n}, 2) or ({gs.n},), and ({gs.n},)')
         cfg, st = self._cfg(gs)
         stage = (torch.empty((gs.n, 2), dtype=torch.uint8, device=gs.device),
                  torch.empty((gs.n,), dtype=torch.uint8, device=gs.device))
-        fn = _lib.lib().orx_step_host_sync
+        name = 'orx_step_host' + ('_packed' if packed else '') + ('_sync' if sync else '')
+        fn = getattr(_lib.lib(), name)
         args = (C.byref(cfg), C.byref(st), C.c_void_p(moves_host.data_ptr()), C.c_void_p(result_host.data_ptr()),
                 C.c_void_p(stage[0].data_ptr()), C.c_void_p(stage[1].data_ptr()), C.c_int64(gs.n),
                 C.c_uint64(gs.game_id_base), C.c_void_p(_stream_ptr(gs.device)))
@@ -191,7 +209,7 @@ class BatchedUpdater:
                 torch.cuda.set_device(dev_index)
             rc = fn(*args)
             if rc != 0:
-                _lib.check(rc, 'orx_step_host_sync')
+                _lib.check(rc, name)
             return keep[4]
         return step
 

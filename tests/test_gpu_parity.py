@@ -238,6 +238,72 @@ def test_host_stepper_matches_oracle():
     gu.assert_state_equal(gs, orc, 'host stepper, pageable')
 
 
+@pytest.mark.parametrize('n,fixed,npc', [(3000, False, 0), (256, False, 0), (100, False, 0), (1500, True, 0), (700, False, 2)])
+def test_packed_commands_match_oracle(n, fixed, npc):
+    """orx_step_packed (p1 | p2 << 4 in one byte): device, pinned-host and pageable-host commands all
+    play the same tick as the oracle does on the unpacked commands, invalid nibbles included."""
+    from optimax_rogue_b200.logic.moves import pack_moves, unpack_moves
+    kw = {}
+    if fixed:
+        tiles = np.ones((12, 9), dtype=np.uint8)
+        tiles[0, :] = tiles[-1, :] = 2; tiles[:, 0] = tiles[:, -1] = 2; tiles[5, 3:6] = 2
+        kw = dict(width=12, height=9, dgen_kind=_abi.DGEN_FIXED, fixed_tiles=tiles)
+    cfg = SimConfig(max_ticks=40, seed=11, auto_reset=True, n_npc=npc, **kw)
+    gs, upd, orc = gu.make_pair(cfg, n)
+    rng = np.random.default_rng(n)
+    pinned = torch.empty((n,), dtype=torch.uint8, pin_memory=True)
+    pinned_res = torch.empty((n,), dtype=torch.uint8, pin_memory=True)
+    step = upd.host_stepper(gs, pinned, pinned_res)
+    pageable = torch.empty((n,), dtype=torch.uint8)
+    for t in range(60):
+        mv = rng.integers(0, 16 if t % 7 == 0 else 6, size=(n, 2), dtype=np.uint8)       # nibbles 0 and 6..15 are Stay
+        packed = pack_moves(mv[:, 0], mv[:, 1])
+        a, b = unpack_moves(packed)
+        assert np.array_equal(a, mv[:, 0]) and np.array_equal(b, mv[:, 1])
+        res_o, ev_o = orc.step(mv, want_events=True)
+        if t % 3 == 0:
+            res, ev = upd.update(gs, torch.from_numpy(packed).cuda(), packed=True, want_events=(t % 6 == 0))
+            res = res.cpu().numpy()
+            if ev is not None:
+                assert np.array_equal(ev.cpu().numpy(), ev_o)
+        elif t % 3 == 1:
+            pinned.copy_(torch.from_numpy(packed))
+            res = step().numpy()
+        else:
+            pageable.copy_(torch.from_numpy(packed))
+            res, _ = upd.update(gs, pageable, packed=True)
+            torch.cuda.synchronize()
+            res = res.numpy()
+        assert np.array_equal(res, res_o), f'tick {t}'
+    gu.assert_state_equal(gs, orc, 'packed commands')
+    with pytest.raises(ValueError):
+        upd.update(gs, torch.zeros((n, 2), dtype=torch.uint8, device='cuda'), packed=True)
+
+
+def test_host_stepper_async_two_batches_in_flight():
+    """sync=False: two independent batches ticked back to back, results read after one event wait each."""
+    cfg = SimConfig(max_ticks=30, seed=21, auto_reset=True)
+    pairs = [gu.make_pair(cfg, 2048, game_id_base=b * 2048) for b in range(2)]
+    bufs = [(torch.empty((2048,), dtype=torch.uint8, pin_memory=True), torch.empty((2048,), dtype=torch.uint8, pin_memory=True))
+            for _ in range(2)]
+    steps = [pairs[b][1].host_stepper(pairs[b][0], bufs[b][0], bufs[b][1], sync=False) for b in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
+    from optimax_rogue_b200.logic.moves import pack_moves
+    for t in range(40):
+        want = []
+        for b in range(2):
+            mv = pairs[b][2].bot_moves(1, 2)
+            bufs[b][0].copy_(torch.from_numpy(pack_moves(mv[:, 0], mv[:, 1])))
+            steps[b]()
+            evs[b].record()
+            want.append(pairs[b][2].step(mv)[0])
+        for b in range(2):
+            evs[b].synchronize()
+            assert np.array_equal(bufs[b][1].numpy(), want[b]), (t, b)
+    for b in range(2):
+        gu.assert_state_equal(pairs[b][0], pairs[b][2], f'async batch {b}')
+
+
 def test_observe():
     cfg = SimConfig(max_ticks=0, seed=4)
     gs, upd, orc = gu.make_pair(cfg, 2000)

@@ -146,3 +146,18 @@ def test_game_state_snapshot_is_byte_identical_to_reference():
     # and the reference can load what we write
     back = ref.state.GameState.from_prims(ours.to_prims())
     assert back == theirs
+
+
+def test_pack_moves_roundtrip():
+    """Nibble-packed command format of orx_step_packed: p1 | p2 << 4, on numpy and torch alike."""
+    import torch
+    from optimax_rogue_b200.logic.moves import pack_moves, unpack_moves
+    rng = np.random.default_rng(0)
+    mv = rng.integers(0, 16, size=(1000, 2), dtype=np.uint8)
+    packed = pack_moves(mv[:, 0], mv[:, 1])
+    assert packed.dtype == np.uint8 and np.array_equal(packed, mv[:, 0] + 16 * mv[:, 1])
+    a, b = unpack_moves(packed)
+    assert np.array_equal(a, mv[:, 0]) and np.array_equal(b, mv[:, 1])
+    t = torch.from_numpy(mv)
+    tp = pack_moves(t[:, 0], t[:, 1])
+    assert tp.dtype == torch.uint8 and np.array_equal(tp.numpy(), packed)

@@ -44,3 +44,27 @@ e1.record(); torch.cuda.synchronize(); print('D2H 1 MB memcpy: %.1f us' % (e0.el
 st1 = [upd.host_stepper(bs[k % 9], hm[k % 4], hr) for k in range(36)]
 def run(k): st1[k % 36]()
 print('host_stepper (sync inside)    : %.1f us' % timeit(run, False))
+# nibble-packed commands, each direction on its own
+from optimax_rogue_b200.logic.moves import pack_moves
+hc = [pack_moves(m[:, 0], m[:, 1]).contiguous().pin_memory() for m in hm]
+dc = hc[0].cuda()
+print('packed: host cmds + host result, no sync : %.1f us' % timeit(lambda k: upd.update(bs[k % 9], hc[k % 4], out=hr, packed=True), False))
+print('packed: host cmds + host result, sync    : %.1f us' % timeit(lambda k: upd.update(bs[k % 9], hc[k % 4], out=hr, packed=True), True))
+print('packed: device cmds + device result, no sync: %.1f us' % timeit(lambda k: upd.update(bs[k % 9], dc, out=dr, packed=True), False))
+# mixed: call the C ABI directly with one side mapped
+import ctypes as C
+from optimax_rogue_b200 import _lib
+L = _lib.lib()
+def raw(k, cmds, res, packed):
+    gs = bs[k % 9]; cfg, st = upd._cfg(gs)
+    fn = L.orx_step_packed if packed else L.orx_step
+    rc = fn(C.byref(cfg), C.byref(st), cmds.data_ptr(), res.data_ptr(), None, gs.n, gs.game_id_base, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+print('packed: host cmds + device result, no sync: %.1f us' % timeit(lambda k: raw(k, hc[k % 4], dr, True), False))
+print('packed: device cmds + host result, no sync: %.1f us' % timeit(lambda k: raw(k, dc, hr, True), False))
+print('bytes : host cmds + device result, no sync: %.1f us' % timeit(lambda k: raw(k, hm[k % 4], dr, False), False))
+print('bytes : device cmds + host result, no sync: %.1f us' % timeit(lambda k: raw(k, dm, hr, False), False))
+st2 = [upd.host_stepper(bs[k % 9], hc[k % 4], hr) for k in range(36)]
+print('host_stepper packed (sync inside): %.1f us' % timeit(lambda k: st2[k % 36](), False))
+st3 = [upd.host_stepper(bs[k % 9], hc[k % 4], hr, sync=False) for k in range(36)]
+print('host_stepper packed (async)      : %.1f us' % timeit(lambda k: st3[k % 36](), False))
