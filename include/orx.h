@@ -2,7 +2,8 @@
  * orx.h -- C ABI of liborx.so, the B200 batched replacement for Optimax Rogue's turn
  * dynamics. Plain pointers and sizes only; every device buffer is owned by the caller
  * (PyTorch tensors on the host side); the library allocates nothing persistent, keeps
- * no global state and enqueues all work on the caller's CUDA stream.
+ * no game state of its own (only a mutex-guarded cache of per-device launch geometry),
+ * may be called from several host threads, and enqueues all work on the caller's CUDA stream.
  *
  * The reference (Tjstretchalot/optimax_rogue) is pure Python and has no FFI; its seams
  * are duck-typed objects. Each entry point below names the reference interface it

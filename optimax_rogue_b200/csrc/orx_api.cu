@@ -3,6 +3,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/orx.h"
 #include "orx_rules.cuh"
 #include "orx_pipe.cuh"
@@ -371,11 +373,14 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     const size_t smem = pipe_smem_bytes((int)tiles_bytes);
     // Launch geometry depends only on (device, kernel, smem): look it up once per process, the
     // occupancy query costs more than the launch itself. (A cache of device properties, not state.)
+    // Guarded by a mutex so that host threads driving different GPUs may call in concurrently.
+    static std::mutex cache_mu;
     static int cache_sms[64] = {0}, cache_per_sm[64][4] = {{0}};
     static size_t cache_smem[64][4] = {{0}};
     int dev = 0;
     cudaGetDevice(&dev);
     const int slot = dev & 63, kd = (DGEN == ORX_DGEN_EMPTY ? 0 : 1) + 2 * CMD;
+    std::unique_lock<std::mutex> lk(cache_mu);
     if (cache_sms[slot] == 0 || cache_smem[slot][kd] != smem || cache_per_sm[slot][kd] == 0) {
         int sms = 148, per_sm = 2;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -387,6 +392,7 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
         cache_per_sm[slot][kd] = per_sm; cache_smem[slot][kd] = smem; cache_sms[slot] = sms;
     }
     const int sms = cache_sms[slot], per_sm = cache_per_sm[slot][kd];
+    lk.unlock();
     unsigned int grid = (unsigned int)sms * (unsigned int)per_sm;       // persistent: every CTA resident
     if (grid > n_tiles) grid = n_tiles;
     cudaLaunchConfig_t lc = {};
