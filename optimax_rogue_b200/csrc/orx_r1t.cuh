@@ -121,12 +121,16 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
     bool moves[NM];
     int newcd0 = 0, newcd1 = 0;
     bool spend0 = false, spend1 = false;
+    uint32_t tgt[NM];      // target key of an acting mover; a per-slot sentinel no key can equal otherwise
 #pragma unroll
-    for (int j = 0; j < NM; ++j) { taken[j] = 0; credit[j] = 0; moves[j] = false; }
+    for (int j = 0; j < NM; ++j) {
+        taken[j] = 0; credit[j] = 0; moves[j] = false;
+        tgt[j] = (G.key[j] != DEAD && dl[j] != 0) ? G.key[j] + (uint32_t)dl[j] : (0xFFFF0000u | (uint32_t)j);
+    }
 #pragma unroll
     for (int m = 0; m < NM; ++m) {
-        if (G.key[m] == DEAD || dl[m] == 0) continue;
-        const uint32_t t = G.key[m] + (uint32_t)dl[m];
+        const uint32_t t = tgt[m];
+        if (t >= 0xFFFF0000u) continue;
         const int my_dmg = m < 2 ? G.damage[m] + min(G.mana[m], G.max_mana[m] / 3) : 2 + kd(G.key[m]) / 4;
         const bool m_on_cd = m < 2 && (m == 0 ? cd_pre0 : cd_pre1) > 0;
         bool has_occ = false;
@@ -138,7 +142,7 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
             if (m >= 2 && o >= 2) continue;                         // enemies do not fight each other
             const int amount = max(0, my_dmg - (o < 2 ? G.armor[o] : 0));
             const int o_cd = o < 2 ? (o == 0 ? cd_pre0 : cd_pre1) : 1;   // enemies never negate
-            if (dl[o] == 0) {
+            if (tgt[o] >= 0xFFFF0000u) {                            // the occupant stays
                 if (o < 2 && o_cd == 0) {                           // negated; the attacker is stunned
                     if (m == 0) { newcd0 = max(newcd0, 1); spend0 = true; }
                     if (m == 1) { newcd1 = max(newcd1, 1); spend1 = true; }
@@ -147,7 +151,7 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
                     if (m == 0) { spend0 = true; if (amount > 0) credit[o] |= 1; }
                     if (m == 1) { spend1 = true; if (amount > 0) credit[o] |= 2; }
                 }
-            } else if (G.key[o] + (uint32_t)dl[o] == G.key[m]) {    // mutual attack: half damage, cooldown
+            } else if (tgt[o] == G.key[m]) {                        // mutual attack: half damage, cooldown
                 taken[o] += amount / 2;
                 if (m == 0) { newcd0 = 3; spend0 = true; if (amount / 2 > 0) credit[o] |= 1; }
                 if (m == 1) { newcd1 = 3; spend1 = true; if (amount / 2 > 0) credit[o] |= 2; }
@@ -158,7 +162,7 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
 #pragma unroll
         for (int c = 0; c < NM; ++c) {
             if (c == m) continue;
-            if (G.key[c] == DEAD || dl[c] == 0 || G.key[c] + (uint32_t)dl[c] != t) continue;
+            if (tgt[c] != t) continue;
             contested = true;
             if (!hit && (m < 2 || c < 2) && !m_on_cd) {           // full damage on the contender's new location
                 hit = true;
@@ -178,7 +182,7 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
         if (G.key[m] == DEAD) continue;
         G.hp[m] -= taken[m];
         cnt.hits += taken[m] > 0;
-        if (moves[m]) G.key[m] += (uint32_t)dl[m];
+        if (moves[m]) G.key[m] = tgt[m];
     }
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
