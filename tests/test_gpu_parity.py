@@ -304,6 +304,42 @@ def test_host_stepper_async_two_batches_in_flight():
         gu.assert_state_equal(pairs[b][0], pairs[b][2], f'async batch {b}')
 
 
+def test_concurrent_host_threads_on_separate_streams():
+    """The library may be driven from several host threads at once (ctypes drops the GIL during the call):
+    four threads tick four independent batches on their own CUDA streams; every batch matches the oracle."""
+    import threading
+    cfg = SimConfig(max_ticks=40, seed=31, auto_reset=True)
+    n, ticks = 4096, 50
+    pairs = [gu.make_pair(cfg, n, game_id_base=b * n) for b in range(4)]
+    rng = np.random.default_rng(5)
+    plans = [rng.integers(1, 6, size=(ticks, n, 2), dtype=np.uint8) for _ in range(4)]
+    dev_plans = [torch.from_numpy(p).cuda() for p in plans]
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(b):
+        try:
+            gs, upd, _ = pairs[b]
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for t in range(ticks):
+                    upd.update(gs, dev_plans[b][t])
+            stream.synchronize()
+        except Exception as e:      # surfaced below
+            errors.append((b, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(b,)) for b in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for b in range(4):
+        for t in range(ticks):
+            pairs[b][2].step(plans[b][t])
+        gu.assert_state_equal(pairs[b][0], pairs[b][2], f'thread {b}')
+
+
 def test_observe():
     cfg = SimConfig(max_ticks=0, seed=4)
     gs, upd, orc = gu.make_pair(cfg, 2000)
