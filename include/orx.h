@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define ORX_ABI_VERSION 1
+#define ORX_ABI_VERSION 2
 
 /* logic/moves.py:6-12 */
 enum { ORX_MOVE_UP = 1, ORX_MOVE_RIGHT = 2, ORX_MOVE_DOWN = 3, ORX_MOVE_LEFT = 4, ORX_MOVE_STAY = 5 };
@@ -112,6 +112,11 @@ typedef struct OrxState {
     uint8_t* npc_pos;   /* [n][n_npc][2] */
     int16_t* npc_hp;    /* [n][n_npc]    */
     int32_t* npc_depth; /* [n][n_npc]    -1 = empty slot */
+    /* Tile scheduler scratch of this state: device uint32[4], zero-initialised by the caller, or NULL.
+     * With it the tick kernel hands its 256-game tiles out dynamically (CTAs that run slower take
+     * fewer), and leaves the words zero again when it completes; without it tiles are assigned
+     * statically. Never shared between states that may be ticked concurrently. */
+    uint32_t* sched;
 } OrxState;
 
 /* One replication-log record (logic/updates.py); slots of game i at events[i*max_events + k],

@@ -4,7 +4,7 @@ Kept free of torch so that the CPU test-suite can check the ABI without a GPU.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MAX_NPC = 8
 MAX_EVENTS_BASE = 4
@@ -50,6 +50,7 @@ class OrxState(C.Structure):
         ('pos', C.c_void_p), ('hp', C.c_void_p), ('depth', C.c_void_p), ('stairs', C.c_void_p),
         ('tick', C.c_void_p), ('episode', C.c_void_p), ('status', C.c_void_p),
         ('npc_pos', C.c_void_p), ('npc_hp', C.c_void_p), ('npc_depth', C.c_void_p),
+        ('sched', C.c_void_p),
     ]
 
 

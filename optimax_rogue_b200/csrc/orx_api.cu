@@ -368,7 +368,8 @@ Params offset_params(const Params& P, int64_t off, int64_t n)
 }
 
 template <int DGEN, int CMD>
-int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, cudaStream_t s)
+int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, unsigned int* sched,
+                cudaStream_t s)
 {
     const size_t smem = pipe_smem_bytes((int)tiles_bytes);
     // Launch geometry depends only on (device, kernel, smem): look it up once per process, the
@@ -401,7 +402,12 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL, see k_step_pipe
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at; lc.numAttrs = ORX_PIPE_PDL ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, k_step_pipe<DGEN, CMD>, P, mv, result, n_tiles);
+#ifdef ORX_PIPE_TRACE
+    static unsigned int trace_slot = 0;
+    const cudaError_t e = cudaLaunchKernelEx(&lc, k_step_pipe<DGEN, CMD>, P, mv, result, n_tiles, sched, trace_slot++);
+#else
+    const cudaError_t e = cudaLaunchKernelEx(&lc, k_step_pipe<DGEN, CMD>, P, mv, result, n_tiles, sched);
+#endif
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
 }
 
@@ -427,10 +433,11 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
         const int64_t n_body = (int64_t)n_tiles * kTile;
         const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
         int rc2;
-        if (packed) rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES>(P, moves, result, n_tiles, 0, s)
-                                : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES>(P, moves, result, n_tiles, smem, s);
-        else rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES>(P, moves, result, n_tiles, 0, s)
-                         : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES>(P, moves, result, n_tiles, smem, s);
+        unsigned int* sched = aligned(st->sched, 4) && getenv("ORX_STATIC_TILES") == nullptr ? st->sched : nullptr;
+        if (packed) rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES>(P, moves, result, n_tiles, 0, sched, s)
+                                : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES>(P, moves, result, n_tiles, smem, sched, s);
+        else rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES>(P, moves, result, n_tiles, 0, sched, s)
+                         : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES>(P, moves, result, n_tiles, smem, sched, s);
         if (rc2 != ORX_OK || n_body == n) return rc2;
         const Params T = offset_params(P, n_body, n - n_body);
         const int tgrid = grid_for(n - n_body);
@@ -479,6 +486,15 @@ extern "C" {
 
 int orx_abi_version(void) { return ORX_ABI_VERSION; }
 
+#ifdef ORX_PIPE_TRACE
+// Tuning builds only (not declared in orx.h): copies the per-CTA time stamps of the last 16 tick launches.
+int orx_debug_trace(unsigned long long* host_out)
+{
+    const cudaError_t e = cudaMemcpyFromSymbol(host_out, orx::g_trace, sizeof(orx::g_trace));
+    return e == cudaSuccess ? ORX_OK : ORX_ERR_CUDA_BASE - (int)e;
+}
+#endif
+
 const char* orx_strerror(int code)
 {
     if (code == ORX_OK) return "ok";
@@ -510,6 +526,11 @@ int orx_reset(const OrxConfig* cfg, const OrxState* st, const uint8_t* mask, int
     const Params P = make_params(cfg, st, n, game_id_base);
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     const int grid = grid_for(n);
+    // The scheduler words are zero between launches; a reset re-establishes that after an aborted run.
+    if (st->sched != nullptr && aligned(st->sched, 4)) {
+        const cudaError_t e = cudaMemsetAsync(st->sched, 0, 4 * sizeof(unsigned int), s);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
     return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
         k_reset<DGEN, NPC><<<grid, kThreads, 0, s>>>(P, mask, bump_episode);
         return launch_done();

@@ -1,6 +1,10 @@
 // Persistent, TMA-fed version of the tick kernel (the hot variant: no NPC slots, no event log).
 //
-// A CTA owns a strided set of 256-game tiles. One producer thread streams each tile's eight
+// Every CTA works through 256-game tiles: its first kStages tiles are fixed (blockIdx.x + i * grid),
+// the rest are claimed from a per-state counter (OrxState.sched) as stages free up, so that CTAs
+// which happen to run slower -- the spread of finishing times under static assignment was 6 us on
+// a 14 us launch -- take fewer tiles and the grid drains within one tile time. Without a counter
+// (sched == NULL) the assignment is the static stride. One producer thread streams each tile's eight
 // plane slices HBM -> shared memory with 1-D bulk copies (cp.async.bulk, completion on an
 // mbarrier), kStages tiles ahead of the eight compute warps; the compute warps pull their game
 // into registers, run tick_lane, write the new planes back into the same stage, and the producer
@@ -37,6 +41,7 @@ constexpr int kTile = ORX_PIPE_TILE;  // games per tile = compute threads per CT
 #endif
 constexpr int kStages = ORX_PIPE_STAGES;
 constexpr int kPipeThreads = kTile + 32;   // + one producer warp
+constexpr uint32_t kTileIdxBytes = ((uint32_t)kStages * 4u + 15u) & ~15u;   // per-stage tile index words
 
 // byte offsets of the plane slices inside a stage (all multiples of 16)
 constexpr uint32_t T4 = 4u * kTile, T8 = 8u * kTile, T2 = 2u * kTile, T1 = kTile;   // slice sizes in bytes
@@ -97,19 +102,32 @@ __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("s
 __device__ __forceinline__ void sts_s32x2(uint32_t a, int x, int y) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifdef ORX_PIPE_TRACE
+// Tuning aid (tools/pipetrace.py, separate build): per-CTA %globaltimer stamps of the last 16 launches.
+__device__ unsigned long long g_trace[16][512][8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ORX_TRACE(slot, idx) do { if (blockIdx.x < 512) g_trace[(slot) & 15][blockIdx.x][idx] = gtime(); } while (0)
+#define ORX_TRACE_PARAM , unsigned int trace_slot
+#else
+#define ORX_TRACE(slot, idx) do { } while (0)
+#define ORX_TRACE_PARAM
+#endif
+
 // n_tiles full tiles of kTile games; the caller handles a ragged tail with the simple kernel.
 template <int DGEN, int CMD>
 __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
 k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, uint8_t* __restrict__ result,
-            unsigned int n_tiles)
+            unsigned int n_tiles, unsigned int* __restrict__ sched ORX_TRACE_PARAM)
 {
+    if (threadIdx.x == 0) ORX_TRACE(trace_slot, 0);
     constexpr uint32_t MV_BYTES = CMD == CMD_NIBBLES ? T1 : T2, LOAD_BYTES = PLANE_LOAD_BYTES + MV_BYTES;
     const uint8_t* moves = static_cast<const uint8_t*>(moves_v);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stages = smem;                                             // kStages * STAGE_BYTES
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);   // full[kStages], done[kStages]
-    uint8_t* tiles_sm = smem + kStages * STAGE_BYTES + 2 * kStages * 8;
+    uint8_t* tiles_sm = smem + kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes;
     const uint32_t full0 = smem_addr(bars), done0 = smem_addr(bars + kStages);
+    const uint32_t tidx0 = smem_addr(bars + 2 * kStages);      // tile index published with each stage
     const uint32_t stage0 = smem_addr(stages);
     const unsigned int tid = threadIdx.x;
     // Programmatic dependent launch: the next kernel in the stream may begin its prologue (barrier
@@ -134,16 +152,18 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
     }
     __syncthreads();
 
-    // tiles of this CTA: blockIdx.x, + gridDim.x, ...
-    const unsigned int my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    constexpr uint32_t NONE = 0xFFFFFFFFu;    // published instead of a tile index: no more work for this CTA
 
     if (tid >= kTile) {
         // ------------------------------------------------------------ producer (one thread)
         if (tid != kTile) return;
-        auto issue_loads = [&](unsigned int it) {
+        // Publishes tile `tile` (or NONE) in the stage of iteration `it` and starts its loads.
+        auto issue = [&](unsigned int it, uint32_t tile) {
             const unsigned int s = it % kStages;
-            const size_t g = ((size_t)blockIdx.x + (size_t)it * gridDim.x) * kTile;     // first game of the tile
             const uint32_t bar = full0 + 8 * s, base = stage0 + s * STAGE_BYTES;
+            sts_u32(tidx0 + 4 * s, tile);
+            if (tile == NONE) { mbar_arrive(bar); return; }
+            const size_t g = (size_t)tile * kTile;     // first game of the tile
             mbar_expect_tx(bar, LOAD_BYTES);
             bulk_load(base + OFF_POS, P.pos + g, T4, bar);
             bulk_load(base + OFF_HP, P.hp + g, T4, bar);
@@ -155,12 +175,38 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
             bulk_load(base + OFF_MOVES, moves + g * (MV_BYTES / kTile), MV_BYTES, bar);
         };
         if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // all earlier work in the stream is complete and visible
-        const unsigned int pre = my_tiles < (unsigned)kStages ? my_tiles : (unsigned)kStages;
-        for (unsigned int it = 0; it < pre; ++it) issue_loads(it);
-        for (unsigned int it = 0; it < my_tiles; ++it) {
+        ORX_TRACE(trace_slot, 1);
+        // Prologue: the first kStages tiles of a CTA are fixed, so its loads start without a round trip
+        // to the counter.
+        bool ended = false;
+        for (unsigned int it = 0; it < (unsigned)kStages && !ended; ++it) {
+            const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
+            const uint32_t tile = t < n_tiles ? (uint32_t)t : NONE;
+            issue(it, tile);
+            ended = tile == NONE;
+        }
+        // Tiles beyond the fixed prefix come from the counter: ticket t is tile dyn_base + t. Every CTA
+        // that got kStages fixed tiles claims until its first miss, so a launch draws exactly
+        // `claims` tickets; whoever draws the last one puts the counter back to zero for the next
+        // launch on this state (which reads it only after griddepcontrol.wait).
+        const uint32_t dyn_base = (uint32_t)kStages * gridDim.x;
+        const uint32_t last_fixed = (uint32_t)(kStages - 1) * gridDim.x;
+        const uint32_t claimers = n_tiles > last_fixed ? (n_tiles - last_fixed < gridDim.x ? n_tiles - last_fixed : gridDim.x) : 0u;
+        const uint32_t claims = (n_tiles > dyn_base ? n_tiles - dyn_base : 0u) + claimers;
+        auto draw = [&]() -> uint32_t {
+            const uint32_t ticket = atomicAdd(sched, 1u);
+            if (ticket == claims - 1u) atomicExch(sched, 0u);
+            return ticket;
+        };
+        // One ticket is always held in advance, so the counter's round trip never delays a refill.
+        uint32_t held = 0;
+        if (!ended && sched != nullptr) held = draw();
+        for (unsigned int it = 0;; ++it) {
             const unsigned int s = it % kStages;
+            const uint32_t tile = lds_u32(tidx0 + 4 * s);
+            if (tile == NONE) break;
             mbar_wait(done0 + 8 * s, (it / kStages) & 1u);
-            const size_t g = ((size_t)blockIdx.x + (size_t)it * gridDim.x) * kTile;
+            const size_t g = (size_t)tile * kTile;
             const uint32_t base = stage0 + s * STAGE_BYTES;
             bulk_store(P.pos + g, base + OFF_POS, T4);
             bulk_store(P.hp + g, base + OFF_HP, T4);
@@ -171,13 +217,24 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
             bulk_store(P.status + g, base + OFF_STATUS, T1);
             bulk_store(result + g, base + OFF_RESULT, T1);
             bulk_commit();
-            if (it + kStages < my_tiles) {
+            if (!ended) {
                 bulk_wait_read_all();              // the stage has been read out: safe to overwrite
-                issue_loads(it + kStages);
+                const uint64_t next = sched != nullptr ? (uint64_t)dyn_base + held
+                                                       : (uint64_t)blockIdx.x + (uint64_t)(it + kStages) * gridDim.x;
+                const uint32_t nt = next < n_tiles ? (uint32_t)next : NONE;
+                issue(it + kStages, nt);
+                ended = nt == NONE;
+                if (!ended && sched != nullptr) held = draw();
             }
         }
         bulk_wait_read_all();     // shared memory may be released once the last stores have read it; the
-        return;                   // writes themselves complete with the grid (as CUTLASS epilogues do)
+                                  // writes themselves complete with the grid (as CUTLASS epilogues do)
+        ORX_TRACE(trace_slot, 3);
+#ifdef ORX_PIPE_TRACE
+        bulk_wait_all();
+        ORX_TRACE(trace_slot, 4);
+#endif
+        return;
     }
 
     // ---------------------------------------------------------------- consumers (8 warps)
@@ -185,13 +242,16 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
     // empty asm so ptxas keeps them in registers instead of re-deriving them (S2R + LEA chains)
     // every tile.
     uint32_t a4 = stage0 + tid * 4u;            // this thread's slot in the 4-byte slices of stage 0
-    uint32_t lane = blockIdx.x * kTile + tid;   // game index inside the launch
-    uint32_t lane_step = gridDim.x * kTile;
-    asm volatile("" : "+r"(a4), "+r"(lane), "+r"(lane_step));
-    for (unsigned int it = 0; it < my_tiles; ++it, lane += lane_step) {
+    asm volatile("" : "+r"(a4));
+    for (unsigned int it = 0;; ++it) {
         const unsigned int s = it % kStages;
         const uint32_t b4 = a4 + s * STAGE_BYTES, b8 = b4 + tid * 4u, b1 = b4 - tid * 3u, b2 = b4 - tid * 2u;
         mbar_wait(full0 + 8 * s, (it / kStages) & 1u);
+        const uint32_t tile = lds_u32(tidx0 + 4 * s);
+        if (tid == 0 && it == 0) ORX_TRACE(trace_slot, 2);
+        if (tile == NONE) break;
+        if (tid == 0) ORX_TRACE(trace_slot, 5);
+        const uint32_t lane = tile * kTile + tid;      // game index inside the launch
         const uint32_t pos = lds_u32(b4 + OFF_POS), hpw = lds_u32(b4 + OFF_HP), stw = lds_u32(b4 + OFF_ST);
         const int tick = (int)lds_u32(b4 + OFF_TICK);
         const uint32_t ep = lds_u32(b4 + OFF_EP);
@@ -232,8 +292,9 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
         __syncwarp();
         if ((tid & 31u) == 0) mbar_arrive(done0 + 8 * s);
     }
+    if (tid == 0) ORX_TRACE(trace_slot, 6);
 }
 
-constexpr size_t pipe_smem_bytes(int fixed_tiles) { return (size_t)kStages * STAGE_BYTES + 2 * kStages * 8 + (size_t)fixed_tiles; }
+constexpr size_t pipe_smem_bytes(int fixed_tiles) { return (size_t)kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes + (size_t)fixed_tiles; }
 
 }  // namespace orx

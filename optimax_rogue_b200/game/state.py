@@ -143,6 +143,8 @@ class BatchedGameState:
         self.npc_pos = torch.zeros((n, e, 2), dtype=torch.uint8, device=dev)
         self.npc_hp = torch.zeros((n, e), dtype=torch.int16, device=dev)
         self.npc_depth = torch.full((n, e), -1, dtype=torch.int32, device=dev)
+        # tile-scheduler scratch of the tick kernel (OrxState.sched): zero between launches, never shared
+        self.sched = torch.zeros((4,), dtype=torch.int32, device=dev)
         # the fixed map (shared by all games) lives beside the state
         self.fixed_tiles = self.fixed_ground = None
         self._fixed_stairs = (_abi.NO_STAIRS, _abi.NO_STAIRS)
@@ -158,6 +160,7 @@ class BatchedGameState:
         st = _abi.OrxState()
         for name in self.PLANES:
             setattr(st, name, getattr(self, name).data_ptr())
+        st.sched = self.sched.data_ptr() if self.sched.is_cuda else None
         return st
 
     def c_config(self, **overrides) -> _abi.OrxConfig:
@@ -189,6 +192,7 @@ class BatchedGameState:
         o.__dict__.update(self.__dict__)
         for name in self.PLANES:
             setattr(o, name, getattr(self, name).clone())
+        o.sched = torch.zeros_like(self.sched)
         return o
 
     def state_dict(self):

@@ -91,7 +91,7 @@ class BatchedUpdater:
     # -- plumbing ------------------------------------------------------------------------------
     def _cfg(self, gs: BatchedGameState):
         key = (id(gs), gs.game_id_base, int(self.despawn_strat), int(self.max_ticks or 0), int(self.auto_reset),
-               gs.pos.data_ptr())
+               gs.pos.data_ptr(), gs.sched.data_ptr())
         if self._cache is None or self._cache[0] != key:
             if (gs.cfg.width, gs.cfg.height, gs.cfg.dgen_kind) != (self.dgen.width, self.dgen.height, self.dgen.kind):
                 raise ValueError('updater.dgen does not match the generator the game state was built with')

@@ -340,6 +340,29 @@ def test_concurrent_host_threads_on_separate_streams():
         gu.assert_state_equal(pairs[b][0], pairs[b][2], f'thread {b}')
 
 
+@pytest.mark.parametrize('n', [(1 << 19) + 37, 1 << 16])
+def test_dynamic_tile_scheduler_equals_static_assignment(n):
+    """OrxState.sched: tiles beyond the first four per CTA are claimed from a counter. The outcome may not
+    depend on who ticks which tile, and the counter words must be zero again after every launch."""
+    cfg = SimConfig(max_ticks=60, seed=17, auto_reset=True)
+    gs, upd, orc = gu.make_pair(cfg, n)
+    static = gs.clone()
+    static.sched = torch.zeros((4,), dtype=torch.int32)          # not on the device -> OrxState.sched = NULL
+    assert static.c_struct().sched is None and gs.c_struct().sched is not None
+    upd_static = type(upd)(upd.dgen, upd.despawn_strat, upd.max_ticks, auto_reset=True)
+    rng = np.random.default_rng(1)
+    for t in range(24):
+        mv = torch.from_numpy(rng.integers(1, 6, size=(n, 2), dtype=np.uint8)).cuda()
+        r_dyn, _ = upd.update(gs, mv)
+        r_sta, _ = upd_static.update(static, mv)
+        assert torch.equal(r_dyn, r_sta), t
+        assert int(gs.sched.abs().sum()) == 0, (t, gs.sched.tolist())
+        orc.step(mv.cpu().numpy())
+    for name in gu.PLANES:
+        assert torch.equal(getattr(gs, name), getattr(static, name)), name
+    gu.assert_state_equal(gs, orc, 'dynamic tiles')
+
+
 def test_observe():
     cfg = SimConfig(max_ticks=0, seed=4)
     gs, upd, orc = gu.make_pair(cfg, 2000)
