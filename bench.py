@@ -330,6 +330,31 @@ def run_b200(args, rank, local_rank, world):
         ms_e2e = time_host_loop(host_cmds, True)
         ms_e2e_pipelined = time_host_loop(host_cmds, False)
 
+        # ---- step + observe (extra): the self-play tick, one pass (orx_step_observe); observation
+        # buffers rotate with the batches so that their writes cannot be absorbed by the L2 either
+        obs_bufs = [torch.empty((G, 2, 12), dtype=torch.int16, device=dev) for _ in range(n_batches)]
+        k_so = max(n_batches, min(K, 10 * n_batches))
+        for k in range(3):
+            upd.update_observe(batches[k % n_batches], moves[k % len(moves)], stairs_radius=4, out=results[k % n_batches],
+                               obs_out=obs_bufs[k % n_batches])
+        torch.cuda.synchronize(dev)
+        g_so = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_so, stream=stream):
+            for k in range(k_so):
+                upd.update_observe(batches[k % n_batches], moves[k % len(moves)], stairs_radius=4,
+                                   out=results[k % n_batches], obs_out=obs_bufs[k % n_batches])
+        g_so.replay()
+        torch.cuda.synchronize(dev)
+        barrier()
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record(stream)
+        g_so.replay()
+        es1.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms_so = es0.elapsed_time(es1)
+        del obs_bufs, g_so
+
         # ---- rollout (extra): fused T-tick kernel, both bots on device
         T = args.rollout_ticks
         stats = torch.zeros((8,), dtype=torch.int64, device=dev)
@@ -402,6 +427,7 @@ def run_b200(args, rank, local_rank, world):
     ms_e2e_unpacked = max_over_ranks(ms_e2e_unpacked)
     ms_e2e_pipelined = max_over_ranks(ms_e2e_pipelined)
     ms_roll = max_over_ranks(ms_roll)
+    ms_so = max_over_ranks(ms_so)
     ms_r1 = max_over_ranks(ms_r1)
     ms_r1_roll = max_over_ranks(ms_r1_roll)
     if world > 1:
@@ -440,6 +466,11 @@ def run_b200(args, rank, local_rank, world):
                                   'api': 'host_stepper(..., sync=False) = orx_step_host_packed on two independent batches in flight; '
                                          'the host waits on step k-1\'s event after enqueueing step k'}},
             'gpu_launches': K,
+            'step_observe': {'value': world * G * k_so / (ms_so * 1e-3), 'unit': UNIT, 'us_per_step': ms_so / k_so * 1e3,
+                             'steps': k_so, 'alg_bytes_per_game_tick': B_ALG + 48,
+                             'hbm_frac': (B_ALG + 48) * G / (ms_so / k_so * 1e-3) / 1e9 / peak,
+                             'note': 'orx_step_observe: the tick plus both players\' observations (int16[N,2,12]) '
+                                     'of the resulting state in one pass; observation buffers rotate with the batches'},
             'rollout': {'value': roll_ticks_all / (ms_roll * 1e-3), 'unit': UNIT, 'ticks_per_launch': T,
                         'launches': r_launches, 'fused': True,
                         'note': 'orx_rollout: bots + tick fused, state in registers for T ticks'},

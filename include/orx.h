@@ -23,6 +23,7 @@
  *   orx_rollout     the tick loop  optimax_rogue/server/main.py:110-113 with both bots inlined
  *   orx_replay      the same loop with both players' commands queued in advance
  *   orx_observe     GameState.view_for  optimax_rogue/game/state.py:53-58
+ *   orx_step_observe  Updater.update followed by view_for for both players (the self-play tick)
  *   orx_step_packed the same tick with both players' commands of a game in one byte (p1 | p2 << 4)
  *   orx_step_host   orx_step with host command/result buffers (what a remote caller holds);
  *   orx_step_host_packed(_sync)  the host-buffer tick with nibble-packed commands (half the PCIe bytes)
@@ -203,6 +204,14 @@ int orx_replay(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, u
 #define ORX_OBS_LEN 12
 int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stairs_radius,
                 int64_t n, void* cuda_stream);
+
+/* orx_step (moves_packed == 0: uint8[n][2]) or orx_step_packed (moves_packed != 0: uint8[n]) fused with
+ * orx_observe of the resulting state: what a self-play loop needs per tick, in one pass over the
+ * planes (61 + 48 bytes per game instead of 61 + 77). obs: device int16[n][2][ORX_OBS_LEN], 16-byte
+ * aligned. Same results and observations as the two calls in sequence. */
+int orx_step_observe(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, int moves_packed,
+                     uint8_t* result, int16_t* obs, int stairs_radius, int64_t n, uint64_t game_id_base,
+                     void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Ruleset R1: the README-only rules (readme.md:44-48,69-74), specified in docs/RULESET_R1.md.

@@ -250,24 +250,12 @@ k_observe(const __grid_constant__ Params P, int16_t* __restrict__ obs, int radiu
     if (i >= P.n) return;
     Lane L;
     load_lane(P, i, L);
-    const bool same = L.d1 == L.d2;   // view_for keeps entities on the viewer's depth
-    const int tk = min(L.tick, 32767);
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const uint32_t me = p == 0 ? (L.pos & 0xFFFFu) : (L.pos >> 16), ot = p == 0 ? (L.pos >> 16) : (L.pos & 0xFFFFu);
-        const uint32_t sxy = p == 0 ? (L.st & 0xFFFFu) : (L.st >> 16);
-        const int mx = me & 255u, my = me >> 8, sx = sxy & 255u, sy = sxy >> 8;
-        const int md = p == 0 ? L.d1 : L.d2, mh = p == 0 ? L.hp1 : L.hp2, oh = p == 0 ? L.hp2 : L.hp1;
-        const bool has_st = sx != ORX_NO_STAIRS;
-        const bool st_vis = has_st && (radius < 0 || max(abs(sx - mx), abs(sy - my)) <= radius);
-        const short q0[4] = {(short)mx, (short)my, (short)min(md, 32767), (short)mh};
-        const short q1[4] = {(short)same, (short)(same ? (int)(ot & 255u) : -1), (short)(same ? (int)(ot >> 8) : -1), (short)(same ? oh : 0)};
-        const short q2[4] = {(short)st_vis, (short)(st_vis ? sx : -1), (short)(st_vis ? sy : -1), (short)tk};
-        short* o = obs + ((size_t)i * 2 + p) * ORX_OBS_LEN;
-        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(q0);
-        *reinterpret_cast<uint2*>(o + 4) = *reinterpret_cast<const uint2*>(q1);
-        *reinterpret_cast<uint2*>(o + 8) = *reinterpret_cast<const uint2*>(q2);
-    }
+    uint32_t w[12];
+    pack_obs(L, radius, w);
+    uint4* o = reinterpret_cast<uint4*>(obs + (size_t)i * 2 * ORX_OBS_LEN);       // 48 B per game, 16-byte aligned
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    o[2] = make_uint4(w[8], w[9], w[10], w[11]);
 }
 
 // ------------------------------------------------------------------ host side
@@ -367,32 +355,34 @@ Params offset_params(const Params& P, int64_t off, int64_t n)
     return T;
 }
 
-template <int DGEN, int CMD>
+template <int DGEN, int CMD, bool OBS, bool TICK>
 int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, unsigned int* sched,
-                cudaStream_t s)
+                int16_t* obs, int obs_radius, cudaStream_t s)
 {
-    const size_t smem = pipe_smem_bytes((int)tiles_bytes);
+    const size_t smem = pipe_smem_bytes<OBS>((int)tiles_bytes);
+    auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK>;
     // Launch geometry depends only on (device, kernel, smem): look it up once per process, the
-    // occupancy query costs more than the launch itself. (A cache of device properties, not state.)
-    // Guarded by a mutex so that host threads driving different GPUs may call in concurrently.
+    // occupancy query costs more than the launch itself. (A cache of device properties, not state;
+    // one per kernel instantiation.) Guarded by a mutex so that host threads driving different GPUs
+    // may call in concurrently.
     static std::mutex cache_mu;
-    static int cache_sms[64] = {0}, cache_per_sm[64][4] = {{0}};
-    static size_t cache_smem[64][4] = {{0}};
+    static int cache_sms[64] = {0}, cache_per_sm[64] = {0};
+    static size_t cache_smem[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    const int slot = dev & 63, kd = (DGEN == ORX_DGEN_EMPTY ? 0 : 1) + 2 * CMD;
+    const int slot = dev & 63;
     std::unique_lock<std::mutex> lk(cache_mu);
-    if (cache_sms[slot] == 0 || cache_smem[slot][kd] != smem || cache_per_sm[slot][kd] == 0) {
+    if (cache_sms[slot] == 0 || cache_smem[slot] != smem || cache_per_sm[slot] == 0) {
         int sms = 148, per_sm = 2;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (smem > 48 * 1024) {
-            const cudaError_t e = cudaFuncSetAttribute(k_step_pipe<DGEN, CMD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e);
         }
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_pipe<DGEN, CMD>, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        cache_per_sm[slot][kd] = per_sm; cache_smem[slot][kd] = smem; cache_sms[slot] = sms;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cache_per_sm[slot] = per_sm; cache_smem[slot] = smem; cache_sms[slot] = sms;
     }
-    const int sms = cache_sms[slot], per_sm = cache_per_sm[slot][kd];
+    const int sms = cache_sms[slot], per_sm = cache_per_sm[slot];
     lk.unlock();
     unsigned int grid = (unsigned int)sms * (unsigned int)per_sm;       // persistent: every CTA resident
     if (grid > n_tiles) grid = n_tiles;
@@ -404,16 +394,28 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     lc.attrs = at; lc.numAttrs = ORX_PIPE_PDL ? 1 : 0;
 #ifdef ORX_PIPE_TRACE
     static unsigned int trace_slot = 0;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, k_step_pipe<DGEN, CMD>, P, mv, result, n_tiles, sched, trace_slot++);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, mv, result, n_tiles, sched, obs, obs_radius, trace_slot++);
 #else
-    const cudaError_t e = cudaLaunchKernelEx(&lc, k_step_pipe<DGEN, CMD>, P, mv, result, n_tiles, sched);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, mv, result, n_tiles, sched, obs, obs_radius);
 #endif
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
 }
 
+template <bool OBS>
+int launch_tick_pipe(bool empty, int packed, const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t smem,
+                     unsigned int* sched, int16_t* obs, int obs_radius, cudaStream_t s)
+{
+    if (packed) return empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES, OBS, true>(P, mv, result, n_tiles, 0, sched, obs, obs_radius, s)
+                             : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES, OBS, true>(P, mv, result, n_tiles, smem, sched, obs, obs_radius, s);
+    return empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES, OBS, true>(P, mv, result, n_tiles, 0, sched, obs, obs_radius, s)
+                 : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES, OBS, true>(P, mv, result, n_tiles, smem, sched, obs, obs_radius, s);
+}
+
 // One tick; packed = 0: moves uint8[n][2], packed = 1: uint8[n] with p1 | p2 << 4.
+// obs != NULL: also writes the observations of the resulting state (orx_step_observe).
 int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uint8_t* result,
-              OrxEvent* events, int64_t n, uint64_t game_id_base, void* cuda_stream, int packed)
+              OrxEvent* events, int64_t n, uint64_t game_id_base, void* cuda_stream, int packed,
+              int16_t* obs = nullptr, int obs_radius = -1)
 {
     const int rc = check_common(cfg, st, n);
     if (rc != ORX_OK) return rc;
@@ -432,24 +434,23 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
         const unsigned int n_tiles = (unsigned int)(n / kTile);
         const int64_t n_body = (int64_t)n_tiles * kTile;
         const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
-        int rc2;
         unsigned int* sched = aligned(st->sched, 4) && getenv("ORX_STATIC_TILES") == nullptr ? st->sched : nullptr;
-        if (packed) rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES>(P, moves, result, n_tiles, 0, sched, s)
-                                : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES>(P, moves, result, n_tiles, smem, sched, s);
-        else rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES>(P, moves, result, n_tiles, 0, sched, s)
-                         : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES>(P, moves, result, n_tiles, smem, sched, s);
+        const int rc2 = obs != nullptr ? launch_tick_pipe<true>(empty, packed, P, moves, result, n_tiles, smem, sched, obs, obs_radius, s)
+                                       : launch_tick_pipe<false>(empty, packed, P, moves, result, n_tiles, smem, sched, nullptr, -1, s);
         if (rc2 != ORX_OK || n_body == n) return rc2;
         const Params T = offset_params(P, n_body, n - n_body);
         const int tgrid = grid_for(n - n_body);
         const uint8_t* tail = moves + (size_t)n_body * mv_stride;
         if (empty) k_step<ORX_DGEN_EMPTY, false, false><<<tgrid, kThreads, 0, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
         else k_step<ORX_DGEN_FIXED, false, false><<<tgrid, kThreads, smem, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
+        if (obs != nullptr) k_observe<<<tgrid, kThreads, 0, s>>>(T, obs + (size_t)n_body * 2 * ORX_OBS_LEN, obs_radius);
         return launch_done();
     }
     const int grid = grid_for(n);
     return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
         if (ev != nullptr) k_step<DGEN, NPC, true><<<grid, kThreads, smem, s>>>(P, moves, result, ev, max_ev, packed);
         else k_step<DGEN, NPC, false><<<grid, kThreads, smem, s>>>(P, moves, result, nullptr, max_ev, packed);
+        if (obs != nullptr) k_observe<<<grid, kThreads, 0, s>>>(P, obs, obs_radius);
         return launch_done();
     });
 }
@@ -640,11 +641,32 @@ int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stai
 {
     const int rc = check_common(cfg, st, n);
     if (rc != ORX_OK) return rc;
-    if (obs == nullptr || !aligned(obs, 8)) return ORX_ERR_BAD_ARG;
+    if (obs == nullptr || !aligned(obs, 16)) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
     const Params P = make_params(cfg, st, n, 0);
-    k_observe<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P, obs, stairs_radius);
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    // Full 256-game tiles stream through the TMA pipeline (planes in, 48 B per game out as bulk stores);
+    // a ragged tail and small batches use the simple kernel.
+    if (n >= kTile && pipe_aligned(st, obs, obs)) {
+        const unsigned int n_tiles = (unsigned int)(n / kTile);
+        const int64_t n_body = (int64_t)n_tiles * kTile;
+        unsigned int* sched = aligned(st->sched, 4) && getenv("ORX_STATIC_TILES") == nullptr ? st->sched : nullptr;
+        const int rc2 = launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES, true, false>(P, nullptr, nullptr, n_tiles, 0, sched, obs, stairs_radius, s);
+        if (rc2 != ORX_OK || n_body == n) return rc2;
+        const Params T = offset_params(P, n_body, n - n_body);
+        k_observe<<<grid_for(n - n_body), kThreads, 0, s>>>(T, obs + (size_t)n_body * 2 * ORX_OBS_LEN, stairs_radius);
+        return launch_done();
+    }
+    k_observe<<<grid_for(n), kThreads, 0, s>>>(P, obs, stairs_radius);
     return launch_done();
+}
+
+int orx_step_observe(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, int moves_packed,
+                     uint8_t* result, int16_t* obs, int stairs_radius, int64_t n, uint64_t game_id_base,
+                     void* cuda_stream)
+{
+    if (obs == nullptr || !aligned(obs, 16)) return ORX_ERR_BAD_ARG;
+    return step_impl(cfg, st, moves, result, nullptr, n, game_id_base, cuda_stream, moves_packed != 0, obs, stairs_radius);
 }
 
 }  // extern "C"

@@ -42,6 +42,12 @@ constexpr int kTile = ORX_PIPE_TILE;  // games per tile = compute threads per CT
 constexpr int kStages = ORX_PIPE_STAGES;
 constexpr int kPipeThreads = kTile + 32;   // + one producer warp
 constexpr uint32_t kTileIdxBytes = ((uint32_t)kStages * 4u + 15u) & ~15u;   // per-stage tile index words
+#ifndef ORX_PIPE_OBS_STAGES
+#define ORX_PIPE_OBS_STAGES 3
+#endif
+// With observations each stage also carries the tile's 48 B/game observation block (12 KB), so three
+// stages keep three CTAs per SM resident.
+template <bool OBS> constexpr int kPipeStages = OBS ? ORX_PIPE_OBS_STAGES : kStages;
 
 // byte offsets of the plane slices inside a stage (all multiples of 16)
 constexpr uint32_t T4 = 4u * kTile, T8 = 8u * kTile, T2 = 2u * kTile, T1 = kTile;   // slice sizes in bytes
@@ -49,6 +55,9 @@ constexpr uint32_t OFF_POS = 0, OFF_HP = T4, OFF_ST = 2 * T4, OFF_TICK = 3 * T4,
                    OFF_DEPTH = 5 * T4, OFF_STATUS = 5 * T4 + T8, OFF_MOVES = OFF_STATUS + T1, OFF_RESULT = OFF_MOVES + T2,
                    STAGE_BYTES = OFF_RESULT + T1;
 constexpr uint32_t PLANE_LOAD_BYTES = 5 * T4 + T8 + T1;         // per tile, HBM -> smem, without the commands
+constexpr uint32_t OBS_GAME_BYTES = 2u * ORX_OBS_LEN * 2u, OBS_BYTES = OBS_GAME_BYTES * kTile, OFF_OBS = STAGE_BYTES;
+static_assert(OBS_GAME_BYTES == 48 && (STAGE_BYTES % 128) == 0, "observation block: 12 words per game behind the planes");
+template <bool OBS> constexpr uint32_t kPipeStageBytes = STAGE_BYTES + (OBS ? OBS_BYTES : 0u);
 // Command formats: CMD_BYTES = uint8[n][2] (p1, p2); CMD_NIBBLES = uint8[n], p1 in the low nibble,
 // p2 in the high nibble (halves the command traffic when the commands come over PCIe).
 constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1;
@@ -100,6 +109,7 @@ __device__ __forceinline__ int2 lds_s32x2(uint32_t a) { int2 v; asm volatile("ld
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_s32x2(uint32_t a, int x, int y) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 #ifdef ORX_PIPE_TRACE
@@ -114,13 +124,19 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #endif
 
 // n_tiles full tiles of kTile games; the caller handles a ragged tail with the simple kernel.
-template <int DGEN, int CMD>
+// TICK: play one tick and write the planes and results back. OBS: also (or, without TICK, only) write
+// the per-player observations of the resulting state, 48 B per game, staged behind the planes of the
+// stage and streamed out with the same bulk stores.
+template <int DGEN, int CMD, bool OBS, bool TICK>
 __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
 k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, uint8_t* __restrict__ result,
-            unsigned int n_tiles, unsigned int* __restrict__ sched ORX_TRACE_PARAM)
+            unsigned int n_tiles, unsigned int* __restrict__ sched, int16_t* __restrict__ obs, int obs_radius ORX_TRACE_PARAM)
 {
+    static_assert(OBS || TICK, "nothing to do");
     if (threadIdx.x == 0) ORX_TRACE(trace_slot, 0);
-    constexpr uint32_t MV_BYTES = CMD == CMD_NIBBLES ? T1 : T2, LOAD_BYTES = PLANE_LOAD_BYTES + MV_BYTES;
+    constexpr int kStages = kPipeStages<OBS>;                      // shadows the namespace constant on purpose
+    constexpr uint32_t STAGE_BYTES = kPipeStageBytes<OBS>;
+    constexpr uint32_t MV_BYTES = CMD == CMD_NIBBLES ? T1 : T2, LOAD_BYTES = PLANE_LOAD_BYTES + (TICK ? MV_BYTES : 0u);
     const uint8_t* moves = static_cast<const uint8_t*>(moves_v);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stages = smem;                                             // kStages * STAGE_BYTES
@@ -143,9 +159,9 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __shared__ CmdEntry lut[256];
-    build_cmd_lut(P, lut, tid, kPipeThreads);
+    if (TICK) build_cmd_lut(P, lut, tid, kPipeThreads);
     const uint8_t* tiles = nullptr;
-    if (DGEN == ORX_DGEN_FIXED) {
+    if (TICK && DGEN == ORX_DGEN_FIXED) {
         const int nt = P.W * P.H;
         for (int t = tid; t < nt; t += kPipeThreads) tiles_sm[t] = P.tiles[t];
         tiles = tiles_sm;
@@ -172,7 +188,7 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
             bulk_load(base + OFF_EP, P.episode + g, T4, bar);
             bulk_load(base + OFF_DEPTH, P.depth + g, T8, bar);
             bulk_load(base + OFF_STATUS, P.status + g, T1, bar);
-            bulk_load(base + OFF_MOVES, moves + g * (MV_BYTES / kTile), MV_BYTES, bar);
+            if (TICK) bulk_load(base + OFF_MOVES, moves + g * (MV_BYTES / kTile), MV_BYTES, bar);
         };
         if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // all earlier work in the stream is complete and visible
         ORX_TRACE(trace_slot, 1);
@@ -208,14 +224,17 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
             mbar_wait(done0 + 8 * s, (it / kStages) & 1u);
             const size_t g = (size_t)tile * kTile;
             const uint32_t base = stage0 + s * STAGE_BYTES;
-            bulk_store(P.pos + g, base + OFF_POS, T4);
-            bulk_store(P.hp + g, base + OFF_HP, T4);
-            bulk_store(P.stairs + g, base + OFF_ST, T4);
-            bulk_store(P.tick + g, base + OFF_TICK, T4);
-            bulk_store(P.episode + g, base + OFF_EP, T4);
-            bulk_store(P.depth + g, base + OFF_DEPTH, T8);
-            bulk_store(P.status + g, base + OFF_STATUS, T1);
-            bulk_store(result + g, base + OFF_RESULT, T1);
+            if (TICK) {
+                bulk_store(P.pos + g, base + OFF_POS, T4);
+                bulk_store(P.hp + g, base + OFF_HP, T4);
+                bulk_store(P.stairs + g, base + OFF_ST, T4);
+                bulk_store(P.tick + g, base + OFF_TICK, T4);
+                bulk_store(P.episode + g, base + OFF_EP, T4);
+                bulk_store(P.depth + g, base + OFF_DEPTH, T8);
+                bulk_store(P.status + g, base + OFF_STATUS, T1);
+                bulk_store(result + g, base + OFF_RESULT, T1);
+            }
+            if (OBS) bulk_store(obs + g * (2 * ORX_OBS_LEN), base + OFF_OBS, OBS_BYTES);
             bulk_commit();
             if (!ended) {
                 bulk_wait_read_all();              // the stage has been read out: safe to overwrite
@@ -257,37 +276,47 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
         const uint32_t ep = lds_u32(b4 + OFF_EP);
         const int2 dep = lds_s32x2(b8 + OFF_DEPTH);
         const int status = (int)lds_u8(b1 + OFF_STATUS);
-        uint32_t mv;
-        if (CMD == CMD_NIBBLES) {
-            const uint32_t c = lds_u8(b1 + OFF_MOVES);
-            mv = (c & 15u) | ((c >> 4) << 8);
-        } else {
-            mv = lds_u16(b2 + OFF_MOVES);
-        }
-        int res = status;
-        if (status == ORX_RESULT_IN_PROGRESS) {          // finished lanes are frozen until reset
-            Lane L;
-            unpack_lane(L, pos, hpw, dep, stw, tick, ep);
-            Stream rs = make_stream(P, lane, ep);
-            const uint4 blk = draw_block(rs, DOM_TICK, SUB_MAIN, (uint32_t)tick);
-            Counters cnt{};
-            EvSink<false> ev{nullptr, 0, 0};
-            res = tick_lane<DGEN, false, false>(P, tiles, lut, L, mv, blk.z, rs, lane, ev, cnt);
-            int new_status = res;
-            if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
-                rs.episode += 1;
-                reset_lane<DGEN, false>(P, L, rs, lane);
-                new_status = ORX_RESULT_IN_PROGRESS;
+        Lane L;
+        unpack_lane(L, pos, hpw, dep, stw, tick, ep);
+        if (TICK) {
+            uint32_t mv;
+            if (CMD == CMD_NIBBLES) {
+                const uint32_t c = lds_u8(b1 + OFF_MOVES);
+                mv = (c & 15u) | ((c >> 4) << 8);
+            } else {
+                mv = lds_u16(b2 + OFF_MOVES);
             }
-            sts_u32(b4 + OFF_POS, L.pos);
-            sts_u32(b4 + OFF_HP, ((uint32_t)L.hp1 & 0xFFFFu) | ((uint32_t)L.hp2 << 16));
-            sts_u32(b4 + OFF_ST, L.st);
-            sts_u32(b4 + OFF_TICK, (uint32_t)L.tick);
-            sts_u32(b4 + OFF_EP, L.episode);
-            sts_s32x2(b8 + OFF_DEPTH, L.d1, L.d2);
-            sts_u8(b1 + OFF_STATUS, (uint32_t)new_status);
+            int res = status;
+            if (status == ORX_RESULT_IN_PROGRESS) {          // finished lanes are frozen until reset
+                Stream rs = make_stream(P, lane, ep);
+                const uint4 blk = draw_block(rs, DOM_TICK, SUB_MAIN, (uint32_t)tick);
+                Counters cnt{};
+                EvSink<false> ev{nullptr, 0, 0};
+                res = tick_lane<DGEN, false, false>(P, tiles, lut, L, mv, blk.z, rs, lane, ev, cnt);
+                int new_status = res;
+                if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
+                    rs.episode += 1;
+                    reset_lane<DGEN, false>(P, L, rs, lane);
+                    new_status = ORX_RESULT_IN_PROGRESS;
+                }
+                sts_u32(b4 + OFF_POS, L.pos);
+                sts_u32(b4 + OFF_HP, ((uint32_t)L.hp1 & 0xFFFFu) | ((uint32_t)L.hp2 << 16));
+                sts_u32(b4 + OFF_ST, L.st);
+                sts_u32(b4 + OFF_TICK, (uint32_t)L.tick);
+                sts_u32(b4 + OFF_EP, L.episode);
+                sts_s32x2(b8 + OFF_DEPTH, L.d1, L.d2);
+                sts_u8(b1 + OFF_STATUS, (uint32_t)new_status);
+            }
+            sts_u8(b1 + OFF_RESULT, (uint32_t)res);
         }
-        sts_u8(b1 + OFF_RESULT, (uint32_t)res);
+        if (OBS) {                                   // what each player sees of the state as it now is
+            uint32_t w[12];
+            pack_obs(L, obs_radius, w);
+            const uint32_t bo = b4 + tid * 44u + OFF_OBS;      // 48 bytes per game
+            sts_u32x4(bo, w[0], w[1], w[2], w[3]);
+            sts_u32x4(bo + 16u, w[4], w[5], w[6], w[7]);
+            sts_u32x4(bo + 32u, w[8], w[9], w[10], w[11]);
+        }
         fence_proxy_async();                 // generic-proxy writes -> visible to the bulk-store engine
         __syncwarp();
         if ((tid & 31u) == 0) mbar_arrive(done0 + 8 * s);
@@ -295,6 +324,10 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
     if (tid == 0) ORX_TRACE(trace_slot, 6);
 }
 
-constexpr size_t pipe_smem_bytes(int fixed_tiles) { return (size_t)kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes + (size_t)fixed_tiles; }
+template <bool OBS>
+constexpr size_t pipe_smem_bytes(int fixed_tiles)
+{
+    return (size_t)kPipeStages<OBS> * kPipeStageBytes<OBS> + 2 * kPipeStages<OBS> * 8 + kTileIdxBytes + (size_t)fixed_tiles;
+}
 
 }  // namespace orx

@@ -357,6 +357,32 @@ __device__ __forceinline__ void store_lane(const Params& P, unsigned int i, cons
     P.status[i] = (uint8_t)status;
 }
 
+// Per-player observation (GameState.view_for, state.py:53-58): 12 int16 per player, both players of a
+// game = 12 words. { x, y, depth, hp, opp_visible, opp_x, opp_y, opp_hp, stairs_visible, stairs_x,
+// stairs_y, tick }, depth and tick saturated at 32767; radius < 0 = the staircase is always visible.
+__device__ __forceinline__ uint32_t pack_i16x2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+__device__ __forceinline__ void pack_obs(const Lane& L, int radius, uint32_t (&w)[12])
+{
+    const bool same = L.d1 == L.d2;   // view_for keeps entities on the viewer's depth
+    const int tk = min(L.tick, 32767);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const uint32_t me = p == 0 ? (L.pos & 0xFFFFu) : (L.pos >> 16), ot = p == 0 ? (L.pos >> 16) : (L.pos & 0xFFFFu);
+        const uint32_t sxy = p == 0 ? (L.st & 0xFFFFu) : (L.st >> 16);
+        const int mx = me & 255u, my = me >> 8, sx = sxy & 255u, sy = sxy >> 8;
+        const int md = p == 0 ? L.d1 : L.d2, mh = p == 0 ? L.hp1 : L.hp2, oh = p == 0 ? L.hp2 : L.hp1;
+        const bool has_st = sx != ORX_NO_STAIRS;
+        const bool st_vis = has_st && (radius < 0 || max(abs(sx - mx), abs(sy - my)) <= radius);
+        w[6 * p + 0] = pack_i16x2(mx, my);
+        w[6 * p + 1] = pack_i16x2(min(md, 32767), mh);
+        w[6 * p + 2] = pack_i16x2(same, same ? (int)(ot & 255u) : -1);
+        w[6 * p + 3] = pack_i16x2(same ? (int)(ot >> 8) : -1, same ? oh : 0);
+        w[6 * p + 4] = pack_i16x2(st_vis, st_vis ? sx : -1);
+        w[6 * p + 5] = pack_i16x2(st_vis ? sy : -1, tk);
+    }
+}
+
 __device__ __forceinline__ Stream make_stream(const Params& P, unsigned int i, uint32_t episode)
 {
     const unsigned long long gid = P.gid_base + (unsigned long long)i;

@@ -282,5 +282,28 @@ class BatchedUpdater:
         _lib.check(rc, 'orx_observe')
         return obs
 
+    def update_observe(self, game_state: BatchedGameState, moves: torch.Tensor, *, packed: bool = False,
+                       stairs_radius: int = -1, out: typing.Optional[torch.Tensor] = None,
+                       obs_out: typing.Optional[torch.Tensor] = None):
+        """One tick plus the observations of the resulting state in one pass over the planes
+        (``orx_step_observe``): ``update`` followed by ``observe``, as a self-play loop needs them.
+        ``moves``: CUDA uint8[N,2], or uint8[N] of ``p1 | p2 << 4`` with ``packed=True``.
+        Returns ``(result uint8[N], obs int16[N,2,OBS_LEN])``."""
+        gs = game_state
+        _require_cuda(gs)
+        shape = (gs.n,) if packed else (gs.n, 2)
+        if (not isinstance(moves, torch.Tensor) or not moves.is_cuda or moves.dtype != torch.uint8
+                or tuple(moves.shape) != shape or not moves.is_contiguous()):
+            raise ValueError(f'moves must be a contiguous CUDA uint8 tensor of shape {shape}')
+        cfg, st = self._cfg(gs)
+        result = out if out is not None else torch.empty((gs.n,), dtype=torch.uint8, device=gs.device)
+        obs = obs_out if obs_out is not None else torch.empty((gs.n, 2, _abi.OBS_LEN), dtype=torch.int16, device=gs.device)
+        with _on_device(gs.device):
+            rc = _lib.lib().orx_step_observe(C.byref(cfg), C.byref(st), moves.data_ptr(), int(bool(packed)),
+                                             result.data_ptr(), obs.data_ptr(), int(stairs_radius), gs.n,
+                                             gs.game_id_base, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_step_observe')
+        return result, obs
+
     def reset(self, game_state: BatchedGameState, mask=None, bump_episode: bool = True):
         reset_games(game_state, mask, bump_episode)

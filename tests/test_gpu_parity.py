@@ -340,10 +340,12 @@ def test_concurrent_host_threads_on_separate_streams():
         gu.assert_state_equal(pairs[b][0], pairs[b][2], f'thread {b}')
 
 
-@pytest.mark.parametrize('n', [(1 << 19) + 37, 1 << 16])
+@pytest.mark.parametrize('n', [(1 << 19) + 37, 1 << 16, 1000 * 256, 1500 * 256 + 5, 1776 * 256, 1777 * 256])
 def test_dynamic_tile_scheduler_equals_static_assignment(n):
     """OrxState.sched: tiles beyond the first four per CTA are claimed from a counter. The outcome may not
-    depend on who ticks which tile, and the counter words must be zero again after every launch."""
+    depend on who ticks which tile, and the counter words must be zero again after every launch. Sizes
+    cover every regime of tiles vs resident CTAs (444 on a B200): fewer tiles than CTAs, a partial fixed
+    prefix, claimers that all miss, exactly no dynamic tile, one dynamic tile, many."""
     cfg = SimConfig(max_ticks=60, seed=17, auto_reset=True)
     gs, upd, orc = gu.make_pair(cfg, n)
     static = gs.clone()
@@ -361,6 +363,62 @@ def test_dynamic_tile_scheduler_equals_static_assignment(n):
     for name in gu.PLANES:
         assert torch.equal(getattr(gs, name), getattr(static, name)), name
     gu.assert_state_equal(gs, orc, 'dynamic tiles')
+
+
+def expected_obs(p, radius):
+    """numpy restatement of the observation record (GameState.view_for + stairs visibility radius)."""
+    n = p['pos'].shape[0]
+    obs = np.zeros((n, 2, 12), dtype=np.int64)
+    same = p['depth'][:, 0] == p['depth'][:, 1]
+    for pl in range(2):
+        o = 1 - pl
+        x, y = p['pos'][:, 2 * pl].astype(int), p['pos'][:, 2 * pl + 1].astype(int)
+        sx, sy = p['stairs'][:, 2 * pl].astype(int), p['stairs'][:, 2 * pl + 1].astype(int)
+        vis = (sx != 255) & ((radius < 0) | (np.maximum(np.abs(sx - x), np.abs(sy - y)) <= radius))
+        cols = [x, y, np.minimum(p['depth'][:, pl], 32767), p['hp'][:, pl], same,
+                np.where(same, p['pos'][:, 2 * o].astype(int), -1), np.where(same, p['pos'][:, 2 * o + 1].astype(int), -1),
+                np.where(same, p['hp'][:, o], 0), vis, np.where(vis, sx, -1), np.where(vis, sy, -1),
+                np.minimum(p['tick'], 32767)]
+        for c, v in enumerate(cols):
+            obs[:, pl, c] = v
+    return obs.astype(np.int16)
+
+
+@pytest.mark.parametrize('n', [100, 2000, 70000])
+def test_observe_all_columns_and_paths(n):
+    """n = 100: simple kernel; 2000: TMA pipeline + ragged tail; 70000: pipeline with claimed tiles."""
+    cfg = SimConfig(max_ticks=0, seed=4)
+    gs, upd, orc = gu.make_pair(cfg, n)
+    upd.rollout(gs, 2, 1, 40)
+    for radius in (-1, 3):
+        obs = upd.observe(gs, stairs_radius=radius).cpu().numpy()
+        assert np.array_equal(obs, expected_obs(gs.planes_cpu(), radius)), radius
+    assert int(gs.sched.abs().sum()) == 0
+
+
+@pytest.mark.parametrize('n,packed,fixed,npc', [(3000, False, False, 0), (70000, True, False, 0), (200, False, False, 0),
+                                                (1500, True, True, 0), (700, False, False, 2)])
+def test_update_observe_equals_update_then_observe(n, packed, fixed, npc):
+    """orx_step_observe = one tick + the observations of the resulting state in one pass: same results,
+    same planes, same observations as the two calls, for both command formats and every kernel path."""
+    from optimax_rogue_b200.logic.moves import pack_moves
+    kw = dict(dgen_kind=_abi.DGEN_FIXED, fixed_tiles=fixed_map(stairs=True)) if fixed else {}
+    cfg = SimConfig(max_ticks=30, seed=23, auto_reset=True, n_npc=npc, **kw)
+    gs, upd, orc = gu.make_pair(cfg, n)
+    ref = gs.clone()
+    rng = np.random.default_rng(n)
+    for t in range(45):
+        mv = rng.integers(1, 6, size=(n, 2), dtype=np.uint8)
+        cmds = torch.from_numpy(pack_moves(mv[:, 0], mv[:, 1]) if packed else mv).cuda()
+        res, obs = upd.update_observe(gs, cmds, packed=packed, stairs_radius=4)
+        res2, _ = upd.update(ref, cmds, packed=packed)
+        obs2 = upd.observe(ref, stairs_radius=4)
+        assert torch.equal(res, res2), t
+        assert torch.equal(obs, obs2), t
+        res_o, _ = orc.step(mv)
+        assert np.array_equal(res.cpu().numpy(), res_o), t
+    gu.assert_state_equal(gs, orc, 'update_observe')
+    assert np.array_equal(obs.cpu().numpy(), expected_obs(gs.planes_cpu(), 4))
 
 
 def test_observe():
