@@ -9,4 +9,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
 python tools/profile_targets.py > gpurun_out/plain_targets.log 2>&1 || { echo "plain targets failed"; exit 1; }
 ncu --set full --clock-control none --import-source on -k regex:^k_step_pipe$ --launch-skip 3 --launch-count 6 -f \
     -o gpurun_out/prof_pipe_$TAG python tools/profile_targets.py > gpurun_out/ncu_pipe.log 2>&1
-tail -2 gpurun_out/ncu_list.log gpurun_out/ncu_pipe.log
+tail -n 2 gpurun_out/ncu_list.log; tail -n 2 gpurun_out/ncu_pipe.log

@@ -1,6 +1,7 @@
 """Turns the ncu artefacts brought back in gpurun_out/ into the committed summaries under profiles/.
 
-  python tools/summarize_profiles.py <round-tag> <launches.csv> <step.ncu-rep> [<rollout.ncu-rep>]
+  python tools/summarize_profiles.py <round-tag> <launches.csv> <prof_pipe.ncu-rep> [<other.ncu-rep> ...]
+  (<prof_pipe.ncu-rep> as captured by tools/profile_round.sh)
 """
 import csv
 import json
@@ -39,8 +40,9 @@ def to_bytes(val, unit):
     return float(val) * m.get(unit, 1)
 
 
-def summarize_report(rep, tag, name):
+def summarize_report(rep, tag, name, first=0, count=None):
     hdr, units, rows = raw_rows(rep)
+    rows = rows[first:first + count] if count else rows[first:]
     idx = {h: i for i, h in enumerate(hdr)}
     launches = []
     for r in rows:
@@ -77,7 +79,10 @@ def main():
     tag, launches_csv, step_rep = sys.argv[1:4]
     os.makedirs(PROF, exist_ok=True)
     print(summarize_launch_list(launches_csv, tag))
-    step = summarize_report(step_rep, tag, 'k_step_pipe')
+    # tools/profile_targets.py order: 2 ticks, 2 observes, 2 fused tick+observe (launches 4..9 of the run)
+    step = summarize_report(step_rep, tag, 'k_step_pipe', 0, 2)
+    summarize_report(step_rep, tag, 'observe_pipe', 2, 2)
+    summarize_report(step_rep, tag, 'step_observe_pipe', 4, 2)
     rd = [to_bytes(*l['dram__bytes_read.sum']) for l in step]
     wr = [to_bytes(*l['dram__bytes_write.sum']) for l in step]
     traffic = {'kernel': step[0]['kernel'], 'launches_profiled': len(step),
