@@ -45,11 +45,12 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     with torch.no_grad():
+        updater.observe(game_state, stairs_radius=4, out=obs)                      # first view; ladder visible when near
         for _ in range(args.ticks):
-            updater.observe(game_state, stairs_radius=4, out=obs)                  # ladder visible when near
             logits = policy(obs.float())                                           # [N, 2, 5]
             moves = (torch.distributions.Categorical(logits=logits).sample() + 1).to(torch.uint8)   # Move codes 1..5
-            updater.update(game_state, moves, out=result)
+            # one pass: the tick and what both players see of the new state (orx_step_observe)
+            updater.update_observe(game_state, moves.contiguous(), stairs_radius=4, out=result, obs_out=obs)
             r = result.long()
             returns[:, 0] += (r == UpdateResult.Player1Win).float() - (r == UpdateResult.Player2Win).float()
             returns[:, 1] -= (r == UpdateResult.Player1Win).float() - (r == UpdateResult.Player2Win).float()
