@@ -94,3 +94,9 @@ def test_product_path_fails_loudly_without_cuda():
     gs = BatchedGameState(SimConfig(), 4, 'cpu')
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         reset_games(gs)
+
+
+def test_graft_entry_build_runs():
+    """The driver's "does it build" hook: compiles (or finds current) liborx + the oracle and checks the ABI version."""
+    import __graft_entry__ as g
+    g.build()
