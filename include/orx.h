@@ -130,7 +130,7 @@ typedef struct OrxEvent {
     int32_t depth;  /* MOVE/DESCEND/DUNGEON: (new) depth; COMBAT: og_damage */
 } OrxEvent;
 
-/* Aggregate counters written by orx_rollout / orx_stats (uint64 each). */
+/* Aggregate counters written by orx_rollout (uint64 each). */
 enum {
     ORX_STAT_TICKS = 0, ORX_STAT_P1_WINS = 1, ORX_STAT_P2_WINS = 2, ORX_STAT_TIES = 3,
     ORX_STAT_EVENTS = 4, ORX_STAT_DESCENTS = 5, ORX_STAT_HITS = 6, ORX_STAT_RESERVED = 7,
