@@ -20,7 +20,7 @@ import torch
 from .. import _abi
 from ..config import SimConfig
 from ..game import world as _world
-from ..game.state import BatchedGameState, empty_room_tiles
+from ..game.state import BatchedGameState
 from . import updates as _updates
 from .updater import BatchedUpdater, DungeonDespawningStrategy, UpdateResult
 

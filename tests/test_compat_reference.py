@@ -4,11 +4,10 @@ same injected draws, and after every tick the two GameStates must be equal (Game
 game/state.py:134-153) and the update lists must agree field by field. No GPU here, so the C oracle
 stands in for the CUDA lane behind the adapter (tests may do that); the CUDA lane itself is checked
 against the same oracle in tests/test_gpu_parity.py."""
-import numpy as np
 import pytest
 import torch
 
-from oracle import cport, philox as px
+from oracle import cport
 from oracle import ref_harness as rh
 from optimax_rogue_b200 import SimConfig
 from optimax_rogue_b200.game.state import empty_room_tiles

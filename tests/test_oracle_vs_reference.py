@@ -1,6 +1,5 @@
 """Pins the C oracle to the LIVE reference (only where /root/reference exists, i.e. the build
 container): same injected draws, every tick compared field by field, events included."""
-import numpy as np
 import pytest
 
 from oracle import ref_harness as rh

@@ -3,7 +3,6 @@ record format of oracle/ref_harness.snapshot, and the vectorised digest."""
 import numpy as np
 
 from oracle import cport
-from oracle import ref_harness as rh
 
 BOT_CODES = {'none': 0, 'random': 1, 'staircase': 2}
 

@@ -3,7 +3,6 @@ CUDA events. Not the judged benchmark (that is bench.py)."""
 import argparse
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
