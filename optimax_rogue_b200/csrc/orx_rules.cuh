@@ -242,7 +242,12 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
     uint32_t pos = __byte_perm(L.pos, 0u, sel);
     uint32_t st = __byte_perm(L.st, 0u, sel);
     const int dA = p2_first ? dl2 : dl1, dB = p2_first ? dl1 : dl2;
-    int depA = p2_first ? L.d2 : L.d1, depB = p2_first ? L.d1 : L.d2;
+    // Depths stay in player order: the hot path only needs "both on the same level", and the role of
+    // each depth is looked up where it is really used (descents, events).
+    int d1 = L.d1, d2 = L.d2;
+    bool same = d1 == d2;
+    auto depA = [&]() { return p2_first ? d2 : d1; };
+    auto depB = [&]() { return p2_first ? d1 : d2; };
     int hpA = p2_first ? L.hp2 : L.hp1, hpB = p2_first ? L.hp1 : L.hp2;
     const int dmgA = p2_first ? P.dmg1 : P.dmg0, dmgB = p2_first ? P.dmg0 : P.dmg1;
     const int idA = p2_first ? 1 : 0, idB = idA ^ 1;
@@ -251,25 +256,26 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
     if (dA != 0) {
         const uint32_t tA = (pos + (uint32_t)dA) & 0xFFFFu;
         int npc = -1;
-        if ((depA == depB) & (tA == (pos >> 16))) {
+        if (same & (tA == (pos >> 16))) {
             // Occupied by B, who acts later: Block if B stays, else Flee. (Parry, updater.py:229-234,
             // would need B.pos + delta == B.pos with a non-Stay move: unreachable.)
             if (dmgA > 0) { hpB -= dmgA; ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idA + 1, idB + 1, dB == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_FLEE, dmgA);
-        } else if (NPC && (npc = npc_at(P, lane, depA, tA & 255u, tA >> 8)) >= 0) {
+        } else if (NPC && (npc = npc_at(P, lane, depA(), tA & 255u, tA >> 8)) >= 0) {
             if (dmgA > 0) { P.npc_hp[(size_t)lane * P.n_npc + npc] -= (int16_t)dmgA; ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idA + 1, 3 + npc, ORX_FLAG_BLOCK, dmgA);
         } else if (is_stairs<DGEN>(P, tiles, tA, st & 0xFFFFu)) {
-            const int nd = depA + 1;
-            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idA, nd, pos >> 16, depB, lane);
-            if (!level_exists(P, idA, nd, depB)) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
+            const int nd = depA() + 1;
+            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idA, nd, pos >> 16, depB(), lane);
+            if (!level_exists(P, idA, nd, depB())) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
             ev.emit(ORX_EV_DESCEND, idA + 1, (r >> 16) & 255u, r >> 24, nd);
-            depA = nd;
+            if (p2_first) d2 = nd; else d1 = nd;
+            same = d1 == d2;
             pos = (pos & 0xFFFF0000u) | (r >> 16);
             st = (st & 0xFFFF0000u) | (r & 0xFFFFu);
             ++cnt.descents;
         } else {
-            ev.emit(ORX_EV_MOVE, idA + 1, tA & 255u, tA >> 8, depA);
+            ev.emit(ORX_EV_MOVE, idA + 1, tA & 255u, tA >> 8, depA());
             pos += (uint32_t)dA;          // the clamp keeps the target on the map: no carry between halves
         }
     }
@@ -277,30 +283,30 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
     if (dB != 0) {
         const uint32_t tB = ((pos >> 16) + (uint32_t)dB) & 0xFFFFu;
         int npc = -1;
-        if ((depA == depB) & (tB == (pos & 0xFFFFu))) {
+        if (same & (tB == (pos & 0xFFFFu))) {
             if (dmgB > 0) { hpA -= dmgB; ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idB + 1, idA + 1, dA == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_AMBUSH, dmgB);
-        } else if (NPC && (npc = npc_at(P, lane, depB, tB & 255u, tB >> 8)) >= 0) {
+        } else if (NPC && (npc = npc_at(P, lane, depB(), tB & 255u, tB >> 8)) >= 0) {
             if (dmgB > 0) { P.npc_hp[(size_t)lane * P.n_npc + npc] -= (int16_t)dmgB; ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idB + 1, 3 + npc, ORX_FLAG_BLOCK, dmgB);
         } else if (is_stairs<DGEN>(P, tiles, tB, st >> 16)) {
-            const int nd = depB + 1;
-            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idB, nd, pos & 0xFFFFu, depA, lane);
-            if (!level_exists(P, idB, nd, depA)) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
+            const int nd = depB() + 1;
+            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idB, nd, pos & 0xFFFFu, depA(), lane);
+            if (!level_exists(P, idB, nd, depA())) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
             ev.emit(ORX_EV_DESCEND, idB + 1, (r >> 16) & 255u, r >> 24, nd);
-            depB = nd;
+            if (p2_first) d1 = nd; else d2 = nd;
             pos = (pos & 0xFFFFu) | (r & 0xFFFF0000u);
             st = (st & 0xFFFFu) | (r << 16);
             ++cnt.descents;
         } else {
-            ev.emit(ORX_EV_MOVE, idB + 1, tB & 255u, tB >> 8, depB);
+            ev.emit(ORX_EV_MOVE, idB + 1, tB & 255u, tB >> 8, depB());
             pos += (uint32_t)dB << 16;
         }
     }
     // ---- back to player order
     L.pos = __byte_perm(pos, 0u, sel);
     L.st = __byte_perm(st, 0u, sel);
-    L.d1 = p2_first ? depB : depA; L.d2 = p2_first ? depA : depB;
+    L.d1 = d1; L.d2 = d2;
     L.hp1 = p2_first ? hpB : hpA; L.hp2 = p2_first ? hpA : hpB;
     if (NPC) {   // dead NPCs leave in reverse entity order (updater.py:137-145)
         for (int k = P.n_npc - 1; k >= 0; --k) {
