@@ -248,8 +248,8 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
     bool same = d1 == d2;
     auto depA = [&]() { return p2_first ? d2 : d1; };
     auto depB = [&]() { return p2_first ? d1 : d2; };
-    int hpA = p2_first ? L.hp2 : L.hp1, hpB = p2_first ? L.hp1 : L.hp2;
-    const int dmgA = p2_first ? P.dmg1 : P.dmg0, dmgB = p2_first ? P.dmg0 : P.dmg1;
+    // Health likewise: a hit is subtracted from the victim's own field inside the (rare) combat branch.
+    int hp1 = L.hp1, hp2 = L.hp2;
     const int idA = p2_first ? 1 : 0, idB = idA ^ 1;
 
     // ---- first mover (handle_move, updater.py:180-243)
@@ -259,9 +259,11 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
         if (same & (tA == (pos >> 16))) {
             // Occupied by B, who acts later: Block if B stays, else Flee. (Parry, updater.py:229-234,
             // would need B.pos + delta == B.pos with a non-Stay move: unreachable.)
-            if (dmgA > 0) { hpB -= dmgA; ++cnt.hits; }
+            const int dmgA = p2_first ? P.dmg1 : P.dmg0;
+            if (dmgA > 0) { if (p2_first) hp1 -= dmgA; else hp2 -= dmgA; ++cnt.hits; }      // the victim is B
             ev.emit(ORX_EV_COMBAT, idA + 1, idB + 1, dB == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_FLEE, dmgA);
         } else if (NPC && (npc = npc_at(P, lane, depA(), tA & 255u, tA >> 8)) >= 0) {
+            const int dmgA = p2_first ? P.dmg1 : P.dmg0;
             if (dmgA > 0) { P.npc_hp[(size_t)lane * P.n_npc + npc] -= (int16_t)dmgA; ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idA + 1, 3 + npc, ORX_FLAG_BLOCK, dmgA);
         } else if (is_stairs<DGEN>(P, tiles, tA, st & 0xFFFFu)) {
@@ -284,9 +286,11 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
         const uint32_t tB = ((pos >> 16) + (uint32_t)dB) & 0xFFFFu;
         int npc = -1;
         if (same & (tB == (pos & 0xFFFFu))) {
-            if (dmgB > 0) { hpA -= dmgB; ++cnt.hits; }
+            const int dmgB = p2_first ? P.dmg0 : P.dmg1;
+            if (dmgB > 0) { if (p2_first) hp2 -= dmgB; else hp1 -= dmgB; ++cnt.hits; }      // the victim is A
             ev.emit(ORX_EV_COMBAT, idB + 1, idA + 1, dA == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_AMBUSH, dmgB);
         } else if (NPC && (npc = npc_at(P, lane, depB(), tB & 255u, tB >> 8)) >= 0) {
+            const int dmgB = p2_first ? P.dmg0 : P.dmg1;
             if (dmgB > 0) { P.npc_hp[(size_t)lane * P.n_npc + npc] -= (int16_t)dmgB; ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idB + 1, 3 + npc, ORX_FLAG_BLOCK, dmgB);
         } else if (is_stairs<DGEN>(P, tiles, tB, st >> 16)) {
@@ -307,7 +311,7 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
     L.pos = __byte_perm(pos, 0u, sel);
     L.st = __byte_perm(st, 0u, sel);
     L.d1 = d1; L.d2 = d2;
-    L.hp1 = p2_first ? hpB : hpA; L.hp2 = p2_first ? hpA : hpB;
+    L.hp1 = hp1; L.hp2 = hp2;
     if (NPC) {   // dead NPCs leave in reverse entity order (updater.py:137-145)
         for (int k = P.n_npc - 1; k >= 0; --k) {
             const size_t j = (size_t)lane * P.n_npc + k;
