@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from optimax_rogue_b200 import build as B          # noqa: E402
 
-TRACED = os.path.join(ROOT, 'optimax_rogue_b200', 'liborx_trace.so')
+TRACED = os.environ.get('ORX_TRACE_LIB') or os.path.join(ROOT, 'optimax_rogue_b200', 'liborx_trace.so')
 if not os.path.exists(TRACED) or '--rebuild' in sys.argv:
     extra = [a for a in sys.argv[1:] if a.startswith('-D')]
     cmd = ['nvcc'] + B.NVCC_FLAGS + ['-DORX_PIPE_TRACE'] + extra + ['-o', TRACED] + B.SOURCES
@@ -61,7 +61,7 @@ with torch.cuda.stream(st):
     torch.cuda.synchronize()
 print(f'games {G}: {e0.elapsed_time(e1) / K * 1e3:.2f} us per step (traced build)')
 lib = _lib.lib()
-buf = np.zeros((16, 512, 8), dtype=np.uint64)
+buf = np.zeros((16, 512, 24), dtype=np.uint64)
 lib.orx_debug_trace.restype = C.c_int
 lib.orx_debug_trace.argtypes = [C.c_void_p]
 assert lib.orx_debug_trace(buf.ctypes.data) == 0
@@ -91,3 +91,48 @@ owned = np.array([(n_tiles - b + n_cta - 1) // n_cta for b in range(n_cta)])
 for k in np.unique(owned):
     e = end[owned == k]
     print(f'CTAs with {k} tiles: {len(e)}; end min {e.min():.2f} med {np.median(e):.2f} max {e.max():.2f} us')
+
+# which CTAs finish late? slot 7 = SM id | tiles handled << 16 (per launch)
+info = t[:, :, 7]
+smid = (info & 0xFFFF)
+ntl = (info >> 16)
+print('last launch: tiles handled per CTA: min %d med %d max %d' % (ntl[15].min(), np.median(ntl[15]), ntl[15].max()))
+ends = np.stack([(t[i, :, 4] - t[i - 1, :, 4].max()) / 1e3 for i in range(1, 16)])      # [15, n_cta]
+sm_of = smid[1:]
+n_sm = int(sm_of.max()) + 1
+per_sm = np.zeros(n_sm); cnt = np.zeros(n_sm)
+for i in range(15):
+    np.add.at(per_sm, sm_of[i], ends[i]); np.add.at(cnt, sm_of[i], 1)
+per_sm /= np.maximum(cnt, 1)
+o = np.argsort(per_sm)
+print('mean CTA end time by SM over 15 launches (us): fastest', ' '.join(f'{k}:{per_sm[k]:.2f}' for k in o[:12]))
+print('                                              slowest', ' '.join(f'{k}:{per_sm[k]:.2f}' for k in o[-12:]))
+print('per-SM mean end: min %.2f p25 %.2f med %.2f p75 %.2f max %.2f' % (per_sm.min(), np.percentile(per_sm, 25), np.median(per_sm), np.percentile(per_sm, 75), per_sm.max()))
+# launch-to-launch consistency: correlation of per-SM end times between two launches
+a = np.zeros(n_sm); b = np.zeros(n_sm)
+np.add.at(a, sm_of[13], ends[13]); np.add.at(b, sm_of[14], ends[14])
+print('correlation of per-SM end-time sums between two launches: %.2f' % np.corrcoef(a, b)[0, 1])
+for i in (13, 14):
+    e = ends[i]; k = ntl[i + 1]
+    for v in np.unique(k):
+        print(f'launch {i + 1}: CTAs that handled {v} tiles: {int((k == v).sum())}, end med {np.median(e[k == v]):.2f} max {e[k == v].max():.2f}')
+
+# per-tile completion times of the last launch (slots 8+k), relative to the previous launch's end
+i = 15
+ref = t[i - 1, :, 4].max()
+k = ntl[i]
+print('tile k done (producer saw the consumers finish it), us after previous end: k | min med max | n CTAs')
+for j in range(12):
+    m = k > j
+    if m.sum() == 0: break
+    v = (t[i, m, 8 + j] - ref) / 1e3
+    print(f'  {j:2d} | {v.min():6.2f} {np.median(v):6.2f} {v.max():6.2f} | {int(m.sum())}')
+# interval between consecutive tiles, early vs late CTAs
+late = ends[14] > np.percentile(ends[14], 80); early = ends[14] < np.percentile(ends[14], 20)
+for name, m in (('late 20%', late), ('early 20%', early)):
+    d = []
+    for j in range(1, 8):
+        mm = m & (k > j)
+        d.append(np.median((t[i, mm, 8 + j] - t[i, mm, 8 + j - 1]) / 1e3))
+    f0 = np.median((t[i, m, 8] - ref) / 1e3)
+    print(f'{name}: first tile done at {f0:.2f}; median interval to next tile, tiles 1..7:', ' '.join(f'{x:.2f}' for x in d), '; tiles handled med', np.median(k[m]))
