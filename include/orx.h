@@ -100,7 +100,13 @@ typedef struct OrxConfig {
     int32_t reserved;
 } OrxConfig;
 
-/* Structure-of-arrays game state; game i of the batch is element i of every plane. */
+/* Structure-of-arrays game state; game i of the batch is element i of every plane.
+ * Layout hint (optional, no effect on results): when the five 4-byte planes are carved out of one
+ * allocation at a common pitch, i.e. hp = pos + pitch, stairs = pos + 2 pitch, tick = pos + 3 pitch,
+ * episode = pos + 4 pitch with pitch a multiple of 16 bytes >= 4 n and pos 16-byte aligned, the tick /
+ * observe kernels address them as one u32[5][n] array through a TMA tensor map and move a 256-game
+ * tile of all five with a single copy instruction each way instead of five. Any other placement works
+ * plane by plane. */
 typedef struct OrxState {
     uint8_t* pos;       /* [n][4]  x1 y1 x2 y2                       Entity.x/.y   entities.py:35-37 */
     int16_t* hp;        /* [n][2]  health                            Entity.health entities.py:38 */

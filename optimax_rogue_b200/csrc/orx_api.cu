@@ -355,6 +355,45 @@ Params offset_params(const Params& P, int64_t off, int64_t n)
     return T;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table: liborx.so does not link libcuda, so
+// it still loads (for the ABI checks) on a machine without a driver.
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder()
+{
+    static const TensorMapEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+
+// The planes pos, hp, stairs, tick, episode as one u32[5][games] array, if the caller laid them out that way
+// (one allocation, common pitch, see orx.h); false: the kernel moves each plane slice on its own.
+bool planes5_map(const Params& P, unsigned int n_tiles, CUtensorMap* map)
+{
+    memset(map, 0, sizeof(*map));
+    if (getenv("ORX_NO_TENSOR_MAP") != nullptr) return false;
+    const char* p0 = reinterpret_cast<const char*>(P.pos);
+    const ptrdiff_t pitch = reinterpret_cast<const char*>(P.hp) - p0;
+    const int64_t games = (int64_t)n_tiles * kTile;
+    if (pitch < games * 4 || (pitch & 15) != 0 || !aligned(p0, 16)) return false;
+    if (reinterpret_cast<const char*>(P.stairs) - p0 != 2 * pitch || reinterpret_cast<const char*>(P.tick) - p0 != 3 * pitch ||
+        reinterpret_cast<const char*>(P.episode) - p0 != 4 * pitch) return false;
+    const TensorMapEncodeFn encode = tensor_map_encoder();
+    if (encode == nullptr) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)games, 5};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)kTile, 5}, estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<char*>(p0), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int DGEN, int CMD, bool OBS, bool TICK>
 int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, unsigned int* sched,
                 int16_t* obs, int obs_radius, cudaStream_t s)
@@ -386,6 +425,8 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     lk.unlock();
     unsigned int grid = (unsigned int)sms * (unsigned int)per_sm;       // persistent: every CTA resident
     if (grid > n_tiles) grid = n_tiles;
+    alignas(64) CUtensorMap planes5;
+    const int use_map = planes5_map(P, n_tiles, &planes5) ? 1 : 0;
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(kPipeThreads); lc.dynamicSmemBytes = smem; lc.stream = s;
     cudaLaunchAttribute at[1];
@@ -394,9 +435,9 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     lc.attrs = at; lc.numAttrs = ORX_PIPE_PDL ? 1 : 0;
 #ifdef ORX_PIPE_TRACE
     static unsigned int trace_slot = 0;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, mv, result, n_tiles, sched, obs, obs_radius, trace_slot++);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, trace_slot++);
 #else
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, mv, result, n_tiles, sched, obs, obs_radius);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius);
 #endif
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
 }

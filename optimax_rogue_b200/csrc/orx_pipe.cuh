@@ -19,6 +19,7 @@
 //             -> fence.proxy.async -> one arrive per warp on done[s]
 //   producer: wait done[s] -> 8 bulk stores + commit_group
 #pragma once
+#include <cuda.h>             // CUtensorMap (type only; the encoder is looked up at run time)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -68,6 +69,8 @@ template <bool OBS> constexpr uint32_t kPipeStageBytes = STAGE_BYTES + (OBS ? OB
 // p2 in the high nibble (halves the command traffic when the commands come over PCIe).
 constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1;
 static_assert(kTile % 32 == 0 && (T1 % 16) == 0, "bulk copies move multiples of 16 bytes");
+static_assert(OFF_HP == OFF_POS + T4 && OFF_ST == OFF_HP + T4 && OFF_TICK == OFF_ST + T4 && OFF_EP == OFF_TICK + T4 && kTile <= 256,
+              "the five 4-byte slices are the rows of the tensor-map box, in plane order");
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -104,6 +107,25 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+// 2-D tiled copies through a tensor map: when the five 4-byte planes (pos, hp, stairs, tick, episode) sit
+// in one allocation at a common pitch they form a u32[5][n] array, and the {256 games x 5 planes} box of a
+// tile moves with ONE instruction instead of five; its rows land back to back in the stage, which is the
+// order the stage already uses. Every bulk instruction costs the producer thread ~40 ns, so this is what
+// bounds how fast a CTA can get its first stages going.
+__device__ __forceinline__ void tensor_load_2d(uint32_t dst_smem, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tensor_store_2d(const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t src_smem)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(src_smem) : "memory");
+}
+__device__ __forceinline__ void tensor_prefetch_l2_2d(const CUtensorMap* map, uint32_t c0, uint32_t c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 // Hint: pull [src, src + bytes) into L2. No architectural effect (L2 is the coherence point of the GPU, a line
 // written later by an earlier grid is updated in place), so it may run ahead of griddepcontrol.wait.
@@ -142,7 +164,8 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 // stage and streamed out with the same bulk stores.
 template <int DGEN, int CMD, bool OBS, bool TICK>
 __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
-k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, uint8_t* __restrict__ result,
+k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap planes5, const int use_map,
+            const void* __restrict__ moves_v, uint8_t* __restrict__ result,
             unsigned int n_tiles, unsigned int* __restrict__ sched, int16_t* __restrict__ obs, int obs_radius ORX_TRACE_PARAM)
 {
     static_assert(OBS || TICK, "nothing to do");
@@ -194,11 +217,15 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
             if (tile == NONE) { mbar_arrive(bar); return; }
             const size_t g = (size_t)tile * kTile;     // first game of the tile
             mbar_expect_tx(bar, LOAD_BYTES);
-            bulk_load(base + OFF_POS, P.pos + g, T4, bar);
-            bulk_load(base + OFF_HP, P.hp + g, T4, bar);
-            bulk_load(base + OFF_ST, P.stairs + g, T4, bar);
-            bulk_load(base + OFF_TICK, P.tick + g, T4, bar);
-            bulk_load(base + OFF_EP, P.episode + g, T4, bar);
+            if (use_map) {
+                tensor_load_2d(base + OFF_POS, &planes5, (uint32_t)g, 0u, bar);
+            } else {
+                bulk_load(base + OFF_POS, P.pos + g, T4, bar);
+                bulk_load(base + OFF_HP, P.hp + g, T4, bar);
+                bulk_load(base + OFF_ST, P.stairs + g, T4, bar);
+                bulk_load(base + OFF_TICK, P.tick + g, T4, bar);
+                bulk_load(base + OFF_EP, P.episode + g, T4, bar);
+            }
             bulk_load(base + OFF_DEPTH, P.depth + g, T8, bar);
             bulk_load(base + OFF_STATUS, P.status + g, T1, bar);
             if (TICK) bulk_load(base + OFF_MOVES, moves + g * (MV_BYTES / kTile), MV_BYTES, bar);
@@ -214,11 +241,15 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
                 const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
                 if (t >= n_tiles) break;
                 const size_t g = (size_t)t * kTile;
-                bulk_prefetch_l2(P.pos + g, T4);
-                bulk_prefetch_l2(P.hp + g, T4);
-                bulk_prefetch_l2(P.stairs + g, T4);
-                bulk_prefetch_l2(P.tick + g, T4);
-                bulk_prefetch_l2(P.episode + g, T4);
+                if (use_map) {
+                    tensor_prefetch_l2_2d(&planes5, (uint32_t)g, 0u);
+                } else {
+                    bulk_prefetch_l2(P.pos + g, T4);
+                    bulk_prefetch_l2(P.hp + g, T4);
+                    bulk_prefetch_l2(P.stairs + g, T4);
+                    bulk_prefetch_l2(P.tick + g, T4);
+                    bulk_prefetch_l2(P.episode + g, T4);
+                }
                 bulk_prefetch_l2(P.depth + g, T8);
                 bulk_prefetch_l2(P.status + g, T1);
             }
@@ -256,6 +287,7 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
         if (!ended && sched != nullptr) held = draw();
 #ifdef ORX_PIPE_TRACE
         unsigned int trace_tiles = 0;
+        ORX_TRACE(trace_slot, 23);          // prologue loads issued
 #endif
         for (unsigned int it = 0;; ++it) {
             const unsigned int s = it % kStages;
@@ -263,17 +295,21 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
             if (tile == NONE) break;
             mbar_wait(done0 + 8 * s, (it / kStages) & 1u);
 #ifdef ORX_PIPE_TRACE
-            if (trace_tiles < 16) ORX_TRACE(trace_slot, 8 + trace_tiles);
+            if (trace_tiles < 14) ORX_TRACE(trace_slot, 8 + trace_tiles);
             ++trace_tiles;
 #endif
             const size_t g = (size_t)tile * kTile;
             const uint32_t base = stage0 + s * STAGE_BYTES;
             if (TICK) {
-                bulk_store(P.pos + g, base + OFF_POS, T4);
-                bulk_store(P.hp + g, base + OFF_HP, T4);
-                bulk_store(P.stairs + g, base + OFF_ST, T4);
-                bulk_store(P.tick + g, base + OFF_TICK, T4);
-                bulk_store(P.episode + g, base + OFF_EP, T4);
+                if (use_map) {
+                    tensor_store_2d(&planes5, (uint32_t)g, 0u, base + OFF_POS);
+                } else {
+                    bulk_store(P.pos + g, base + OFF_POS, T4);
+                    bulk_store(P.hp + g, base + OFF_HP, T4);
+                    bulk_store(P.stairs + g, base + OFF_ST, T4);
+                    bulk_store(P.tick + g, base + OFF_TICK, T4);
+                    bulk_store(P.episode + g, base + OFF_EP, T4);
+                }
                 bulk_store(P.depth + g, base + OFF_DEPTH, T8);
                 bulk_store(P.status + g, base + OFF_STATUS, T1);
                 bulk_store(result + g, base + OFF_RESULT, T1);
@@ -374,6 +410,7 @@ k_step_pipe(const __grid_constant__ Params P, const void* __restrict__ moves_v, 
             sts_u32x4(bo + 16u, w[4], w[5], w[6], w[7]);
             sts_u32x4(bo + 32u, w[8], w[9], w[10], w[11]);
         }
+        if (tid == 0 && it == 0) ORX_TRACE(trace_slot, 22);          // first tile ticked (warp 0)
         fence_proxy_async();                 // generic-proxy writes -> visible to the bulk-store engine
         __syncwarp();
         if ((tid & 31u) == 0) mbar_arrive(done0 + 8 * s);

@@ -132,12 +132,8 @@ class BatchedGameState:
         self.device = torch.device(device)
         self.game_id_base = int(game_id_base)
         dev = self.device
-        self.pos = torch.zeros((n, 4), dtype=torch.uint8, device=dev)
-        self.hp = torch.zeros((n, 2), dtype=torch.int16, device=dev)
+        self._alloc_word_planes()
         self.depth = torch.zeros((n, 2), dtype=torch.int32, device=dev)
-        self.stairs = torch.zeros((n, 4), dtype=torch.uint8, device=dev)
-        self.tick = torch.zeros((n,), dtype=torch.int32, device=dev)
-        self.episode = torch.zeros((n,), dtype=torch.int32, device=dev)
         self.status = torch.ones((n,), dtype=torch.uint8, device=dev)
         e = max(cfg.n_npc, 1)
         self.npc_pos = torch.zeros((n, e, 2), dtype=torch.uint8, device=dev)
@@ -154,6 +150,21 @@ class BatchedGameState:
             # uint16 table shipped as int16 bit pattern (torch has no general uint16 support)
             self.fixed_ground = torch.from_numpy(ground.view(np.int16).copy()).to(dev)
             self._fixed_stairs = stairs
+
+    WORD_PLANES = (('pos', torch.uint8, (4,)), ('hp', torch.int16, (2,)), ('stairs', torch.uint8, (4,)),
+                   ('tick', torch.int32, ()), ('episode', torch.int32, ()))
+
+    def _alloc_word_planes(self):
+        """The five 4-byte-per-game planes are carved out of ONE zeroed allocation at a common pitch (a
+        multiple of 128 bytes), in the order pos, hp, stairs, tick, episode: each stays an ordinary
+        contiguous tensor, and together they form the u32[5][n] array whose {256 games x 5 planes} boxes the
+        tick kernel moves with one tensor-map copy each (include/orx.h, OrxState)."""
+        n = self.n
+        pitch = max(128, (4 * n + 127) // 128 * 128)
+        self._word_planes = torch.zeros((5 * pitch,), dtype=torch.uint8, device=self.device)
+        for k, (name, dtype, shape) in enumerate(self.WORD_PLANES):
+            plane = self._word_planes[k * pitch:k * pitch + 4 * n].view(dtype).view((n,) + shape)
+            setattr(self, name, plane)
 
     # -- ABI views -----------------------------------------------------------------------------
     def c_struct(self) -> _abi.OrxState:
@@ -190,8 +201,13 @@ class BatchedGameState:
     def clone(self) -> 'BatchedGameState':
         o = BatchedGameState.__new__(BatchedGameState)
         o.__dict__.update(self.__dict__)
+        o._alloc_word_planes()
+        word = {name for name, _, _ in self.WORD_PLANES}
         for name in self.PLANES:
-            setattr(o, name, getattr(self, name).clone())
+            if name in word:
+                getattr(o, name).copy_(getattr(self, name))
+            else:
+                setattr(o, name, getattr(self, name).clone())
         o.sched = torch.zeros_like(self.sched)
         return o
 

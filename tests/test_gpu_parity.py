@@ -640,3 +640,44 @@ def test_long_horizon_soak():
             if name == 'episode':
                 a = a.view(np.uint32)
             assert np.array_equal(a, getattr(orc.state, name)), (start, name)
+
+
+@pytest.mark.gpu
+def test_plane_placement_does_not_change_results():
+    """The tick kernel moves pos/hp/stairs/tick/episode with one tensor-map copy per tile when they share an
+    allocation at a common pitch (BatchedGameState does that) and plane by plane otherwise; both equal."""
+    import torch
+    from optimax_rogue_b200 import SimConfig
+    from optimax_rogue_b200.game.state import BatchedGameState
+    from optimax_rogue_b200.logic.updater import BatchedUpdater, reset_games
+    from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
+    dev = torch.device('cuda')
+    n = 256 * 37 + 19                                  # full tiles plus a ragged tail
+    cfg = SimConfig(max_ticks=40, seed=11, auto_reset=True)
+    upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, 40, auto_reset=True)
+    a = BatchedGameState(cfg, n, dev)
+    reset_games(a)
+    assert a.hp.data_ptr() - a.pos.data_ptr() == a.stairs.data_ptr() - a.hp.data_ptr()      # stacked
+    b = a.clone()
+    pitch = (4 * n + 127) // 128 * 128                                                      # scattered:
+    backing = torch.zeros((5 * pitch + 256,), dtype=torch.uint8, device=dev)                # uneven spacing
+    for (name, dtype, shape), off in zip(BatchedGameState.WORD_PLANES, (0, pitch + 16, 2 * pitch + 64, 3 * pitch + 16, 4 * pitch + 128)):
+        plane = backing[off:off + 4 * n].view(dtype).view((n,) + shape)
+        plane.copy_(getattr(a, name))
+        setattr(b, name, plane)
+    pitch_b = b.hp.data_ptr() - b.pos.data_ptr()
+    assert (b.stairs.data_ptr() - b.pos.data_ptr(), b.tick.data_ptr() - b.pos.data_ptr()) != (2 * pitch_b, 3 * pitch_b)
+    g = torch.Generator(device='cpu').manual_seed(5)
+    obs_a = torch.empty((n, 2, 12), dtype=torch.int16, device=dev)
+    obs_b = torch.empty_like(obs_a)
+    for t in range(90):
+        mv = torch.randint(0, 8, (n, 2), dtype=torch.uint8, generator=g).to(dev)
+        if t % 3 == 0:
+            ra, _ = upd.update_observe(a, mv, obs_out=obs_a)
+            rb, _ = upd.update_observe(b, mv, obs_out=obs_b)
+            assert torch.equal(obs_a, obs_b)
+        else:
+            ra, rb = upd.update(a, mv)[0], upd.update(b, mv)[0]
+        assert torch.equal(ra, rb)
+    for name in BatchedGameState.PLANES:
+        assert torch.equal(getattr(a, name), getattr(b, name)), name

@@ -136,3 +136,9 @@ for name, m in (('late 20%', late), ('early 20%', early)):
         d.append(np.median((t[i, mm, 8 + j] - t[i, mm, 8 + j - 1]) / 1e3))
     f0 = np.median((t[i, m, 8] - ref) / 1e3)
     print(f'{name}: first tile done at {f0:.2f}; median interval to next tile, tiles 1..7:', ' '.join(f'{x:.2f}' for x in d), '; tiles handled med', np.median(k[m]))
+
+def rel(col):
+    v = (t[i, :, col] - ref) / 1e3
+    return f'{v.min():.2f}/{np.median(v):.2f}/{v.max():.2f}'
+print('last launch, min/med/max us after previous end: wait passed', rel(1), '| prologue loads issued', rel(23), '| first tile landed (warp 0)', rel(2),
+      '| first tile ticked (warp 0)', rel(22), '| producer saw tile 0 done', rel(8))
