@@ -209,6 +209,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     if (tid >= kTile) {
         // ------------------------------------------------------------ producer (one thread)
         if (tid != kTile) return;
+        if (use_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&planes5) : "memory");     // descriptor fetch off the first copy's path
         // Publishes tile `tile` (or NONE) in the stage of iteration `it` and starts its loads.
         auto issue = [&](unsigned int it, uint32_t tile) {
             const unsigned int s = it % kStages;

@@ -212,8 +212,10 @@ class BatchedGameState:
         return o
 
     def state_dict(self):
-        """Checkpoint: plain tensors + scalars (``torch.save``-able)."""
-        d = {name: getattr(self, name) for name in self.PLANES}
+        """Checkpoint: plain tensors + scalars (``torch.save``-able). The planes that share one
+        allocation are copied out (torch cannot serialise views of one storage under different dtypes)."""
+        word = {name for name, _, _ in self.WORD_PLANES}
+        d = {name: getattr(self, name).clone() if name in word else getattr(self, name) for name in self.PLANES}
         d['game_id_base'] = self.game_id_base
         return d
 
