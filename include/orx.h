@@ -151,6 +151,12 @@ size_t orx_state_bytes(const OrxConfig* cfg);
 /* Event slots per game per tick for this config (ORX_MAX_EVENTS_BASE + n_npc). */
 int orx_max_events(const OrxConfig* cfg);
 
+/* Updater.current_update_order over a batch (updater.py:71-74: every emitted GameStateUpdate takes the next
+ * order number): order[i] += number of records game i emitted this tick (slots with kind != ORX_EV_NONE).
+ * events: device OrxEvent[n][max_events] as written by orx_step; order: device uint64[n]. One pass. */
+int orx_event_count_add(const OrxEvent* events, int max_events, unsigned long long* order, int64_t n,
+                        void* cuda_stream);
+
 /* Episode reset (worldgen.py:77-87 / :124-135). mask: device uint8[n], nullable = all lanes.
  * bump_episode != 0 increments episode[i] before drawing (use 0 for the first initialisation
  * or when the caller wrote the episode plane itself). */

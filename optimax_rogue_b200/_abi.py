@@ -85,6 +85,7 @@ PROTOTYPES = {
     'orx_strerror': (C.c_char_p, [C.c_int]),
     'orx_state_bytes': (C.c_size_t, [C.POINTER(OrxConfig)]),
     'orx_max_events': (C.c_int, [C.POINTER(OrxConfig)]),
+    'orx_event_count_add': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     'orx_reset': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_int,
                             C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_step': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,

@@ -258,6 +258,23 @@ k_observe(const __grid_constant__ Params P, int16_t* __restrict__ obs, int radiu
     o[2] = make_uint4(w[8], w[9], w[10], w[11]);
 }
 
+// ------------------------------------------------------------------ Updater.current_update_order (updater.py:71-74)
+__global__ void __launch_bounds__(kThreads)
+k_event_count_add(const uint2* __restrict__ events, int max_ev, unsigned long long* __restrict__ order, unsigned int n)
+{
+    const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const uint2* e = events + (size_t)i * max_ev;
+    unsigned int c = 0;
+    if (max_ev == ORX_MAX_EVENTS_BASE) {              // 32 bytes per game: two 16-byte loads
+        const uint4 a = reinterpret_cast<const uint4*>(e)[0], b = reinterpret_cast<const uint4*>(e)[1];
+        c = ((a.x & 255u) != 0) + ((a.z & 255u) != 0) + ((b.x & 255u) != 0) + ((b.z & 255u) != 0);
+    } else {
+        for (int k = 0; k < max_ev; ++k) c += (e[k].x & 255u) != 0;
+    }
+    if (c != 0) order[i] += c;
+}
+
 // ------------------------------------------------------------------ host side
 int cuda_fail(cudaError_t e) { return ORX_ERR_CUDA_BASE - (int)e; }
 
@@ -394,12 +411,12 @@ bool planes5_map(const Params& P, unsigned int n_tiles, CUtensorMap* map)
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int DGEN, int CMD, bool OBS, bool TICK>
+template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false>
 int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, unsigned int* sched,
-                int16_t* obs, int obs_radius, cudaStream_t s)
+                int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr)
 {
-    const size_t smem = pipe_smem_bytes<OBS>((int)tiles_bytes);
-    auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK>;
+    const size_t smem = pipe_smem_bytes<OBS, EV>((int)tiles_bytes);
+    auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK, EV>;
     // Launch geometry depends only on (device, kernel, smem): look it up once per process, the
     // occupancy query costs more than the launch itself. (A cache of device properties, not state;
     // one per kernel instantiation.) Guarded by a mutex so that host threads driving different GPUs
@@ -435,21 +452,21 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     lc.attrs = at; lc.numAttrs = ORX_PIPE_PDL ? 1 : 0;
 #ifdef ORX_PIPE_TRACE
     static unsigned int trace_slot = 0;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, trace_slot++);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, events, trace_slot++);
 #else
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, events);
 #endif
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
 }
 
-template <bool OBS>
+template <bool OBS, bool EV = false>
 int launch_tick_pipe(bool empty, int packed, const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t smem,
-                     unsigned int* sched, int16_t* obs, int obs_radius, cudaStream_t s)
+                     unsigned int* sched, int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr)
 {
-    if (packed) return empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES, OBS, true>(P, mv, result, n_tiles, 0, sched, obs, obs_radius, s)
-                             : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES, OBS, true>(P, mv, result, n_tiles, smem, sched, obs, obs_radius, s);
-    return empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES, OBS, true>(P, mv, result, n_tiles, 0, sched, obs, obs_radius, s)
-                 : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES, OBS, true>(P, mv, result, n_tiles, smem, sched, obs, obs_radius, s);
+    if (packed) return empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES, OBS, true, EV>(P, mv, result, n_tiles, 0, sched, obs, obs_radius, s, events)
+                             : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES, OBS, true, EV>(P, mv, result, n_tiles, smem, sched, obs, obs_radius, s, events);
+    return empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES, OBS, true, EV>(P, mv, result, n_tiles, 0, sched, obs, obs_radius, s, events)
+                 : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES, OBS, true, EV>(P, mv, result, n_tiles, smem, sched, obs, obs_radius, s, events);
 }
 
 // One tick; packed = 0: moves uint8[n][2], packed = 1: uint8[n] with p1 | p2 << 4.
@@ -469,20 +486,26 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
     const size_t mv_stride = packed ? 1 : 2;        // command bytes per game
     uint2* ev = reinterpret_cast<uint2*>(events);
     const int max_ev = orx_max_events(cfg);
-    // Hot variant (no NPC slots, no event log): persistent TMA-pipelined kernel over the full
-    // 256-game tiles, the simple kernel for a ragged tail (< 256 games).
-    if (ev == nullptr && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
+    // Hot variants (no NPC slots; plain, with observations, or with the event log): persistent
+    // TMA-pipelined kernel over the full 256-game tiles, the simple kernel for a ragged tail (< 256 games).
+    const bool ev_pipe = ev != nullptr && obs == nullptr && aligned(ev, 16) && getenv("ORX_NO_EVENT_PIPE") == nullptr;
+    if ((ev == nullptr || ev_pipe) && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
         const unsigned int n_tiles = (unsigned int)(n / kTile);
         const int64_t n_body = (int64_t)n_tiles * kTile;
         const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
         unsigned int* sched = aligned(st->sched, 4) && getenv("ORX_STATIC_TILES") == nullptr ? st->sched : nullptr;
         const int rc2 = obs != nullptr ? launch_tick_pipe<true>(empty, packed, P, moves, result, n_tiles, smem, sched, obs, obs_radius, s)
+                        : ev_pipe      ? launch_tick_pipe<false, true>(empty, packed, P, moves, result, n_tiles, smem, sched, nullptr, -1, s, ev)
                                        : launch_tick_pipe<false>(empty, packed, P, moves, result, n_tiles, smem, sched, nullptr, -1, s);
         if (rc2 != ORX_OK || n_body == n) return rc2;
         const Params T = offset_params(P, n_body, n - n_body);
         const int tgrid = grid_for(n - n_body);
         const uint8_t* tail = moves + (size_t)n_body * mv_stride;
-        if (empty) k_step<ORX_DGEN_EMPTY, false, false><<<tgrid, kThreads, 0, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
+        if (ev_pipe) {
+            uint2* tev = ev + (size_t)n_body * max_ev;
+            if (empty) k_step<ORX_DGEN_EMPTY, false, true><<<tgrid, kThreads, 0, s>>>(T, tail, result + n_body, tev, max_ev, packed);
+            else k_step<ORX_DGEN_FIXED, false, true><<<tgrid, kThreads, smem, s>>>(T, tail, result + n_body, tev, max_ev, packed);
+        } else if (empty) k_step<ORX_DGEN_EMPTY, false, false><<<tgrid, kThreads, 0, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
         else k_step<ORX_DGEN_FIXED, false, false><<<tgrid, kThreads, smem, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
         if (obs != nullptr) k_observe<<<tgrid, kThreads, 0, s>>>(T, obs + (size_t)n_body * 2 * ORX_OBS_LEN, obs_radius);
         return launch_done();
@@ -556,6 +579,17 @@ size_t orx_state_bytes(const OrxConfig* cfg)
 int orx_max_events(const OrxConfig* cfg)
 {
     return ORX_MAX_EVENTS_BASE + (cfg != nullptr && cfg->n_npc > 0 ? cfg->n_npc : 0);
+}
+
+int orx_event_count_add(const OrxEvent* events, int max_events, unsigned long long* order, int64_t n, void* cuda_stream)
+{
+    if (events == nullptr || order == nullptr || n < 0 || n > kMaxGamesPerCall || max_events < 1 ||
+        max_events > ORX_MAX_EVENTS_BASE + ORX_MAX_NPC) return ORX_ERR_BAD_ARG;
+    if (!aligned(order, 8) || !aligned(events, max_events == ORX_MAX_EVENTS_BASE ? 16 : 8)) return ORX_ERR_BAD_ARG;
+    if (n == 0) return ORX_OK;
+    k_event_count_add<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        reinterpret_cast<const uint2*>(events), max_events, order, (unsigned int)n);
+    return launch_done();
 }
 
 int orx_reset(const OrxConfig* cfg, const OrxState* st, const uint8_t* mask, int bump_episode,

@@ -54,7 +54,11 @@ constexpr uint32_t kTileIdxBytes = ((uint32_t)kStages * 4u + 15u) & ~15u;   // p
 #endif
 // With observations each stage also carries the tile's 48 B/game observation block (12 KB), so three
 // stages keep three CTAs per SM resident.
-template <bool OBS> constexpr int kPipeStages = OBS ? ORX_PIPE_OBS_STAGES : kStages;
+#ifndef ORX_PIPE_EV_STAGES
+#define ORX_PIPE_EV_STAGES 4
+#endif
+// ... and with the event log its 32 B/game of records (8 KB): four stages.
+template <bool OBS, bool EV = false> constexpr int kPipeStages = OBS ? ORX_PIPE_OBS_STAGES : EV ? ORX_PIPE_EV_STAGES : kStages;
 
 // byte offsets of the plane slices inside a stage (all multiples of 16)
 constexpr uint32_t T4 = 4u * kTile, T8 = 8u * kTile, T2 = 2u * kTile, T1 = kTile;   // slice sizes in bytes
@@ -64,7 +68,9 @@ constexpr uint32_t OFF_POS = 0, OFF_HP = T4, OFF_ST = 2 * T4, OFF_TICK = 3 * T4,
 constexpr uint32_t PLANE_LOAD_BYTES = 5 * T4 + T8 + T1;         // per tile, HBM -> smem, without the commands
 constexpr uint32_t OBS_GAME_BYTES = 2u * ORX_OBS_LEN * 2u, OBS_BYTES = OBS_GAME_BYTES * kTile, OFF_OBS = STAGE_BYTES;
 static_assert(OBS_GAME_BYTES == 48 && (STAGE_BYTES % 128) == 0, "observation block: 12 words per game behind the planes");
-template <bool OBS> constexpr uint32_t kPipeStageBytes = STAGE_BYTES + (OBS ? OBS_BYTES : 0u);
+constexpr uint32_t EV_GAME_BYTES = 8u * ORX_MAX_EVENTS_BASE, EV_BYTES = EV_GAME_BYTES * kTile, OFF_EV = STAGE_BYTES;   // event records share the slot behind the planes
+static_assert(EV_GAME_BYTES == 32, "four 8-byte records per game without NPC slots");
+template <bool OBS, bool EV = false> constexpr uint32_t kPipeStageBytes = STAGE_BYTES + (OBS ? OBS_BYTES : 0u) + (EV ? EV_BYTES : 0u);
 // Command formats: CMD_BYTES = uint8[n][2] (p1, p2); CMD_NIBBLES = uint8[n], p1 in the low nibble,
 // p2 in the high nibble (halves the command traffic when the commands come over PCIe).
 constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1;
@@ -162,16 +168,20 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 // TICK: play one tick and write the planes and results back. OBS: also (or, without TICK, only) write
 // the per-player observations of the resulting state, 48 B per game, staged behind the planes of the
 // stage and streamed out with the same bulk stores.
-template <int DGEN, int CMD, bool OBS, bool TICK>
+// EV: also write the tick's replication-log records (OrxEvent[4] per game, no NPC slots), staged like the
+// observations and streamed out with one bulk store per tile.
+template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false>
 __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
 k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap planes5, const int use_map,
             const void* __restrict__ moves_v, uint8_t* __restrict__ result,
-            unsigned int n_tiles, unsigned int* __restrict__ sched, int16_t* __restrict__ obs, int obs_radius ORX_TRACE_PARAM)
+            unsigned int n_tiles, unsigned int* __restrict__ sched, int16_t* __restrict__ obs, int obs_radius,
+            uint2* __restrict__ events ORX_TRACE_PARAM)
 {
     static_assert(OBS || TICK, "nothing to do");
+    static_assert(!EV || (TICK && !OBS), "the event log rides with the plain tick");
     if (threadIdx.x == 0) ORX_TRACE(trace_slot, 0);
-    constexpr int kStages = kPipeStages<OBS>;                      // shadows the namespace constant on purpose
-    constexpr uint32_t STAGE_BYTES = kPipeStageBytes<OBS>;
+    constexpr int kStages = kPipeStages<OBS, EV>;                  // shadows the namespace constant on purpose
+    constexpr uint32_t STAGE_BYTES = kPipeStageBytes<OBS, EV>;
     constexpr uint32_t MV_BYTES = CMD == CMD_NIBBLES ? T1 : T2, LOAD_BYTES = PLANE_LOAD_BYTES + (TICK ? MV_BYTES : 0u);
     const uint8_t* moves = static_cast<const uint8_t*>(moves_v);
     extern __shared__ __align__(128) uint8_t smem[];
@@ -316,6 +326,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                 bulk_store(result + g, base + OFF_RESULT, T1);
             }
             if (OBS) bulk_store(obs + g * (2 * ORX_OBS_LEN), base + OFF_OBS, OBS_BYTES);
+            if (EV) bulk_store(events + g * ORX_MAX_EVENTS_BASE, base + OFF_EV, EV_BYTES);
             bulk_commit();
             // Refill. With a deep pipeline (>= 5 stages) one iteration late, i.e. the stage whose stores were
             // committed in the PREVIOUS iteration: waiting for the group just committed parks this thread
@@ -381,12 +392,14 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                 mv = lds_u16(b2 + OFF_MOVES);
             }
             int res = status;
+            // this game's four record slots in the stage (generic pointer into shared memory)
+            EvSink<EV> ev{EV ? reinterpret_cast<uint2*>(smem + s * STAGE_BYTES + OFF_EV) + tid * ORX_MAX_EVENTS_BASE : nullptr, 0,
+                          ORX_MAX_EVENTS_BASE};
             if (status == ORX_RESULT_IN_PROGRESS) {          // finished lanes are frozen until reset
                 Stream rs = make_stream(P, lane, ep);
                 const uint4 blk = draw_block(rs, DOM_TICK, SUB_MAIN, (uint32_t)tick);
                 Counters cnt{};
-                EvSink<false> ev{nullptr, 0, 0};
-                res = tick_lane<DGEN, false, false>(P, tiles, lut, L, mv, blk.z, rs, lane, ev, cnt);
+                res = tick_lane<DGEN, false, EV>(P, tiles, lut, L, mv, blk.z, rs, lane, ev, cnt);
                 int new_status = res;
                 if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
                     rs.episode += 1;
@@ -402,6 +415,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                 sts_u8(b1 + OFF_STATUS, (uint32_t)new_status);
             }
             sts_u8(b1 + OFF_RESULT, (uint32_t)res);
+            ev.finish();                             // unused slots (all four of a frozen lane) read ORX_EV_NONE
         }
         if (OBS) {                                   // what each player sees of the state as it now is
             uint32_t w[12];
@@ -419,10 +433,10 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     if (tid == 0) ORX_TRACE(trace_slot, 6);
 }
 
-template <bool OBS>
+template <bool OBS, bool EV = false>
 constexpr size_t pipe_smem_bytes(int fixed_tiles)
 {
-    return (size_t)kPipeStages<OBS> * kPipeStageBytes<OBS> + 2 * kPipeStages<OBS> * 8 + kTileIdxBytes + (size_t)fixed_tiles;
+    return (size_t)kPipeStages<OBS, EV> * kPipeStageBytes<OBS, EV> + 2 * kPipeStages<OBS, EV> * 8 + kTileIdxBytes + (size_t)fixed_tiles;
 }
 
 }  // namespace orx

@@ -86,12 +86,13 @@ class BatchedUpdater:
         self.max_ticks = max_ticks
         self.auto_reset = auto_reset
         self.current_update_order = None
+        self.track_order = True        # False: want_events=True returns the records without counting them (saves two passes over them)
         self._cache = None
 
     # -- plumbing ------------------------------------------------------------------------------
     def _cfg(self, gs: BatchedGameState):
         key = (id(gs), gs.game_id_base, int(self.despawn_strat), int(self.max_ticks or 0), int(self.auto_reset),
-               gs.pos.data_ptr(), gs.sched.data_ptr())
+               gs.sched.data_ptr()) + tuple(id(getattr(gs, name)) for name in gs.PLANES)
         if self._cache is None or self._cache[0] != key:
             if (gs.cfg.width, gs.cfg.height, gs.cfg.dgen_kind) != (self.dgen.width, self.dgen.height, self.dgen.kind):
                 raise ValueError('updater.dgen does not match the generator the game state was built with')
@@ -156,7 +157,7 @@ class BatchedUpdater:
                     events.data_ptr() if events is not None else None, gs.n,
                     gs.game_id_base, _stream_ptr(gs.device))
         _lib.check(rc, 'orx_step_packed' if packed else 'orx_step')
-        if events is not None:
+        if events is not None and self.track_order:
             self._advance_order(gs, events)
         return result, events
 
@@ -216,7 +217,10 @@ class BatchedUpdater:
     def _advance_order(self, gs, events):
         if self.current_update_order is None:
             self.current_update_order = torch.zeros((gs.n,), dtype=torch.int64, device=gs.device)
-        self.current_update_order += ((events[:, :, 0] & 0xFF) != 0).sum(dim=1)
+        with _on_device(gs.device):
+            rc = _lib.lib().orx_event_count_add(events.data_ptr(), int(events.shape[1]),
+                                                self.current_update_order.data_ptr(), gs.n, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_event_count_add')
 
     def get_incr_upd_order(self):
         """Per-game count of GameStateUpdates emitted so far (updater.py:71-74)."""

@@ -681,3 +681,44 @@ def test_plane_placement_does_not_change_results():
         assert torch.equal(ra, rb)
     for name in BatchedGameState.PLANES:
         assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
+@pytest.mark.gpu
+def test_event_log_through_the_tile_pipeline_equals_the_simple_kernel():
+    """With no NPC slots the event records of full 256-game tiles are staged in shared memory and
+    streamed out by the pipelined tick kernel; ORX_NO_EVENT_PIPE=1 forces the one-thread-per-game
+    kernel. Same records, same results, same states; and the running update order
+    (Updater.get_incr_upd_order, updater.py:71-74) equals the number of records emitted."""
+    import os
+    import torch
+    from optimax_rogue_b200 import SimConfig
+    from optimax_rogue_b200.game.state import BatchedGameState
+    from optimax_rogue_b200.logic.updater import BatchedUpdater, reset_games
+    from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
+    dev = torch.device('cuda')
+    n = 256 * 21 + 77
+    cfg = SimConfig(max_ticks=50, seed=23, auto_reset=True, width=12, height=7)     # small room: combat and stairs are frequent
+    dg = EmptyDungeonGenerator(12, 7)
+    ua, ub = BatchedUpdater(dg, 2, 50, auto_reset=True), BatchedUpdater(dg, 2, 50, auto_reset=True)
+    a = BatchedGameState(cfg, n, dev)
+    reset_games(a)
+    b = a.clone()
+    g = torch.Generator(device='cpu').manual_seed(9)
+    expect = torch.zeros((n,), dtype=torch.int64, device=dev)
+    kinds_seen = set()
+    for t in range(120):
+        mv = torch.randint(0, 7, (n, 2), dtype=torch.uint8, generator=g).to(dev)
+        ra, ea = ua.update(a, mv, want_events=True)
+        os.environ['ORX_NO_EVENT_PIPE'] = '1'
+        try:
+            rb, eb = ub.update(b, mv, want_events=True)
+        finally:
+            del os.environ['ORX_NO_EVENT_PIPE']
+        assert torch.equal(ra, rb) and torch.equal(ea, eb), t
+        k = ea[:, :, 0] & 0xFF
+        expect += (k != 0).sum(dim=1)
+        kinds_seen.update(int(x) for x in torch.unique(k).cpu())
+    assert {1, 2, 3, 5} <= kinds_seen                   # move, combat, dungeon created, descend (4 = NPC death: no NPCs here)
+    for name in BatchedGameState.PLANES:
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(ua.get_incr_upd_order(), expect) and torch.equal(ub.get_incr_upd_order(), expect)
