@@ -17,6 +17,7 @@ Timed regions (CUDA events on the launching stream, max over ranks):
             nibble-packed commands (1 B per game in, 1 B out); ``unpacked`` = uint8[N,2] commands;
             ``pipelined`` = two independent batches in flight, no per-step stream sync
   rollout   (extra) fused multi-tick kernel with both bots on device
+  roofline.large_batch  (extra) the value leg at 4 G games per launch, where the fixed cost of a launch weighs a quarter
 L2: the timed loop rotates over B independent batches whose combined state exceeds the 126 MB L2.
 
 ``--impl reference`` times the CPU side instead: the plain-C restatement of the reference updater
@@ -374,6 +375,36 @@ def run_b200(args, rank, local_rank, world):
         ms_roll = e4.elapsed_time(e5)
         roll_ticks = int(stats[0].item())
 
+        # ---- the same tick kernel at 4x the batch (extra): the fixed per-launch cost (ramp / drain of one
+        # dependent kernel boundary, ~2.4 us) weighs a quarter as much, which shows what the kernel body streams
+        GL, nbl, KL = 4 * G, 3, 60
+        big = []
+        for b in range(nbl):
+            gsl = BatchedGameState(cfg, GL, dev, game_id_base=(1 << 40) + (rank * nbl + b) * GL)
+            reset_games(gsl)
+            upd.rollout(gsl, 1, 1, 29 * (b + 1))
+            big.append(gsl)
+        big_moves = torch.randint(1, 6, (4, GL, 2), dtype=torch.uint8, device=dev, generator=gen)
+        big_res = torch.empty((GL,), dtype=torch.uint8, device=dev)
+        for k in range(3):
+            upd.update(big[k % nbl], big_moves[k % 4], out=big_res)
+        torch.cuda.synchronize(dev)
+        g_big = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_big, stream=stream):
+            for k in range(KL):
+                upd.update(big[k % nbl], big_moves[k % 4], out=big_res)
+        g_big.replay()
+        torch.cuda.synchronize(dev)
+        barrier()
+        e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e8.record(stream)
+        g_big.replay()
+        e9.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms_big = e8.elapsed_time(e9)
+        del big, big_moves, big_res, g_big
+
         # ---- ruleset R1 (extra; README-only rules, parity unpinned): configs[2], 65,536 games per GPU
         from optimax_rogue_b200.r1 import R1GameState
         G1, nb1, K1 = 1 << 16, 18, 72
@@ -428,6 +459,7 @@ def run_b200(args, rank, local_rank, world):
     ms_e2e_pipelined = max_over_ranks(ms_e2e_pipelined)
     ms_roll = max_over_ranks(ms_roll)
     ms_so = max_over_ranks(ms_so)
+    ms_big = max_over_ranks(ms_big)
     ms_r1 = max_over_ranks(ms_r1)
     ms_r1_roll = max_over_ranks(ms_r1_roll)
     if world > 1:
@@ -454,7 +486,12 @@ def run_b200(args, rank, local_rank, world):
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (tr or {}).get('dram_bytes_per_launch'), 'peak_source': peak_src,
                          'kernel': 'k_step_pipe<EMPTY,CMD_BYTES>', 'alg_bytes_per_game_tick': B_ALG,
-                         'games_per_launch': G},
+                         'games_per_launch': G,
+                         'large_batch': {'games_per_launch': GL, 'us_per_step': ms_big / KL * 1e3, 'steps': KL,
+                                         'achieved': B_ALG * GL / (ms_big / KL * 1e-3) / 1e9,
+                                         'frac': B_ALG * GL / (ms_big / KL * 1e-3) / 1e9 / peak,
+                                         'note': 'same kernel, same config, 4x the games per launch (3 rotating batches, '
+                                                 f'{3 * 32 * GL / 1e6:.0f} MB of planes): the per-launch ramp/drain weighs a quarter as much'}},
             'e2e': {'value': world * G * k_e2e / (ms_e2e * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': G, 'd2h_bytes_per_step': G, 'steps': k_e2e,
                     'api': 'BatchedUpdater.host_stepper(state, pinned host uint8[N] commands p1|p2<<4, pinned host uint8[N] results)() '
