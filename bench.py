@@ -405,6 +405,37 @@ def run_b200(args, rank, local_rank, world):
         ms_big = e8.elapsed_time(e9)
         del big, big_moves, big_res, g_big
 
+        # ---- strong scaling (extra, N > 1): BASELINE.json's "1M games sharded across 8xB200" read literally,
+        # 2^20 games in total, 2^20 / N per GPU; still one launch per step per GPU, rotating batches > L2
+        ms_strong, Gs, KS = 0.0, G // world, 400
+        if world > 1:
+            nbs = min(64, max(2, -(-300_000_000 // (32 * Gs))))
+            small = []
+            for b in range(nbs):
+                gss = BatchedGameState(cfg, Gs, dev, game_id_base=(1 << 41) + b * G + rank * Gs)
+                reset_games(gss)
+                upd.rollout(gss, 1, 1, 11 * (b + 1))
+                small.append(gss)
+            small_res = torch.empty((Gs,), dtype=torch.uint8, device=dev)
+            for k in range(3):
+                upd.update(small[k % nbs], moves[k % n_move_sets][:Gs], out=small_res)
+            torch.cuda.synchronize(dev)
+            g_small = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_small, stream=stream):
+                for k in range(KS):
+                    upd.update(small[k % nbs], moves[k % n_move_sets][:Gs], out=small_res)
+            g_small.replay()
+            torch.cuda.synchronize(dev)
+            barrier()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            g_small.replay()
+            eb.record(stream)
+            torch.cuda.synchronize(dev)
+            barrier()
+            ms_strong = ea.elapsed_time(eb)
+            del small, small_res, g_small
+
         # ---- ruleset R1 (extra; README-only rules, parity unpinned): configs[2], 65,536 games per GPU
         from optimax_rogue_b200.r1 import R1GameState
         G1, nb1, K1 = 1 << 16, 18, 72
@@ -460,6 +491,7 @@ def run_b200(args, rank, local_rank, world):
     ms_roll = max_over_ranks(ms_roll)
     ms_so = max_over_ranks(ms_so)
     ms_big = max_over_ranks(ms_big)
+    ms_strong = max_over_ranks(ms_strong)
     ms_r1 = max_over_ranks(ms_r1)
     ms_r1_roll = max_over_ranks(ms_r1_roll)
     if world > 1:
@@ -503,6 +535,10 @@ def run_b200(args, rank, local_rank, world):
                                   'api': 'host_stepper(..., sync=False) = orx_step_host_packed on two independent batches in flight; '
                                          'the host waits on step k-1\'s event after enqueueing step k'}},
             'gpu_launches': K,
+            **({'strong_scaling': {'value': world * Gs * KS / (ms_strong * 1e-3), 'unit': UNIT, 'global_games': world * Gs,
+                                   'games_per_gpu': Gs, 'us_per_step': ms_strong / KS * 1e3, 'steps': KS,
+                                   'note': '2^20 games in total sharded over the GPUs (BASELINE.json configs[3] read literally); '
+                                           'the headline value is the weak-scaling figure at 2^20 games per GPU'}} if world > 1 else {}),
             'step_observe': {'value': world * G * k_so / (ms_so * 1e-3), 'unit': UNIT, 'us_per_step': ms_so / k_so * 1e3,
                              'steps': k_so, 'alg_bytes_per_game_tick': B_ALG + 48,
                              'hbm_frac': (B_ALG + 48) * G / (ms_so / k_so * 1e-3) / 1e9 / peak,
