@@ -1,23 +1,30 @@
-// Persistent, TMA-fed version of the tick kernel (the hot variant: no NPC slots, no event log).
+// Persistent, TMA-fed version of the tick kernel (the hot variants: no NPC slots; plain, with the
+// observations, or with the event log).
 //
 // Every CTA works through 256-game tiles: its first kStages tiles are fixed (blockIdx.x + i * grid),
 // the rest are claimed from a per-state counter (OrxState.sched) as stages free up, so that CTAs
 // which happen to run slower -- the spread of finishing times under static assignment was 6 us on
-// a 14 us launch -- take fewer tiles and the grid drains within one tile time. Without a counter
-// (sched == NULL) the assignment is the static stride. One producer thread streams each tile's eight
-// plane slices HBM -> shared memory with 1-D bulk copies (cp.async.bulk, completion on an
-// mbarrier), kStages tiles ahead of the eight compute warps; the compute warps pull their game
-// into registers, run tick_lane, write the new planes back into the same stage, and the producer
-// streams the stage shared memory -> HBM with bulk stores before refilling it. Loads therefore
-// stay in flight for the whole life of the CTA instead of only at the start of each thread, and
-// no thread does per-plane 64-bit address arithmetic.
+// a 14 us launch -- take fewer tiles. Without a counter (sched == NULL) the assignment is the static
+// stride. One producer thread streams each tile's plane slices HBM -> shared memory (completion on
+// an mbarrier), kStages tiles ahead of the eight compute warps: the five 4-byte planes as ONE 2-D
+// tensor-map box when the caller stacked them at a common pitch (else five 1-D bulk copies), depth,
+// status and commands as 1-D bulk copies. The compute warps pull their game into registers, run
+// tick_lane, write the new planes back into the same stage, and the producer streams the stage
+// shared memory -> HBM with bulk stores before refilling it. Loads therefore stay in flight for the
+// whole life of the CTA instead of only at the start of each thread, and no thread does per-plane
+// 64-bit address arithmetic.
 //
 // Stage life cycle (stage s, tiles s, s+kStages, ...):
-//   producer: wait_group.read (previous bulk stores have drained the stage) -> expect_tx(full[s])
-//             -> 8 bulk loads
+//   producer: wait_group.read (earlier bulk stores have drained the stage) -> expect_tx(full[s])
+//             -> loads (4 copies with the tensor map, 8 without)
 //   consumer: wait full[s] -> smem -> registers -> tick -> registers -> smem (in place)
 //             -> fence.proxy.async -> one arrive per warp on done[s]
-//   producer: wait done[s] -> 8 bulk stores + commit_group
+//   producer: wait done[s] -> stores + commit_group; with >= 5 stages the refill of a stage happens
+//             one iteration after its stores were committed (wait_group.read 1), so the producer never
+//             sits out the read-out of the stage it has just handed to the store engine
+//
+// Between launches: PDL lets the next grid's CTAs become resident while this grid drains; until
+// griddepcontrol.wait releases them they prefetch their first two tiles into L2.
 #pragma once
 #include <cuda.h>             // CUtensorMap (type only; the encoder is looked up at run time)
 #include <cuda_runtime.h>
