@@ -340,12 +340,14 @@ def test_concurrent_host_threads_on_separate_streams():
         gu.assert_state_equal(pairs[b][0], pairs[b][2], f'thread {b}')
 
 
-@pytest.mark.parametrize('n', [(1 << 19) + 37, 1 << 16, 1000 * 256, 1500 * 256 + 5, 1776 * 256, 1777 * 256])
+@pytest.mark.parametrize('n', [(1 << 19) + 37, 1 << 16, 1000 * 256, 1500 * 256 + 5, 1776 * 256, 1777 * 256,
+                               2300 * 256, 2664 * 256, 2665 * 256, 3000 * 256 + 5])
 def test_dynamic_tile_scheduler_equals_static_assignment(n):
-    """OrxState.sched: tiles beyond the first four per CTA are claimed from a counter. The outcome may not
-    depend on who ticks which tile, and the counter words must be zero again after every launch. Sizes
-    cover every regime of tiles vs resident CTAs (444 on a B200): fewer tiles than CTAs, a partial fixed
-    prefix, claimers that all miss, exactly no dynamic tile, one dynamic tile, many."""
+    """OrxState.sched: tiles beyond the first kStages (6; 4 earlier in the round) per CTA are claimed from a
+    counter. The outcome may not depend on who ticks which tile, and the counter words must be zero again
+    after every launch. Sizes cover every regime of tiles vs resident CTAs (444 on a B200) for both depths:
+    fewer tiles than CTAs, a partial fixed prefix, claimers that all miss (last fixed round partly filled),
+    exactly no dynamic tile (1776 / 2664 tiles), one dynamic tile, many."""
     cfg = SimConfig(max_ticks=60, seed=17, auto_reset=True)
     gs, upd, orc = gu.make_pair(cfg, n)
     static = gs.clone()
