@@ -273,7 +273,9 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             }
         }
 #endif
+#ifndef ORX_EXPERIMENT_NO_GRID_WAIT     // tuning experiment only: measures what the grid dependency costs when consecutive launches touch different states
         if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // all earlier work in the stream is complete and visible
+#endif
         ORX_TRACE(trace_slot, 1);
         // Prologue: the first kStages tiles of a CTA are fixed, so its loads start without a round trip
         // to the counter.
