@@ -217,6 +217,15 @@ int orx_replay(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, u
 int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stairs_radius,
                 int64_t n, void* cuda_stream);
 
+/* orx_step with scripted players (optimax_rogue_bots/randombot.py:20-21, staircasebot.py:9-20): a player whose
+ * bot kind is ORX_BOT_RANDOM / ORX_BOT_STAIRCASE gets the command orx_bot_moves would compute for this tick, inside
+ * the tick kernel (no second launch, no round trip of the commands through HBM); ORX_BOT_NONE takes the player's
+ * command from moves (device uint8[n][2], always required). events and obs as in orx_step / orx_step_observe, both
+ * nullable. For training a policy against a scripted opponent. */
+int orx_step_bots(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, int bot_p1, int bot_p2,
+                  uint8_t* result, OrxEvent* events, int16_t* obs, int stairs_radius, int64_t n,
+                  uint64_t game_id_base, void* cuda_stream);
+
 /* orx_step (moves_packed == 0: uint8[n][2]) or orx_step_packed (moves_packed != 0: uint8[n]) fused with
  * orx_observe of the resulting state: what a self-play loop needs per tick, in one pass over the
  * planes (61 + 48 bytes per game instead of 61 + 77). obs: device int16[n][2][ORX_OBS_LEN], 16-byte

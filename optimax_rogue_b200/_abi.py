@@ -106,6 +106,8 @@ PROTOTYPES = {
                               C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_replay': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p, C.c_int,
                              C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step_bots': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_step_observe': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_observe': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_int,

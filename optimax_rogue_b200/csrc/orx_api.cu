@@ -57,7 +57,7 @@ __device__ __forceinline__ const uint8_t* stage_tiles(const Params& P, uint8_t* 
 template <int DGEN, bool NPC, bool EV>
 __global__ void __launch_bounds__(kThreads, 4)
 k_step(const __grid_constant__ Params P, const void* __restrict__ moves, uint8_t* __restrict__ result,
-       uint2* __restrict__ events, int max_ev, int packed)
+       uint2* __restrict__ events, int max_ev, int packed, int bots = 0)
 {
     extern __shared__ uint8_t smem[];
     __shared__ CmdEntry lut[256];
@@ -91,6 +91,10 @@ k_step(const __grid_constant__ Params P, const void* __restrict__ moves, uint8_t
     unpack_lane(L, pos, hpw, dep, stw, tick, ep);
     Stream s = make_stream(P, i, ep);
     const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)tick);
+    if (bots != 0) {                      // scripted players (orx_step_bots): kind of p1 | kind of p2 << 8
+        if ((bots & 255) != ORX_BOT_NONE) mv = (mv & 0xFF00u) | bot_move(bots & 255, L.pos & 0xFFFFu, L.st & 0xFFFFu, blk.x);
+        if ((bots >> 8) != ORX_BOT_NONE) mv = (mv & 0x00FFu) | (bot_move(bots >> 8, L.pos >> 16, L.st >> 16, blk.y) << 8);
+    }
     Counters cnt{};
     int res = tick_lane<DGEN, NPC, EV>(P, tiles, lut, L, mv, blk.z, s, i, ev, cnt);
     ev.finish();
@@ -413,7 +417,7 @@ bool planes5_map(const Params& P, unsigned int n_tiles, CUtensorMap* map)
 
 template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false>
 int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, unsigned int* sched,
-                int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr)
+                int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
 {
     const size_t smem = pipe_smem_bytes<OBS, EV>((int)tiles_bytes);
     auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK, EV>;
@@ -452,17 +456,22 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     lc.attrs = at; lc.numAttrs = ORX_PIPE_PDL ? 1 : 0;
 #ifdef ORX_PIPE_TRACE
     static unsigned int trace_slot = 0;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, events, trace_slot++);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, events, bots, trace_slot++);
 #else
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, events);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, events, bots);
 #endif
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
 }
 
 template <bool OBS, bool EV = false>
 int launch_tick_pipe(bool empty, int packed, const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t smem,
-                     unsigned int* sched, int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr)
+                     unsigned int* sched, int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
 {
+    if constexpr (!EV) {
+        if (bots != 0 && !packed)
+            return empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES_BOTS, OBS, true>(P, mv, result, n_tiles, 0, sched, obs, obs_radius, s, nullptr, bots)
+                         : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES_BOTS, OBS, true>(P, mv, result, n_tiles, smem, sched, obs, obs_radius, s, nullptr, bots);
+    }
     if (packed) return empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES, OBS, true, EV>(P, mv, result, n_tiles, 0, sched, obs, obs_radius, s, events)
                              : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES, OBS, true, EV>(P, mv, result, n_tiles, smem, sched, obs, obs_radius, s, events);
     return empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES, OBS, true, EV>(P, mv, result, n_tiles, 0, sched, obs, obs_radius, s, events)
@@ -473,7 +482,7 @@ int launch_tick_pipe(bool empty, int packed, const Params& P, const void* mv, ui
 // obs != NULL: also writes the observations of the resulting state (orx_step_observe).
 int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, uint8_t* result,
               OrxEvent* events, int64_t n, uint64_t game_id_base, void* cuda_stream, int packed,
-              int16_t* obs = nullptr, int obs_radius = -1)
+              int16_t* obs = nullptr, int obs_radius = -1, int bots = 0)
 {
     const int rc = check_common(cfg, st, n);
     if (rc != ORX_OK) return rc;
@@ -488,15 +497,15 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
     const int max_ev = orx_max_events(cfg);
     // Hot variants (no NPC slots; plain, with observations, or with the event log): persistent
     // TMA-pipelined kernel over the full 256-game tiles, the simple kernel for a ragged tail (< 256 games).
-    const bool ev_pipe = ev != nullptr && obs == nullptr && aligned(ev, 16) && getenv("ORX_NO_EVENT_PIPE") == nullptr;
+    const bool ev_pipe = ev != nullptr && obs == nullptr && bots == 0 && aligned(ev, 16) && getenv("ORX_NO_EVENT_PIPE") == nullptr;
     if ((ev == nullptr || ev_pipe) && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
         const unsigned int n_tiles = (unsigned int)(n / kTile);
         const int64_t n_body = (int64_t)n_tiles * kTile;
         const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
         unsigned int* sched = aligned(st->sched, 4) && getenv("ORX_STATIC_TILES") == nullptr ? st->sched : nullptr;
-        const int rc2 = obs != nullptr ? launch_tick_pipe<true>(empty, packed, P, moves, result, n_tiles, smem, sched, obs, obs_radius, s)
+        const int rc2 = obs != nullptr ? launch_tick_pipe<true>(empty, packed, P, moves, result, n_tiles, smem, sched, obs, obs_radius, s, nullptr, bots)
                         : ev_pipe      ? launch_tick_pipe<false, true>(empty, packed, P, moves, result, n_tiles, smem, sched, nullptr, -1, s, ev)
-                                       : launch_tick_pipe<false>(empty, packed, P, moves, result, n_tiles, smem, sched, nullptr, -1, s);
+                                       : launch_tick_pipe<false>(empty, packed, P, moves, result, n_tiles, smem, sched, nullptr, -1, s, nullptr, bots);
         if (rc2 != ORX_OK || n_body == n) return rc2;
         const Params T = offset_params(P, n_body, n - n_body);
         const int tgrid = grid_for(n - n_body);
@@ -505,15 +514,15 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
             uint2* tev = ev + (size_t)n_body * max_ev;
             if (empty) k_step<ORX_DGEN_EMPTY, false, true><<<tgrid, kThreads, 0, s>>>(T, tail, result + n_body, tev, max_ev, packed);
             else k_step<ORX_DGEN_FIXED, false, true><<<tgrid, kThreads, smem, s>>>(T, tail, result + n_body, tev, max_ev, packed);
-        } else if (empty) k_step<ORX_DGEN_EMPTY, false, false><<<tgrid, kThreads, 0, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
-        else k_step<ORX_DGEN_FIXED, false, false><<<tgrid, kThreads, smem, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
+        } else if (empty) k_step<ORX_DGEN_EMPTY, false, false><<<tgrid, kThreads, 0, s>>>(T, tail, result + n_body, nullptr, max_ev, packed, bots);
+        else k_step<ORX_DGEN_FIXED, false, false><<<tgrid, kThreads, smem, s>>>(T, tail, result + n_body, nullptr, max_ev, packed, bots);
         if (obs != nullptr) k_observe<<<tgrid, kThreads, 0, s>>>(T, obs + (size_t)n_body * 2 * ORX_OBS_LEN, obs_radius);
         return launch_done();
     }
     const int grid = grid_for(n);
     return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
-        if (ev != nullptr) k_step<DGEN, NPC, true><<<grid, kThreads, smem, s>>>(P, moves, result, ev, max_ev, packed);
-        else k_step<DGEN, NPC, false><<<grid, kThreads, smem, s>>>(P, moves, result, nullptr, max_ev, packed);
+        if (ev != nullptr) k_step<DGEN, NPC, true><<<grid, kThreads, smem, s>>>(P, moves, result, ev, max_ev, packed, bots);
+        else k_step<DGEN, NPC, false><<<grid, kThreads, smem, s>>>(P, moves, result, nullptr, max_ev, packed, bots);
         if (obs != nullptr) k_observe<<<grid, kThreads, 0, s>>>(P, obs, obs_radius);
         return launch_done();
     });
@@ -734,6 +743,14 @@ int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stai
     }
     k_observe<<<grid_for(n), kThreads, 0, s>>>(P, obs, stairs_radius);
     return launch_done();
+}
+
+int orx_step_bots(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, int bot_p1, int bot_p2, uint8_t* result,
+                  OrxEvent* events, int16_t* obs, int stairs_radius, int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    if (bot_p1 < ORX_BOT_NONE || bot_p1 > ORX_BOT_STAIRCASE || bot_p2 < ORX_BOT_NONE || bot_p2 > ORX_BOT_STAIRCASE) return ORX_ERR_BAD_ARG;
+    if (obs != nullptr && !aligned(obs, 16)) return ORX_ERR_BAD_ARG;
+    return step_impl(cfg, st, moves, result, events, n, game_id_base, cuda_stream, 0, obs, stairs_radius, bot_p1 | (bot_p2 << 8));
 }
 
 int orx_step_observe(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, int moves_packed,

@@ -80,7 +80,7 @@ static_assert(EV_GAME_BYTES == 32, "four 8-byte records per game without NPC slo
 template <bool OBS, bool EV = false> constexpr uint32_t kPipeStageBytes = STAGE_BYTES + (OBS ? OBS_BYTES : 0u) + (EV ? EV_BYTES : 0u);
 // Command formats: CMD_BYTES = uint8[n][2] (p1, p2); CMD_NIBBLES = uint8[n], p1 in the low nibble,
 // p2 in the high nibble (halves the command traffic when the commands come over PCIe).
-constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1;
+constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1, CMD_BYTES_BOTS = 2;   // _BOTS: uint8[n][2], scripted players' commands computed in the kernel
 static_assert(kTile % 32 == 0 && (T1 % 16) == 0, "bulk copies move multiples of 16 bytes");
 static_assert(OFF_HP == OFF_POS + T4 && OFF_ST == OFF_HP + T4 && OFF_TICK == OFF_ST + T4 && OFF_EP == OFF_TICK + T4 && kTile <= 256,
               "the five 4-byte slices are the rows of the tensor-map box, in plane order");
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
 k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap planes5, const int use_map,
             const void* __restrict__ moves_v, uint8_t* __restrict__ result,
             unsigned int n_tiles, unsigned int* __restrict__ sched, int16_t* __restrict__ obs, int obs_radius,
-            uint2* __restrict__ events ORX_TRACE_PARAM)
+            uint2* __restrict__ events, int bots ORX_TRACE_PARAM)
 {
     static_assert(OBS || TICK, "nothing to do");
     static_assert(!EV || (TICK && !OBS), "the event log rides with the plain tick");
@@ -407,6 +407,10 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             if (status == ORX_RESULT_IN_PROGRESS) {          // finished lanes are frozen until reset
                 Stream rs = make_stream(P, lane, ep);
                 const uint4 blk = draw_block(rs, DOM_TICK, SUB_MAIN, (uint32_t)tick);
+                if (CMD == CMD_BYTES_BOTS) {      // bots = kind of p1 | kind of p2 << 8; words 0 / 1 of the block are the RandomBots' draws
+                    if ((bots & 255) != ORX_BOT_NONE) mv = (mv & 0xFF00u) | bot_move(bots & 255, L.pos & 0xFFFFu, L.st & 0xFFFFu, blk.x);
+                    if ((bots >> 8) != ORX_BOT_NONE) mv = (mv & 0x00FFu) | (bot_move(bots >> 8, L.pos >> 16, L.st >> 16, blk.y) << 8);
+                }
                 Counters cnt{};
                 res = tick_lane<DGEN, false, EV>(P, tiles, lut, L, mv, blk.z, rs, lane, ev, cnt);
                 int new_status = res;

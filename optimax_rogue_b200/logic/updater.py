@@ -309,5 +309,35 @@ class BatchedUpdater:
         _lib.check(rc, 'orx_step_observe')
         return result, obs
 
+    def update_with_bots(self, game_state: BatchedGameState, moves: torch.Tensor, bot_p1: int = 0, bot_p2: int = 0, *,
+                         want_events: bool = False, observe: bool = False, stairs_radius: int = -1,
+                         out: typing.Optional[torch.Tensor] = None, obs_out: typing.Optional[torch.Tensor] = None):
+        """One tick in which scripted players move themselves (``orx_step_bots``): ``bot_p1`` / ``bot_p2`` are
+        ``bots.BOT_NONE`` (the player's command comes from ``moves``), ``BOT_RANDOM`` or ``BOT_STAIRCASE``
+        (``optimax_rogue_bots/randombot.py``, ``staircasebot.py``; computed inside the tick kernel, exactly the
+        command ``bot_moves`` would return). ``moves``: CUDA uint8[N,2]. For training a policy against a scripted
+        opponent without a second launch. Returns ``(result, events or None, obs or None)``."""
+        gs = game_state
+        _require_cuda(gs)
+        if (not isinstance(moves, torch.Tensor) or not moves.is_cuda or moves.dtype != torch.uint8
+                or tuple(moves.shape) != (gs.n, 2) or not moves.is_contiguous()):
+            raise ValueError(f'moves must be a contiguous CUDA uint8 tensor of shape ({gs.n}, 2)')
+        cfg, st = self._cfg(gs)
+        result = out if out is not None else torch.empty((gs.n,), dtype=torch.uint8, device=gs.device)
+        events = obs = None
+        if want_events:
+            events = torch.empty((gs.n, _abi.MAX_EVENTS_BASE + gs.cfg.n_npc, 2), dtype=torch.int32, device=gs.device)
+        if observe or obs_out is not None:
+            obs = obs_out if obs_out is not None else torch.empty((gs.n, 2, _abi.OBS_LEN), dtype=torch.int16, device=gs.device)
+        with _on_device(gs.device):
+            rc = _lib.lib().orx_step_bots(C.byref(cfg), C.byref(st), moves.data_ptr(), int(bot_p1), int(bot_p2),
+                                          result.data_ptr(), events.data_ptr() if events is not None else None,
+                                          obs.data_ptr() if obs is not None else None, int(stairs_radius), gs.n,
+                                          gs.game_id_base, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_step_bots')
+        if events is not None and self.track_order:
+            self._advance_order(gs, events)
+        return result, events, obs
+
     def reset(self, game_state: BatchedGameState, mask=None, bump_episode: bool = True):
         reset_games(game_state, mask, bump_episode)

@@ -724,3 +724,47 @@ def test_event_log_through_the_tile_pipeline_equals_the_simple_kernel():
     for name in BatchedGameState.PLANES:
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert torch.equal(ua.get_incr_upd_order(), expect) and torch.equal(ub.get_incr_upd_order(), expect)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('bots', [(0, 1), (2, 0), (1, 2), (2, 2), (0, 0)])
+@pytest.mark.parametrize('fixed', [False, True])
+def test_scripted_players_inside_the_tick(bots, fixed):
+    """orx_step_bots == orx_bot_moves for the scripted players, merged with the caller's commands for the
+    others, then orx_step: same results, planes, event records and observations; pipelined tiles and the ragged
+    tail."""
+    import torch
+    from optimax_rogue_b200.game.state import BatchedGameState
+    from optimax_rogue_b200.logic.updater import BatchedUpdater, reset_games
+    dev = torch.device('cuda')
+    n = 256 * 9 + 31
+    if fixed:
+        cfg = SimConfig(dgen_kind=_abi.DGEN_FIXED, fixed_tiles=fixed_map(stairs=True), max_ticks=70, seed=41, auto_reset=True)
+    else:
+        cfg = SimConfig(max_ticks=70, seed=41, auto_reset=True, width=14, height=8)
+    a, upd, _ = gu.make_pair(cfg, n)
+    b = a.clone()
+    upd_b = BatchedUpdater(upd.dgen, upd.despawn_strat, upd.max_ticks, auto_reset=True)
+    g = torch.Generator(device='cpu').manual_seed(3)
+    for t in range(80):
+        mv = torch.randint(1, 6, (n, 2), dtype=torch.uint8, generator=g).to(dev)
+        ref_mv = mv.clone()
+        scripted = upd_b.bot_moves(b, bots[0], bots[1])
+        for p in range(2):
+            if bots[p] != 0:
+                ref_mv[:, p] = scripted[:, p]
+        mode = t % 3
+        if mode == 0:
+            ra, _, _ = upd.update_with_bots(a, mv, bots[0], bots[1])
+            rb, _ = upd_b.update(b, ref_mv)
+        elif mode == 1:
+            ra, _, oa = upd.update_with_bots(a, mv, bots[0], bots[1], observe=True, stairs_radius=3)
+            rb, ob = upd_b.update_observe(b, ref_mv, stairs_radius=3)
+            assert torch.equal(oa, ob), t
+        else:
+            ra, ea, _ = upd.update_with_bots(a, mv, bots[0], bots[1], want_events=True)
+            rb, eb = upd_b.update(b, ref_mv, want_events=True)
+            assert torch.equal(ea, eb), t
+        assert torch.equal(ra, rb), t
+    for name in BatchedGameState.PLANES:
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
