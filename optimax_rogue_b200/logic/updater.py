@@ -313,7 +313,7 @@ class BatchedUpdater:
                          want_events: bool = False, observe: bool = False, stairs_radius: int = -1,
                          out: typing.Optional[torch.Tensor] = None, obs_out: typing.Optional[torch.Tensor] = None):
         """One tick in which scripted players move themselves (``orx_step_bots``): ``bot_p1`` / ``bot_p2`` are
-        ``bots.BOT_NONE`` (the player's command comes from ``moves``), ``BOT_RANDOM`` or ``BOT_STAIRCASE``
+        ``_abi.BOT_NONE`` = 0 (the player's command comes from ``moves``), ``_abi.BOT_RANDOM`` or ``_abi.BOT_STAIRCASE``
         (``optimax_rogue_bots/randombot.py``, ``staircasebot.py``; computed inside the tick kernel, exactly the
         command ``bot_moves`` would return). ``moves``: CUDA uint8[N,2]. For training a policy against a scripted
         opponent without a second launch. Returns ``(result, events or None, obs or None)``."""
