@@ -214,6 +214,57 @@ class BatchedUpdater:
             return keep[4]
         return step
 
+    def device_stepper(self, game_state: BatchedGameState, moves: torch.Tensor, result: torch.Tensor, *,
+                       packed: bool = False, obs: typing.Optional[torch.Tensor] = None, stairs_radius: int = -1,
+                       bots: typing.Tuple[int, int] = (0, 0), stream: typing.Optional[torch.cuda.Stream] = None):
+        """The device-resident counterpart of ``host_stepper``: binds one game state, a CUDA command buffer
+        (uint8[N,2], or uint8[N] with ``packed=True``), a CUDA result buffer and optionally an observation
+        buffer (int16[N,2,OBS_LEN]) and returns ``step()``: one call = one tick (``orx_step`` /
+        ``orx_step_packed`` / ``orx_step_observe`` / ``orx_step_bots``) on ``stream`` (default: the stream
+        current NOW) with the commands that are in ``moves`` at that point of the stream. All argument
+        marshalling happens here, once, so an eager loop pays one ctypes call per tick -- what a loop that
+        alternates a small policy network with the environment needs. The bound tensors must stay alive and
+        in place (the closure keeps references)."""
+        gs = game_state
+        _require_cuda(gs)
+        shape = (gs.n,) if packed else (gs.n, 2)
+        if (not moves.is_cuda or moves.dtype != torch.uint8 or tuple(moves.shape) != shape or not moves.is_contiguous()
+                or not result.is_cuda or result.dtype != torch.uint8 or tuple(result.shape) != (gs.n,)):
+            raise ValueError(f'need contiguous CUDA uint8 tensors of shape {shape} and ({gs.n},)')
+        if obs is not None and (not obs.is_cuda or obs.dtype != torch.int16 or tuple(obs.shape) != (gs.n, 2, _abi.OBS_LEN)
+                                or not obs.is_contiguous()):
+            raise ValueError(f'obs must be a contiguous CUDA int16 tensor of shape ({gs.n}, 2, {_abi.OBS_LEN})')
+        if tuple(bots) != (0, 0) and packed:
+            raise ValueError('scripted players take the uint8[N,2] command format')
+        cfg, st = self._cfg(gs)
+        sptr = C.c_void_p((stream or torch.cuda.current_stream(gs.device)).cuda_stream)
+        n, gid = C.c_int64(gs.n), C.c_uint64(gs.game_id_base)
+        mv, res = C.c_void_p(moves.data_ptr()), C.c_void_p(result.data_ptr())
+        lib = _lib.lib()
+        if tuple(bots) != (0, 0):
+            name, fn = 'orx_step_bots', lib.orx_step_bots
+            args = (C.byref(cfg), C.byref(st), mv, C.c_int(int(bots[0])), C.c_int(int(bots[1])), res, None,
+                    C.c_void_p(obs.data_ptr()) if obs is not None else None, C.c_int(int(stairs_radius)), n, gid, sptr)
+        elif obs is not None:
+            name, fn = 'orx_step_observe', lib.orx_step_observe
+            args = (C.byref(cfg), C.byref(st), mv, C.c_int(int(bool(packed))), res, C.c_void_p(obs.data_ptr()),
+                    C.c_int(int(stairs_radius)), n, gid, sptr)
+        else:
+            name = 'orx_step_packed' if packed else 'orx_step'
+            fn = getattr(lib, name)
+            args = (C.byref(cfg), C.byref(st), mv, res, None, n, gid, sptr)
+        keep = (cfg, st, moves, result, obs, gs, stream)
+        dev_index = gs.device.index or 0
+
+        def step():
+            if torch.cuda.current_device() != dev_index:
+                torch.cuda.set_device(dev_index)
+            rc = fn(*args)
+            if rc != 0:
+                _lib.check(rc, name)
+            return keep[3]
+        return step
+
     def _advance_order(self, gs, events):
         if self.current_update_order is None:
             self.current_update_order = torch.zeros((gs.n,), dtype=torch.int64, device=gs.device)

@@ -768,3 +768,41 @@ def test_scripted_players_inside_the_tick(bots, fixed):
         assert torch.equal(ra, rb), t
     for name in BatchedGameState.PLANES:
         assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
+@pytest.mark.gpu
+def test_device_stepper_equals_update():
+    """BatchedUpdater.device_stepper: the bound, pre-marshalled call equals update / update_observe /
+    update_with_bots, with the commands read from the bound buffer at each call."""
+    import torch
+    from optimax_rogue_b200.game.state import BatchedGameState
+    from optimax_rogue_b200.logic.moves import pack_moves
+    from optimax_rogue_b200.logic.updater import BatchedUpdater
+    n = 256 * 5 + 9
+    cfg = SimConfig(max_ticks=50, seed=77, auto_reset=True, width=16, height=9)
+    a, upd, _ = gu.make_pair(cfg, n)
+    b = a.clone()
+    upd_b = BatchedUpdater(upd.dgen, upd.despawn_strat, upd.max_ticks, auto_reset=True)
+    mv = torch.empty((n, 2), dtype=torch.uint8, device='cuda')
+    cmd = torch.empty((n,), dtype=torch.uint8, device='cuda')
+    res = torch.empty((n,), dtype=torch.uint8, device='cuda')
+    obs = torch.empty((n, 2, 12), dtype=torch.int16, device='cuda')
+    steppers = [upd.device_stepper(a, mv, res), upd.device_stepper(a, cmd, res, packed=True),
+                upd.device_stepper(a, mv, res, obs=obs, stairs_radius=2), upd.device_stepper(a, mv, res, bots=(2, 0))]
+    g = torch.Generator(device='cpu').manual_seed(1)
+    for t in range(60):
+        m = torch.randint(1, 6, (n, 2), dtype=torch.uint8, generator=g).cuda()
+        mv.copy_(m)
+        cmd.copy_(pack_moves(m[:, 0], m[:, 1]))
+        k = t % 4
+        ra = steppers[k]()
+        if k < 2:
+            rb, _ = upd_b.update(b, m)
+        elif k == 2:
+            rb, ob = upd_b.update_observe(b, m, stairs_radius=2)
+            assert torch.equal(obs, ob), t
+        else:
+            rb, _, _ = upd_b.update_with_bots(b, m, 2, 0)
+        assert torch.equal(ra, rb), t
+    for name in BatchedGameState.PLANES:
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
