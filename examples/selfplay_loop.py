@@ -28,6 +28,8 @@ def main():
     ap.add_argument('--games', type=int, default=65536)
     ap.add_argument('--ticks', type=int, default=200)
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--opponent', choices=['self', 'random', 'staircase'], default='self',
+                    help='player 2: the same policy (self-play), or a scripted bot that moves inside the tick kernel')
     args = ap.parse_args()
     dev = torch.device('cuda')
     torch.manual_seed(args.seed)
@@ -49,8 +51,14 @@ def main():
         for _ in range(args.ticks):
             logits = policy(obs.float())                                           # [N, 2, 5]
             moves = (torch.distributions.Categorical(logits=logits).sample() + 1).to(torch.uint8)   # Move codes 1..5
-            # one pass: the tick and what both players see of the new state (orx_step_observe)
-            updater.update_observe(game_state, moves.contiguous(), stairs_radius=4, out=result, obs_out=obs)
+            # one pass: the tick and what both players see of the new state (orx_step_observe); against a
+            # scripted opponent its command is computed inside the same kernel (orx_step_bots)
+            if args.opponent == 'self':
+                updater.update_observe(game_state, moves.contiguous(), stairs_radius=4, out=result, obs_out=obs)
+            else:
+                kind = _abi.BOT_RANDOM if args.opponent == 'random' else _abi.BOT_STAIRCASE
+                updater.update_with_bots(game_state, moves.contiguous(), _abi.BOT_NONE, kind, stairs_radius=4,
+                                         out=result, obs_out=obs)
             r = result.long()
             returns[:, 0] += (r == UpdateResult.Player1Win).float() - (r == UpdateResult.Player2Win).float()
             returns[:, 1] -= (r == UpdateResult.Player1Win).float() - (r == UpdateResult.Player2Win).float()

@@ -511,6 +511,9 @@ def test_selfplay_example_runs():
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert 'game-ticks/s' in out.stdout
+    out = subprocess.run([sys.executable, os.path.join(root, 'examples', 'selfplay_loop.py'), '--games', '4096', '--ticks', '20',
+                          '--opponent', 'staircase'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and 'game-ticks/s' in out.stdout, out.stderr[-2000:]
 
 
 def test_single_game_interop_and_event_decoding():
