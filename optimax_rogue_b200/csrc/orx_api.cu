@@ -96,12 +96,14 @@ k_step(const __grid_constant__ Params P, const void* __restrict__ moves, uint8_t
         if ((bots >> 8) != ORX_BOT_NONE) mv = (mv & 0x00FFu) | (bot_move(bots >> 8, L.pos >> 16, L.st >> 16, blk.y) << 8);
     }
     Counters cnt{};
-    int res = tick_lane<DGEN, NPC, EV>(P, tiles, lut, L, mv, blk.z, s, i, ev, cnt);
+    const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
+    const NpcView* nv = NPC ? &slots : nullptr;
+    int res = tick_lane<DGEN, NPC, EV>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
     ev.finish();
     result[i] = (uint8_t)res;
     if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
         s.episode += 1;
-        reset_lane<DGEN, NPC>(P, L, s, i);
+        reset_lane<DGEN, NPC>(P, L, s, nv);
         res = ORX_RESULT_IN_PROGRESS;
     }
     store_lane(P, i, L, res);
@@ -117,7 +119,8 @@ k_reset(const __grid_constant__ Params P, const uint8_t* __restrict__ mask, int 
     if (mask != nullptr && mask[i] == 0) return;
     Lane L;
     Stream s = make_stream(P, i, P.episode[i] + (bump ? 1u : 0u));
-    reset_lane<DGEN, NPC>(P, L, s, i);
+    const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
+    reset_lane<DGEN, NPC>(P, L, s, NPC ? &slots : nullptr);
     store_lane(P, i, L, ORX_RESULT_IN_PROGRESS);
 }
 
@@ -174,11 +177,13 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
             load_lane(P, i, L);
             Stream s = make_stream(P, i, L.episode);
             EvSink<false> ev{nullptr, 0, 0};
+            const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
+            const NpcView* nv = NPC ? &slots : nullptr;
             for (int t = 0; t < n_ticks; ++t) {
                 const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
                 const uint32_t m1 = bot_move(bot1, L.pos & 0xFFFFu, L.st & 0xFFFFu, blk.x);
                 const uint32_t m2 = bot_move(bot2, L.pos >> 16, L.st >> 16, blk.y);
-                const int res = tick_lane<DGEN, NPC, false>(P, tiles, lut, L, m1 | (m2 << 8), blk.z, s, i, ev, cnt);
+                const int res = tick_lane<DGEN, NPC, false>(P, tiles, lut, L, m1 | (m2 << 8), blk.z, s, nv, ev, cnt);
                 ++cnt.ticks;
                 if (res != ORX_RESULT_IN_PROGRESS) {
                     cnt.p1 += res == ORX_RESULT_PLAYER1_WIN;
@@ -186,7 +191,7 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
                     cnt.ties += res == ORX_RESULT_TIE;
                     if (P.auto_reset) {
                         s.episode += 1;
-                        reset_lane<DGEN, NPC>(P, L, s, i);
+                        reset_lane<DGEN, NPC>(P, L, s, nv);
                     } else {
                         status = res;
                         break;
@@ -229,15 +234,17 @@ k_replay(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, u
     Stream s = make_stream(P, i, L.episode);
     EvSink<false> ev{nullptr, 0, 0};
     Counters cnt{};
+    const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
+    const NpcView* nv = NPC ? &slots : nullptr;
     for (int t = 0; t < n_ticks; ++t) {
         const size_t at = (size_t)t * P.n + i;
         if (status != ORX_RESULT_IN_PROGRESS) { results[at] = (uint8_t)status; continue; }   // frozen lane
         const uint32_t mv = moves[at];
         const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
-        const int res = tick_lane<DGEN, NPC, false>(P, tiles, lut, L, mv, blk.z, s, i, ev, cnt);
+        const int res = tick_lane<DGEN, NPC, false>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
         results[at] = (uint8_t)res;
         if (res != ORX_RESULT_IN_PROGRESS) {
-            if (P.auto_reset) { s.episode += 1; reset_lane<DGEN, NPC>(P, L, s, i); }
+            if (P.auto_reset) { s.episode += 1; reset_lane<DGEN, NPC>(P, L, s, nv); }
             else status = res;
         }
     }
@@ -372,6 +379,7 @@ Params offset_params(const Params& P, int64_t off, int64_t n)
 {
     Params T = P;
     T.pos += off; T.hp += off; T.depth += off; T.stairs += off; T.tick += off; T.episode += off; T.status += off;
+    if (P.n_npc > 0) { T.npc_pos += 2 * off * P.n_npc; T.npc_hp += off * P.n_npc; T.npc_depth += off * P.n_npc; }
     T.n = (unsigned int)n; T.gid_base = P.gid_base + (unsigned long long)off;
     return T;
 }
@@ -415,12 +423,12 @@ bool planes5_map(const Params& P, unsigned int n_tiles, CUtensorMap* map)
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false>
+template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, bool NPC = false>
 int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, unsigned int* sched,
                 int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
 {
-    const size_t smem = pipe_smem_bytes<OBS, EV>((int)tiles_bytes);
-    auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK, EV>;
+    const size_t smem = pipe_smem_bytes<OBS, EV, NPC>((int)tiles_bytes);
+    auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK, EV, NPC>;
     // Launch geometry depends only on (device, kernel, smem): look it up once per process, the
     // occupancy query costs more than the launch itself. (A cache of device properties, not state;
     // one per kernel instantiation.) Guarded by a mutex so that host threads driving different GPUs
@@ -495,8 +503,28 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
     const size_t mv_stride = packed ? 1 : 2;        // command bytes per game
     uint2* ev = reinterpret_cast<uint2*>(events);
     const int max_ev = orx_max_events(cfg);
-    // Hot variants (no NPC slots; plain, with observations, or with the event log): persistent
+    // Hot variants (plain, with observations, with the event log, or with NPC slots): persistent
     // TMA-pipelined kernel over the full 256-game tiles, the simple kernel for a ragged tail (< 256 games).
+    const bool npc_pipe = cfg->n_npc > 0 && ev == nullptr && obs == nullptr && bots == 0 && aligned(st->npc_pos, 16) &&
+                          aligned(st->npc_hp, 16) && aligned(st->npc_depth, 16) && getenv("ORX_NO_NPC_PIPE") == nullptr;
+    if (npc_pipe && n >= kTile && pipe_aligned(st, moves, result)) {
+        const unsigned int n_tiles = (unsigned int)(n / kTile);
+        const int64_t n_body = (int64_t)n_tiles * kTile;
+        const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
+        unsigned int* sched = aligned(st->sched, 4) && getenv("ORX_STATIC_TILES") == nullptr ? st->sched : nullptr;
+        int rc2;
+        if (packed) rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES, false, true, false, true>(P, moves, result, n_tiles, 0, sched, nullptr, -1, s)
+                                : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES, false, true, false, true>(P, moves, result, n_tiles, smem, sched, nullptr, -1, s);
+        else rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES, false, true, false, true>(P, moves, result, n_tiles, 0, sched, nullptr, -1, s)
+                         : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES, false, true, false, true>(P, moves, result, n_tiles, smem, sched, nullptr, -1, s);
+        if (rc2 != ORX_OK || n_body == n) return rc2;
+        const Params T = offset_params(P, n_body, n - n_body);
+        const int tgrid = grid_for(n - n_body);
+        const uint8_t* tail = moves + (size_t)n_body * mv_stride;
+        if (empty) k_step<ORX_DGEN_EMPTY, true, false><<<tgrid, kThreads, 0, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
+        else k_step<ORX_DGEN_FIXED, true, false><<<tgrid, kThreads, smem, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
+        return launch_done();
+    }
     const bool ev_pipe = ev != nullptr && obs == nullptr && bots == 0 && aligned(ev, 16) && getenv("ORX_NO_EVENT_PIPE") == nullptr;
     if ((ev == nullptr || ev_pipe) && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
         const unsigned int n_tiles = (unsigned int)(n / kTile);

@@ -65,7 +65,11 @@ constexpr uint32_t kTileIdxBytes = ((uint32_t)kStages * 4u + 15u) & ~15u;   // p
 #define ORX_PIPE_EV_STAGES 4
 #endif
 // ... and with the event log its 32 B/game of records (8 KB): four stages.
-template <bool OBS, bool EV = false> constexpr int kPipeStages = OBS ? ORX_PIPE_OBS_STAGES : EV ? ORX_PIPE_EV_STAGES : kStages;
+#ifndef ORX_PIPE_NPC_STAGES
+#define ORX_PIPE_NPC_STAGES 3
+#endif
+// ... and with NPC slots room for eight of them per game (16 KB per tile): three stages.
+template <bool OBS, bool EV = false, bool NPC = false> constexpr int kPipeStages = NPC ? ORX_PIPE_NPC_STAGES : OBS ? ORX_PIPE_OBS_STAGES : EV ? ORX_PIPE_EV_STAGES : kStages;
 
 // byte offsets of the plane slices inside a stage (all multiples of 16)
 constexpr uint32_t T4 = 4u * kTile, T8 = 8u * kTile, T2 = 2u * kTile, T1 = kTile;   // slice sizes in bytes
@@ -77,7 +81,10 @@ constexpr uint32_t OBS_GAME_BYTES = 2u * ORX_OBS_LEN * 2u, OBS_BYTES = OBS_GAME_
 static_assert(OBS_GAME_BYTES == 48 && (STAGE_BYTES % 128) == 0, "observation block: 12 words per game behind the planes");
 constexpr uint32_t EV_GAME_BYTES = 8u * ORX_MAX_EVENTS_BASE, EV_BYTES = EV_GAME_BYTES * kTile, OFF_EV = STAGE_BYTES;   // event records share the slot behind the planes
 static_assert(EV_GAME_BYTES == 32, "four 8-byte records per game without NPC slots");
-template <bool OBS, bool EV = false> constexpr uint32_t kPipeStageBytes = STAGE_BYTES + (OBS ? OBS_BYTES : 0u) + (EV ? EV_BYTES : 0u);
+// NPC slot planes of a tile, sized for ORX_MAX_NPC slots: pos 2 B, hp 2 B, depth 4 B per slot
+constexpr uint32_t NPC_POS_MAX = 2u * ORX_MAX_NPC * kTile, NPC_BYTES_MAX = 8u * ORX_MAX_NPC * kTile,
+                   OFF_NPOS = STAGE_BYTES, OFF_NHP = OFF_NPOS + NPC_POS_MAX, OFF_NDEPTH = OFF_NHP + NPC_POS_MAX;
+template <bool OBS, bool EV = false, bool NPC = false> constexpr uint32_t kPipeStageBytes = STAGE_BYTES + (OBS ? OBS_BYTES : 0u) + (EV ? EV_BYTES : 0u) + (NPC ? NPC_BYTES_MAX : 0u);
 // Command formats: CMD_BYTES = uint8[n][2] (p1, p2); CMD_NIBBLES = uint8[n], p1 in the low nibble,
 // p2 in the high nibble (halves the command traffic when the commands come over PCIe).
 constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1, CMD_BYTES_BOTS = 2;   // _BOTS: uint8[n][2], scripted players' commands computed in the kernel
@@ -177,7 +184,8 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 // stage and streamed out with the same bulk stores.
 // EV: also write the tick's replication-log records (OrxEvent[4] per game, no NPC slots), staged like the
 // observations and streamed out with one bulk store per tile.
-template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false>
+// NPC: the game's NPC slot planes (n_npc <= ORX_MAX_NPC slots) travel with the tile as three more slices.
+template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, bool NPC = false>
 __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
 k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap planes5, const int use_map,
             const void* __restrict__ moves_v, uint8_t* __restrict__ result,
@@ -186,9 +194,11 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
 {
     static_assert(OBS || TICK, "nothing to do");
     static_assert(!EV || (TICK && !OBS), "the event log rides with the plain tick");
+    static_assert(!NPC || (TICK && !OBS && !EV), "NPC slots ride with the plain tick");
     if (threadIdx.x == 0) ORX_TRACE(trace_slot, 0);
-    constexpr int kStages = kPipeStages<OBS, EV>;                  // shadows the namespace constant on purpose
-    constexpr uint32_t STAGE_BYTES = kPipeStageBytes<OBS, EV>;
+    constexpr int kStages = kPipeStages<OBS, EV, NPC>;             // shadows the namespace constant on purpose
+    constexpr uint32_t STAGE_BYTES = kPipeStageBytes<OBS, EV, NPC>;
+    const uint32_t npc2 = NPC ? 2u * (uint32_t)P.n_npc * kTile : 0u;     // bytes of a tile's npc_pos / npc_hp slice; npc_depth: twice that
     constexpr uint32_t MV_BYTES = CMD == CMD_NIBBLES ? T1 : T2, LOAD_BYTES = PLANE_LOAD_BYTES + (TICK ? MV_BYTES : 0u);
     const uint8_t* moves = static_cast<const uint8_t*>(moves_v);
     extern __shared__ __align__(128) uint8_t smem[];
@@ -234,7 +244,12 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             sts_u32(tidx0 + 4 * s, tile);
             if (tile == NONE) { mbar_arrive(bar); return; }
             const size_t g = (size_t)tile * kTile;     // first game of the tile
-            mbar_expect_tx(bar, LOAD_BYTES);
+            mbar_expect_tx(bar, LOAD_BYTES + 4u * npc2);
+            if (NPC) {
+                bulk_load(base + OFF_NPOS, P.npc_pos + g * 2u * P.n_npc, npc2, bar);
+                bulk_load(base + OFF_NHP, P.npc_hp + g * P.n_npc, npc2, bar);
+                bulk_load(base + OFF_NDEPTH, P.npc_depth + g * P.n_npc, 2u * npc2, bar);
+            }
             if (use_map) {
                 tensor_load_2d(base + OFF_POS, &planes5, (uint32_t)g, 0u, bar);
             } else {
@@ -336,6 +351,11 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             }
             if (OBS) bulk_store(obs + g * (2 * ORX_OBS_LEN), base + OFF_OBS, OBS_BYTES);
             if (EV) bulk_store(events + g * ORX_MAX_EVENTS_BASE, base + OFF_EV, EV_BYTES);
+            if (NPC) {
+                bulk_store(P.npc_pos + g * 2u * P.n_npc, base + OFF_NPOS, npc2);
+                bulk_store(P.npc_hp + g * P.n_npc, base + OFF_NHP, npc2);
+                bulk_store(P.npc_depth + g * P.n_npc, base + OFF_NDEPTH, 2u * npc2);
+            }
             bulk_commit();
             // Refill. With a deep pipeline (>= 5 stages) one iteration late, i.e. the stage whose stores were
             // committed in the PREVIOUS iteration: waiting for the group just committed parks this thread
@@ -404,6 +424,13 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             // this game's four record slots in the stage (generic pointer into shared memory)
             EvSink<EV> ev{EV ? reinterpret_cast<uint2*>(smem + s * STAGE_BYTES + OFF_EV) + tid * ORX_MAX_EVENTS_BASE : nullptr, 0,
                           ORX_MAX_EVENTS_BASE};
+            // this game's NPC slots in the stage (generic pointers into shared memory)
+            uint8_t* const stage_g = smem + s * STAGE_BYTES;
+            const NpcView slots = NPC ? NpcView{stage_g + OFF_NPOS + tid * 2u * P.n_npc,
+                                                reinterpret_cast<int16_t*>(stage_g + OFF_NHP) + tid * P.n_npc,
+                                                reinterpret_cast<int*>(stage_g + OFF_NDEPTH) + tid * P.n_npc}
+                                      : NpcView{nullptr, nullptr, nullptr};
+            const NpcView* nv = NPC ? &slots : nullptr;
             if (status == ORX_RESULT_IN_PROGRESS) {          // finished lanes are frozen until reset
                 Stream rs = make_stream(P, lane, ep);
                 const uint4 blk = draw_block(rs, DOM_TICK, SUB_MAIN, (uint32_t)tick);
@@ -412,11 +439,11 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                     if ((bots >> 8) != ORX_BOT_NONE) mv = (mv & 0x00FFu) | (bot_move(bots >> 8, L.pos >> 16, L.st >> 16, blk.y) << 8);
                 }
                 Counters cnt{};
-                res = tick_lane<DGEN, false, EV>(P, tiles, lut, L, mv, blk.z, rs, lane, ev, cnt);
+                res = tick_lane<DGEN, NPC, EV>(P, tiles, lut, L, mv, blk.z, rs, nv, ev, cnt);
                 int new_status = res;
                 if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
                     rs.episode += 1;
-                    reset_lane<DGEN, false>(P, L, rs, lane);
+                    reset_lane<DGEN, NPC>(P, L, rs, nv);
                     new_status = ORX_RESULT_IN_PROGRESS;
                 }
                 sts_u32(b4 + OFF_POS, L.pos);
@@ -446,10 +473,10 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     if (tid == 0) ORX_TRACE(trace_slot, 6);
 }
 
-template <bool OBS, bool EV = false>
+template <bool OBS, bool EV = false, bool NPC = false>
 constexpr size_t pipe_smem_bytes(int fixed_tiles)
 {
-    return (size_t)kPipeStages<OBS, EV> * kPipeStageBytes<OBS, EV> + 2 * kPipeStages<OBS, EV> * 8 + kTileIdxBytes + (size_t)fixed_tiles;
+    return (size_t)kPipeStages<OBS, EV, NPC> * kPipeStageBytes<OBS, EV, NPC> + 2 * kPipeStages<OBS, EV, NPC> * 8 + kTileIdxBytes + (size_t)fixed_tiles;
 }
 
 }  // namespace orx

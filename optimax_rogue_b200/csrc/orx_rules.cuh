@@ -118,12 +118,24 @@ __device__ __forceinline__ void kth_ground(const Params& P, int sx, int sy, int 
     }
 }
 
-__device__ __forceinline__ int npc_at(const Params& P, unsigned int lane, int depth, int x, int y)
+// The NPC slots of ONE game: pointers to its slot 0 in the three slot planes (in HBM for the simple kernels,
+// in the shared-memory stage for the pipelined one). Unused (NULL) when the configuration has no NPC slots.
+struct NpcView {
+    uint8_t* pos;     // [n_npc][2]
+    int16_t* hp;      // [n_npc]
+    int* depth;       // [n_npc], -1 = empty slot
+};
+
+__device__ __forceinline__ NpcView npc_view(const Params& P, unsigned int lane)
 {
-    for (int k = 0; k < P.n_npc; ++k) {
-        const size_t j = (size_t)lane * P.n_npc + k;
-        if (P.npc_depth[j] == depth && P.npc_pos[2 * j] == x && P.npc_pos[2 * j + 1] == y) return k;
-    }
+    const size_t j = (size_t)lane * P.n_npc;
+    return NpcView{P.npc_pos + 2 * j, P.npc_hp + j, P.npc_depth + j};
+}
+
+__device__ __forceinline__ int npc_at(const Params& P, const NpcView* nv, int depth, int x, int y)
+{
+    for (int k = 0; k < P.n_npc; ++k)
+        if (nv->depth[k] == depth && nv->pos[2 * k] == x && nv->pos[2 * k + 1] == y) return k;
     return -1;
 }
 
@@ -141,7 +153,7 @@ __device__ __forceinline__ bool level_exists(const Params& P, int pid, int depth
 // (updater.py:282-285). Returns sx | sy<<8 | x<<16 | y<<24  (= new st half | new pos half << 16).
 template <int DGEN, bool NPC>
 __device__ __noinline__ uint32_t descend_draw(const Params& P, Stream s, int tick, int pid, int new_depth,
-                                              uint32_t oxy, int odepth, unsigned int lane)
+                                              uint32_t oxy, int odepth, const NpcView* nv)
 {
     int sx, sy, x, y;
     level_stairs<DGEN>(P, s, new_depth, sx, sy);
@@ -152,7 +164,7 @@ __device__ __noinline__ uint32_t descend_draw(const Params& P, Stream s, int tic
         const int k = (int)seq_bounded(s, DOM_TICK, SUB_DESCEND + 64u * (uint32_t)pid, (uint32_t)tick, q++, (uint32_t)ng);
         kth_ground<DGEN>(P, sx, sy, k, x, y);
         taken = (odepth == new_depth) & (oxy == ((uint32_t)x | ((uint32_t)y << 8)));
-        if (NPC) taken = taken || npc_at(P, lane, new_depth, x, y) >= 0;
+        if (NPC) taken = taken || npc_at(P, nv, new_depth, x, y) >= 0;
     } while (taken);
     return (uint32_t)sx | ((uint32_t)sy << 8) | ((uint32_t)x << 16) | ((uint32_t)y << 24);
 }
@@ -230,7 +242,7 @@ __device__ __forceinline__ bool is_stairs(const Params& P, const uint8_t* tiles,
 // block. Returns the UpdateResult.
 template <int DGEN, bool NPC, bool EV>
 __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, const CmdEntry* lut, Lane& L, uint32_t mv,
-                                         uint32_t w_init, const Stream& s, unsigned int lane,
+                                         uint32_t w_init, const Stream& s, const NpcView* nv,
                                          EvSink<EV>& ev, Counters& cnt)
 {
     const int dl1 = clamped_delta<DGEN>(P, tiles, lut, mv & 255u, L.pos & 0xFFFFu);
@@ -262,13 +274,13 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
             const int dmgA = p2_first ? P.dmg1 : P.dmg0;
             if (dmgA > 0) { if (p2_first) hp1 -= dmgA; else hp2 -= dmgA; ++cnt.hits; }      // the victim is B
             ev.emit(ORX_EV_COMBAT, idA + 1, idB + 1, dB == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_FLEE, dmgA);
-        } else if (NPC && (npc = npc_at(P, lane, depA(), tA & 255u, tA >> 8)) >= 0) {
+        } else if (NPC && (npc = npc_at(P, nv, depA(), tA & 255u, tA >> 8)) >= 0) {
             const int dmgA = p2_first ? P.dmg1 : P.dmg0;
-            if (dmgA > 0) { P.npc_hp[(size_t)lane * P.n_npc + npc] -= (int16_t)dmgA; ++cnt.hits; }
+            if (dmgA > 0) { nv->hp[npc] -= (int16_t)dmgA; ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idA + 1, 3 + npc, ORX_FLAG_BLOCK, dmgA);
         } else if (is_stairs<DGEN>(P, tiles, tA, st & 0xFFFFu)) {
             const int nd = depA() + 1;
-            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idA, nd, pos >> 16, depB(), lane);
+            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idA, nd, pos >> 16, depB(), nv);
             if (!level_exists(P, idA, nd, depB())) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
             ev.emit(ORX_EV_DESCEND, idA + 1, (r >> 16) & 255u, r >> 24, nd);
             if (p2_first) d2 = nd; else d1 = nd;
@@ -289,13 +301,13 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
             const int dmgB = p2_first ? P.dmg0 : P.dmg1;
             if (dmgB > 0) { if (p2_first) hp2 -= dmgB; else hp1 -= dmgB; ++cnt.hits; }      // the victim is A
             ev.emit(ORX_EV_COMBAT, idB + 1, idA + 1, dA == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_AMBUSH, dmgB);
-        } else if (NPC && (npc = npc_at(P, lane, depB(), tB & 255u, tB >> 8)) >= 0) {
+        } else if (NPC && (npc = npc_at(P, nv, depB(), tB & 255u, tB >> 8)) >= 0) {
             const int dmgB = p2_first ? P.dmg0 : P.dmg1;
-            if (dmgB > 0) { P.npc_hp[(size_t)lane * P.n_npc + npc] -= (int16_t)dmgB; ++cnt.hits; }
+            if (dmgB > 0) { nv->hp[npc] -= (int16_t)dmgB; ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idB + 1, 3 + npc, ORX_FLAG_BLOCK, dmgB);
         } else if (is_stairs<DGEN>(P, tiles, tB, st >> 16)) {
             const int nd = depB() + 1;
-            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idB, nd, pos & 0xFFFFu, depA(), lane);
+            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idB, nd, pos & 0xFFFFu, depA(), nv);
             if (!level_exists(P, idB, nd, depA())) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
             ev.emit(ORX_EV_DESCEND, idB + 1, (r >> 16) & 255u, r >> 24, nd);
             if (p2_first) d1 = nd; else d2 = nd;
@@ -314,10 +326,9 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
     L.hp1 = hp1; L.hp2 = hp2;
     if (NPC) {   // dead NPCs leave in reverse entity order (updater.py:137-145)
         for (int k = P.n_npc - 1; k >= 0; --k) {
-            const size_t j = (size_t)lane * P.n_npc + k;
-            if (P.npc_depth[j] >= 0 && P.npc_hp[j] <= 0) {
+            if (nv->depth[k] >= 0 && nv->hp[k] <= 0) {
                 ev.emit(ORX_EV_DEATH, 3 + k, 0, 0, 0);
-                P.npc_depth[j] = -1;
+                nv->depth[k] = -1;
             }
         }
     }
@@ -331,7 +342,7 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
 
 // Re-initialise a lane for the episode already stored in s.episode.
 template <int DGEN, bool NPC>
-__device__ __forceinline__ void reset_lane(const Params& P, Lane& L, const Stream& s, unsigned int lane)
+__device__ __forceinline__ void reset_lane(const Params& P, Lane& L, const Stream& s, const NpcView* nv)
 {
     const uint2 r = reset_draw<DGEN>(P, s);
     L.pos = r.x; L.st = r.y;
@@ -340,7 +351,7 @@ __device__ __forceinline__ void reset_lane(const Params& P, Lane& L, const Strea
     L.d2 = P.start_kind == ORX_START_SEPARATED ? P.sd1 : P.sd0;
     L.tick = 1;                                                          // worldgen.py:87
     L.episode = s.episode;
-    if (NPC) for (int k = 0; k < P.n_npc; ++k) P.npc_depth[(size_t)lane * P.n_npc + k] = -1;
+    if (NPC) for (int k = 0; k < P.n_npc; ++k) nv->depth[k] = -1;
 }
 
 __device__ __forceinline__ void unpack_lane(Lane& L, uint32_t pos, uint32_t hp, int2 d, uint32_t st, int tick, uint32_t ep)

@@ -809,3 +809,42 @@ def test_device_stepper_equals_update():
         assert torch.equal(ra, rb), t
     for name in BatchedGameState.PLANES:
         assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n_npc', [1, 3, 8])
+def test_npc_slots_through_the_tile_pipeline(n_npc):
+    """With NPC slots the slot planes travel through the tile pipeline as three more slices per tile;
+    ORX_NO_NPC_PIPE=1 forces the one-thread-per-game kernel. Both equal the oracle: planes, NPC planes,
+    results; players bump into NPCs, kill them, and descend next to them."""
+    import os
+    import torch
+    n = 256 * 6 + 40
+    cfg = SimConfig(max_ticks=0, seed=19, width=9, height=6, damage=(3, 2), n_npc=n_npc)
+    a, upd, orc = gu.make_pair(cfg, n)
+    rng = np.random.default_rng(4)
+    live = rng.random((n, n_npc)) < 0.7               # scatter NPCs over the first two levels
+    orc.state.npc_depth[:] = np.where(live, rng.integers(0, 2, size=(n, n_npc)), -1)
+    orc.state.npc_pos[:, :, 0] = rng.integers(1, 8, size=(n, n_npc))
+    orc.state.npc_pos[:, :, 1] = rng.integers(1, 5, size=(n, n_npc))
+    orc.state.npc_hp[:] = rng.integers(1, 7, size=(n, n_npc))
+    a.npc_depth.copy_(torch.from_numpy(orc.state.npc_depth))
+    a.npc_pos.copy_(torch.from_numpy(orc.state.npc_pos))
+    a.npc_hp.copy_(torch.from_numpy(orc.state.npc_hp))
+    culled0 = int((a.npc_depth < 0).sum())
+    b = a.clone()
+    upd_b = type(upd)(upd.dgen, upd.despawn_strat, upd.max_ticks, auto_reset=False)
+    for t in range(70):
+        mv = orc.bot_moves(1, 2) if t % 2 else rng.integers(1, 6, size=(n, 2), dtype=np.uint8)
+        m = torch.from_numpy(mv).cuda()
+        ra, _ = upd.update(a, m)
+        os.environ['ORX_NO_NPC_PIPE'] = '1'
+        try:
+            rb, _ = upd_b.update(b, m)
+        finally:
+            del os.environ['ORX_NO_NPC_PIPE']
+        ro, _ = orc.step(mv, want_events=False)
+        assert torch.equal(ra, rb) and np.array_equal(ra.cpu().numpy(), ro), t
+        gu.assert_state_equal(a, orc, f'tick {t} (pipeline)')
+    gu.assert_state_equal(b, orc, 'simple kernel')
+    assert int((a.npc_depth < 0).sum()) > culled0      # some NPCs were killed and culled (updater.py:137-145)

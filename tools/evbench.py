@@ -44,6 +44,6 @@ def run(n_npc, events, track=True, steps=60, reps=5):
     return best * 1e3
 
 
-for n_npc, ev, track in ((0, False, False), (0, True, False), (0, True, True), (2, False, False), (2, True, False)):
+for n_npc, ev, track in ((0, False, False), (0, True, False), (0, True, True), (2, False, False), (8, False, False), (2, True, False)):
     us = run(n_npc, ev, track)
     print(f'G={G} npc={n_npc} events={ev} track_order={track}: {us:.1f} us/step (CUDA graph), {G / us * 1e6:.3e} ticks/s', flush=True)
