@@ -1,5 +1,5 @@
-// Persistent, TMA-fed version of the tick kernel (the hot variants: no NPC slots; plain, with the
-// observations, or with the event log).
+// Persistent, TMA-fed version of the tick kernel (plain, with the observations, with the event log, with
+// scripted players, or with NPC slots).
 //
 // Every CTA works through 256-game tiles: its first kStages tiles are fixed (blockIdx.x + i * grid),
 // the rest are claimed from a per-state counter (OrxState.sched) as stages free up, so that CTAs

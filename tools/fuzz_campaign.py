@@ -43,6 +43,11 @@ while time.time() - t0 < budget:
         if rng.integers(0, 2):
             t[tuple(g[len(g) // 2])] = 3
         kw.update(dgen_kind=_abi.DGEN_FIXED, fixed_tiles=t)
+    n_npc = int(rng.integers(1, 9)) if rng.integers(0, 4) == 0 else 0
+    if n_npc and (w - 2) * (h - 2) - 1 >= 2 + n_npc:
+        kw.update(n_npc=n_npc)
+    else:
+        n_npc = 0
     cfg = SimConfig(**kw)
     size_class = int(rng.integers(0, 4))
     n = int(rng.integers(1, 700)) if size_class == 0 else int(rng.integers(700, 40000)) if size_class < 3 else int(rng.integers(40000, 300000))
@@ -50,15 +55,28 @@ while time.time() - t0 < budget:
     bots = (int(rng.integers(1, 3)), int(rng.integers(1, 3)))
     events = bool(rng.integers(0, 2))
     base = int(rng.integers(0, 2**53))
+    setup = None
+    if n_npc:
+        srng = np.random.default_rng(int(rng.integers(0, 2**31)))
+
+        def setup(gs, orc, srng=srng, n_npc=n_npc, w=w, h=h):      # static NPCs on the first levels (updater.py:116-128)
+            live = srng.random((orc.n, n_npc)) < 0.6
+            orc.state.npc_depth[:] = np.where(live, srng.integers(0, 3, size=(orc.n, n_npc)), -1)
+            orc.state.npc_pos[:, :, 0] = srng.integers(1, w - 1, size=(orc.n, n_npc))
+            orc.state.npc_pos[:, :, 1] = srng.integers(1, h - 1, size=(orc.n, n_npc))
+            orc.state.npc_hp[:] = srng.integers(1, 6, size=(orc.n, n_npc))
+            gs.npc_depth.copy_(torch.from_numpy(orc.state.npc_depth))
+            gs.npc_pos.copy_(torch.from_numpy(orc.state.npc_pos))
+            gs.npc_hp.copy_(torch.from_numpy(orc.state.npc_hp))
     if rng.integers(0, 2):
-        gu.run_parity(cfg, n, n_ticks, bots=bots, events=events, game_id_base=base)
+        gu.run_parity(cfg, n, n_ticks, bots=bots, events=events, game_id_base=base, setup=setup)
         kind = 'bots'
     else:
         mrng = np.random.default_rng(int(rng.integers(0, 2**31)))
-        gu.run_parity(cfg, n, n_ticks, events=events, game_id_base=base,
+        gu.run_parity(cfg, n, n_ticks, events=events, game_id_base=base, setup=setup,
                       moves_fn=lambda t, orc: mrng.integers(0, 8, size=(orc.n, 2), dtype=np.uint8))
         kind = 'random bytes'
-    key = (kind, 'fixed map' if fixed else 'empty rooms', 'events' if events else 'no events')
+    key = (kind, 'fixed map' if fixed else 'empty rooms', 'events' if events else 'no events', 'NPC slots' if n_npc else 'players only')
     kinds[key] = kinds.get(key, 0) + 1
     runs += 1
     games += n
