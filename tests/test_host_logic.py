@@ -161,3 +161,38 @@ def test_pack_moves_roundtrip():
     t = torch.from_numpy(mv)
     tp = pack_moves(t[:, 0], t[:, 1])
     assert tp.dtype == torch.uint8 and np.array_equal(tp.numpy(), packed)
+
+
+def test_word_planes_share_one_allocation_at_a_common_pitch():
+    """include/orx.h, layout hint of OrxState: pos, hp, stairs, tick, episode are carved out of one
+    allocation, in that order, at a pitch that is a multiple of 128 bytes and >= 4 n, each one an ordinary
+    contiguous tensor; clone() keeps the layout, state_dict() round-trips through torch.save."""
+    import io
+    import torch
+    from optimax_rogue_b200 import SimConfig
+    from optimax_rogue_b200.game.state import BatchedGameState
+    for n in (1, 255, 1000, 4096):
+        gs = BatchedGameState(SimConfig(), n, 'cpu')
+        for other in (gs, gs.clone()):
+            base = other.pos.data_ptr()
+            pitch = other.hp.data_ptr() - base
+            assert pitch % 128 == 0 and pitch >= 4 * n
+            assert [getattr(other, k).data_ptr() - base for k in ('pos', 'hp', 'stairs', 'tick', 'episode')] == [k * pitch for k in range(5)]
+            assert all(getattr(other, k).is_contiguous() for k in ('pos', 'hp', 'stairs', 'tick', 'episode'))
+            assert (other.pos.shape, other.hp.shape, other.stairs.shape, other.tick.shape, other.episode.shape) == \
+                ((n, 4), (n, 2), (n, 4), (n,), (n,))
+            assert (other.pos.dtype, other.hp.dtype, other.tick.dtype) == (torch.uint8, torch.int16, torch.int32)
+        gs.pos[:] = 7
+        gs.hp[:, 1] = -3
+        gs.tick[:] = 11
+        assert int(gs.stairs.sum()) == 0 and int(gs.episode.sum()) == 0 and int(gs.hp[:, 0].sum()) == 0      # no overlap
+        c = gs.clone()
+        c.tick[:] = 5
+        assert int(gs.tick[0]) == 11                                                                       # clone owns its planes
+        buf = io.BytesIO()
+        torch.save(gs.state_dict(), buf)
+        buf.seek(0)
+        back = BatchedGameState(SimConfig(), n, 'cpu')
+        back.load_state_dict(torch.load(buf))
+        for name in BatchedGameState.PLANES:
+            assert torch.equal(getattr(back, name), getattr(gs, name)), name
