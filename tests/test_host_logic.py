@@ -196,3 +196,16 @@ def test_word_planes_share_one_allocation_at_a_common_pitch():
         back.load_state_dict(torch.load(buf))
         for name in BatchedGameState.PLANES:
             assert torch.equal(getattr(back, name), getattr(gs, name)), name
+
+
+def test_tools_and_examples_compile():
+    """The tuning / evidence scripts under tools/ and examples/ only run on a GPU box; keep them importable."""
+    import glob
+    import os
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, 'tools', '*.py')) + glob.glob(os.path.join(root, 'examples', '*.py')) + \
+        [os.path.join(root, 'bench.py'), os.path.join(root, '__graft_entry__.py')]
+    assert len(files) >= 10
+    for f in files:
+        py_compile.compile(f, doraise=True, cfile=os.devnull)
