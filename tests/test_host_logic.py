@@ -202,10 +202,10 @@ def test_tools_and_examples_compile():
     """The tuning / evidence scripts under tools/ and examples/ only run on a GPU box; keep them importable."""
     import glob
     import os
-    import py_compile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     files = glob.glob(os.path.join(root, 'tools', '*.py')) + glob.glob(os.path.join(root, 'examples', '*.py')) + \
         [os.path.join(root, 'bench.py'), os.path.join(root, '__graft_entry__.py')]
     assert len(files) >= 10
     for f in files:
-        py_compile.compile(f, doraise=True, cfile=os.devnull)
+        with open(f) as fh:
+            compile(fh.read(), f, 'exec')
