@@ -3,7 +3,7 @@ plain-C oracle on every plane, result and event record, every tick. Larger and l
 tests/test_properties.py (batches of up to a few hundred thousand games, so the multi-tile, dynamically scheduled,
 tensor-map and event-pipeline paths are all exercised). The oracle is test infrastructure; this is a test tool.
 
-  python tools/fuzz_campaign.py [seconds] [seed]
+  python tests/fuzz_campaign.py [seconds] [seed]      (lives under tests/: it calls the oracle, which only tests may do)
 """
 import os
 import sys
