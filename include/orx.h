@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define ORX_ABI_VERSION 2
+#define ORX_ABI_VERSION 3
 
 /* logic/moves.py:6-12 */
 enum { ORX_MOVE_UP = 1, ORX_MOVE_RIGHT = 2, ORX_MOVE_DOWN = 3, ORX_MOVE_LEFT = 4, ORX_MOVE_STAY = 5 };
@@ -97,8 +97,20 @@ typedef struct OrxConfig {
     const uint16_t* fixed_ground; /* flat indices of the Ground tiles in ascending (x-major) order */
     int32_t fixed_n_ground;
     int32_t fixed_stairs[2];      /* first StaircaseDown in x-major order, or ORX_NO_STAIRS */
-    int32_t reserved;
+    uint32_t path_flags;          /* ORX_PATH_* bits, 0 = the default (fastest) kernels. Results never depend on them;
+                                     they exist so that tests and A/B measurements can pin a code path without
+                                     process-wide switches (the library reads no environment variables). */
 } OrxConfig;
+
+/* OrxConfig.path_flags. NO_TILE_FLAGS and STATIC_TILES choose how launches on ONE state are ordered; keep them
+ * constant for a state between two operations that serialise the stream (orx_reset, any non-step kernel). */
+#define ORX_PATH_NO_TENSOR_MAP 1u   /* move the five 4-byte planes as five 1-D bulk copies */
+#define ORX_PATH_NO_NPC_PIPE 2u     /* NPC slots: one-thread-per-game kernel instead of the tile pipeline */
+#define ORX_PATH_STATIC_TILES 4u    /* grid-wait mode: static tile striding instead of the dynamic counter */
+#define ORX_PATH_NO_EVENT_PIPE 8u   /* event log: one-thread-per-game kernel */
+#define ORX_PATH_HOST_STAGED 16u    /* host buffers: staged cudaMemcpyAsync instead of in-kernel PCIe access */
+#define ORX_PATH_NO_TILE_FLAGS 32u  /* order consecutive launches by a grid-wide dependency, not tile by tile */
+#define ORX_PATH_TILES_PER_CTA_SHIFT 8  /* bits 8..15: tiles per CTA in tile-flag mode (0 = built-in default) */
 
 /* Structure-of-arrays game state; game i of the batch is element i of every plane.
  * Layout hint (optional, no effect on results): when the five 4-byte planes are carved out of one
@@ -119,11 +131,20 @@ typedef struct OrxState {
     uint8_t* npc_pos;   /* [n][n_npc][2] */
     int16_t* npc_hp;    /* [n][n_npc]    */
     int32_t* npc_depth; /* [n][n_npc]    -1 = empty slot */
-    /* Tile scheduler scratch of this state: device uint32[4], zero-initialised by the caller, or NULL.
-     * With it the tick kernel hands its 256-game tiles out dynamically (CTAs that run slower take
-     * fewer), and leaves the words zero again when it completes; without it tiles are assigned
-     * statically. Never shared between states that may be ticked concurrently. */
+    /* Scratch of the tick kernel for THIS state: device uint32[sched_words], 16-byte aligned, zero-initialised
+     * by the caller (orx_reset zeroes it again), or NULL. Never shared between states, and tied to the batch
+     * size the state is ticked with. Two uses (csrc/orx_pipe.cuh):
+     *   sched_words >= ORX_SCHED_HEADER_WORDS: word 0 is a tile counter, 256-game tiles are handed out
+     *     dynamically (CTAs that run slower take fewer); zero again when a launch completes.
+     *   sched_words >= orx_sched_words(n): words 4.. hold {tickets, completed passes} per tile, and consecutive
+     *     tick launches on the state are ordered tile by tile instead of grid by grid: tick k+1 starts on a
+     *     tile as soon as tick k has written it, and ticks of different states in one stream overlap freely.
+     *     Stream order towards everything else is kept (a tick completes only after all earlier work has).
+     *     In this mode two consecutive tick calls on DIFFERENT states must not share a result / observation /
+     *     event buffer unless something else in the stream consumes it in between. */
     uint32_t* sched;
+    uint32_t sched_words;
+    uint32_t reserved;
 } OrxState;
 
 /* One replication-log record (logic/updates.py); slots of game i at events[i*max_events + k],
@@ -145,6 +166,10 @@ enum {
 
 int orx_abi_version(void);
 const char* orx_strerror(int code);
+
+/* Words of OrxState.sched that enable tile-by-tile ordering for a batch of n games. */
+#define ORX_SCHED_HEADER_WORDS 4
+size_t orx_sched_words(int64_t n);
 
 /* Bytes of per-game mutable state (S_rw of the roofline formula) for this config. */
 size_t orx_state_bytes(const OrxConfig* cfg);

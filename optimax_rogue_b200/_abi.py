@@ -4,7 +4,7 @@ Kept free of torch so that the CPU test-suite can check the ABI without a GPU.
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MAX_NPC = 8
 MAX_EVENTS_BASE = 4
@@ -20,6 +20,17 @@ BOT_NONE, BOT_RANDOM, BOT_STAIRCASE = 0, 1, 2
 EV_NONE, EV_MOVE, EV_COMBAT, EV_DUNGEON, EV_DEATH, EV_DESCEND = 0, 1, 2, 3, 4, 5
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA_BASE = 0, -1, -2, -100
+
+# OrxConfig.path_flags (include/orx.h)
+PATH_NO_TENSOR_MAP, PATH_NO_NPC_PIPE, PATH_STATIC_TILES, PATH_NO_EVENT_PIPE, PATH_HOST_STAGED, PATH_NO_TILE_FLAGS = 1, 2, 4, 8, 16, 32
+PATH_TILES_PER_CTA_SHIFT = 8
+SCHED_HEADER_WORDS = 4
+TILE = 256
+
+
+def sched_words(n: int) -> int:
+    """orx_sched_words: scratch words that enable tile-by-tile ordering for n games."""
+    return SCHED_HEADER_WORDS + 2 * (max(int(n), 0) // TILE)
 
 
 class OrxConfig(C.Structure):
@@ -41,7 +52,7 @@ class OrxConfig(C.Structure):
         ('fixed_ground', C.c_void_p),
         ('fixed_n_ground', C.c_int32),
         ('fixed_stairs', C.c_int32 * 2),
-        ('reserved', C.c_int32),
+        ('path_flags', C.c_uint32),
     ]
 
 
@@ -50,7 +61,7 @@ class OrxState(C.Structure):
         ('pos', C.c_void_p), ('hp', C.c_void_p), ('depth', C.c_void_p), ('stairs', C.c_void_p),
         ('tick', C.c_void_p), ('episode', C.c_void_p), ('status', C.c_void_p),
         ('npc_pos', C.c_void_p), ('npc_hp', C.c_void_p), ('npc_depth', C.c_void_p),
-        ('sched', C.c_void_p),
+        ('sched', C.c_void_p), ('sched_words', C.c_uint32), ('reserved', C.c_uint32),
     ]
 
 
@@ -83,6 +94,7 @@ class OrxR1State(C.Structure):
 PROTOTYPES = {
     'orx_abi_version': (C.c_int, []),
     'orx_strerror': (C.c_char_p, [C.c_int]),
+    'orx_sched_words': (C.c_size_t, [C.c_int64]),
     'orx_state_bytes': (C.c_size_t, [C.POINTER(OrxConfig)]),
     'orx_max_events': (C.c_int, [C.POINTER(OrxConfig)]),
     'orx_event_count_add': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -25,6 +25,7 @@ class SimConfig:
     n_npc: int = 0
     seed: int = 0
     fixed_tiles: typing.Optional[np.ndarray] = None   # uint8[W,H] Tile codes (DGEN_FIXED)
+    path_flags: int = 0                 # _abi.PATH_* bits: pins a kernel path for tests / A-B runs, never changes results
 
     def validate(self):
         if not (4 <= self.width <= _abi.MAX_DIM and 4 <= self.height <= _abi.MAX_DIM):
@@ -75,4 +76,5 @@ class SimConfig:
         c.fixed_ground = ground_ptr or None
         c.fixed_n_ground = n_ground
         c.fixed_stairs[0], c.fixed_stairs[1] = stairs
+        c.path_flags = int(self.path_flags)
         return c

@@ -310,6 +310,11 @@ int check_common(const OrxConfig* cfg, const OrxState* st, int64_t n)
     if (cfg->despawn_strat != ORX_DESPAWN_UNREACHABLE && cfg->despawn_strat != ORX_DESPAWN_UNUSED) return ORX_ERR_BAD_ARG;
     if (cfg->start_kind == ORX_START_SEPARATED && cfg->start_depth[0] == cfg->start_depth[1]) return ORX_ERR_BAD_ARG;
     if (cfg->max_ticks < 0) return ORX_ERR_BAD_ARG;
+    for (int k = 0; k < 2; ++k) {   // health lives in int16 planes; a hit is subtracted from them
+        if (cfg->hp[k] < 1 || cfg->hp[k] > 32767) return ORX_ERR_BAD_ARG;
+        const int64_t hit = (int64_t)cfg->damage[k] - (int64_t)cfg->armor[k];
+        if (hit < -32767 || hit > 32767) return ORX_ERR_BAD_ARG;
+    }
     if (cfg->dgen_kind == ORX_DGEN_FIXED) {
         if (cfg->fixed_tiles == nullptr || cfg->fixed_ground == nullptr) return ORX_ERR_BAD_ARG;
         if (cfg->fixed_n_ground < 2 + cfg->n_npc) return ORX_ERR_BAD_ARG;
@@ -403,59 +408,141 @@ TensorMapEncodeFn tensor_map_encoder()
 
 // The planes pos, hp, stairs, tick, episode as one u32[5][games] array, if the caller laid them out that way
 // (one allocation, common pitch, see orx.h); false: the kernel moves each plane slice on its own.
+// Encoding a descriptor costs the host a driver call, so the last few (base, pitch, games) are kept: a state is
+// ticked over and over with the same planes.
 bool planes5_map(const Params& P, unsigned int n_tiles, CUtensorMap* map)
 {
-    memset(map, 0, sizeof(*map));
-    if (getenv("ORX_NO_TENSOR_MAP") != nullptr) return false;
     const char* p0 = reinterpret_cast<const char*>(P.pos);
     const ptrdiff_t pitch = reinterpret_cast<const char*>(P.hp) - p0;
     const int64_t games = (int64_t)n_tiles * kTile;
     if (pitch < games * 4 || (pitch & 15) != 0 || !aligned(p0, 16)) return false;
     if (reinterpret_cast<const char*>(P.stairs) - p0 != 2 * pitch || reinterpret_cast<const char*>(P.tick) - p0 != 3 * pitch ||
         reinterpret_cast<const char*>(P.episode) - p0 != 4 * pitch) return false;
+    struct Entry { const char* base; ptrdiff_t pitch; int64_t games; int dev; CUtensorMap map; };
+    constexpr int kEntries = 64;
+    static std::mutex mu;
+    static Entry cache[kEntries];
+    static unsigned int used = 0, next = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (unsigned int k = 0; k < used; ++k)
+            if (cache[k].base == p0 && cache[k].pitch == pitch && cache[k].games == games && cache[k].dev == dev) { *map = cache[k].map; return true; }
+    }
     const TensorMapEncodeFn encode = tensor_map_encoder();
     if (encode == nullptr) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)games, 5};
     const cuuint64_t strides[1] = {(cuuint64_t)pitch};
     const cuuint32_t box[2] = {(cuuint32_t)kTile, 5}, estr[2] = {1, 1};
-    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<char*>(p0), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<char*>(p0), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    Entry& e = cache[next];
+    e.base = p0; e.pitch = pitch; e.games = games; e.dev = dev; e.map = *map;
+    next = (next + 1) % kEntries;
+    if (used < kEntries) ++used;
+    return true;
 }
 
+// How the tiles of one launch are handed out and how consecutive launches on a state are ordered (orx_pipe.cuh).
+struct TileCtl {
+    unsigned int* counter;   // grid-wait mode: dynamic tile counter (sched[0]) or NULL = static stride
+    unsigned int* flags;     // flag mode: {next, serving} per tile (sched + ORX_SCHED_HEADER_WORDS) or NULL
+    int tiles_per_cta;       // flag mode: target number of tiles per CTA (smaller grids let consecutive launches share the SMs)
+    int no_tensor_map;
+};
+
+int device_sms(int dev)
+{
+    static std::mutex mu;
+    static int sms[64] = {0};
+    std::lock_guard<std::mutex> lk(mu);
+    int& v = sms[dev & 63];
+    if (v == 0 && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); v = 148; }
+    return v;
+}
+
+// Flag mode is a property of the STATE (its scratch size and its number of tiles), never of the kernel variant:
+// every pipelined launch on a state must make the same choice, because a flag-mode launch does not wait for an
+// earlier grid-wait-mode launch on the same planes.
+TileCtl tile_ctl(const OrxConfig* cfg, const OrxState* st, unsigned int n_tiles)
+{
+    TileCtl c{nullptr, nullptr, 0, (cfg->path_flags & ORX_PATH_NO_TENSOR_MAP) != 0};
+    if (st->sched == nullptr || !aligned(st->sched, 16)) return c;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t need = (uint64_t)ORX_SCHED_HEADER_WORDS + 2ull * n_tiles;
+    if (!(cfg->path_flags & ORX_PATH_NO_TILE_FLAGS) && st->sched_words >= need &&
+        n_tiles <= (unsigned int)(kMaxTilesPerCtaFlagged * device_sms(dev))) {
+        c.flags = st->sched + ORX_SCHED_HEADER_WORDS;
+        c.tiles_per_cta = (int)((cfg->path_flags >> ORX_PATH_TILES_PER_CTA_SHIFT) & 255u);
+        return c;
+    }
+    if (!(cfg->path_flags & ORX_PATH_STATIC_TILES) && st->sched_words >= ORX_SCHED_HEADER_WORDS) c.counter = st->sched;
+    return c;
+}
+
+#ifndef ORX_PIPE_TILES_PER_CTA
+#define ORX_PIPE_TILES_PER_CTA 4
+#endif
+
 template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, bool NPC = false>
-int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, unsigned int* sched,
+int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, const TileCtl& ctl,
                 int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
 {
     const size_t smem = pipe_smem_bytes<OBS, EV, NPC>((int)tiles_bytes);
     auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK, EV, NPC>;
-    // Launch geometry depends only on (device, kernel, smem): look it up once per process, the
-    // occupancy query costs more than the launch itself. (A cache of device properties, not state;
-    // one per kernel instantiation.) Guarded by a mutex so that host threads driving different GPUs
-    // may call in concurrently.
+    // Launch geometry depends only on (device, kernel, smem): looked up once per process, the occupancy query
+    // costs more than the launch itself. (A cache of device properties, not state; one per kernel instantiation.)
+    // The dynamic shared-memory limit of the kernel is raised ONCE per device to the most any configuration
+    // needs (stages + the largest fixed map), so concurrent host threads with different maps never lower it
+    // under each other. Guarded by a mutex: host threads driving different GPUs may call in concurrently.
+    struct Geom { int dev; size_t smem; int per_sm; };
     static std::mutex cache_mu;
-    static int cache_sms[64] = {0}, cache_per_sm[64] = {0};
-    static size_t cache_smem[64] = {0};
+    static Geom cache[16];
+    static unsigned int cache_used = 0, cache_next = 0;
+    static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    const int slot = dev & 63;
-    std::unique_lock<std::mutex> lk(cache_mu);
-    if (cache_sms[slot] == 0 || cache_smem[slot] != smem || cache_per_sm[slot] == 0) {
-        int sms = 148, per_sm = 2;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (smem > 48 * 1024) {
-            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return cuda_fail(e);
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        if (!attr_set[dev & 63]) {
+            const size_t most = pipe_smem_bytes<OBS, EV, NPC>(kMaxFixedTiles);
+            if (most > 48 * 1024) {
+                const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
+                if (e != cudaSuccess) return cuda_fail(e);
+            }
+            attr_set[dev & 63] = true;
         }
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPipeThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        cache_per_sm[slot] = per_sm; cache_smem[slot] = smem; cache_sms[slot] = sms;
+        for (unsigned int k = 0; k < cache_used; ++k)
+            if (cache[k].dev == dev && cache[k].smem == smem) per_sm = cache[k].per_sm;
+        if (per_sm == 0) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPipeThreads, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+            cache[cache_next] = Geom{dev, smem, per_sm};
+            cache_next = (cache_next + 1) % 16;
+            if (cache_used < 16) ++cache_used;
+        }
     }
-    const int sms = cache_sms[slot], per_sm = cache_per_sm[slot];
-    lk.unlock();
-    unsigned int grid = (unsigned int)sms * (unsigned int)per_sm;       // persistent: every CTA resident
+    const unsigned int sms = (unsigned int)device_sms(dev);
+    unsigned int grid = sms * (unsigned int)per_sm;       // persistent: every CTA resident
     if (grid > n_tiles) grid = n_tiles;
+    if (ctl.flags != nullptr) {
+        // Flag mode: a launch need not fill the machine on its own, the launches before and after it run beside
+        // it. A few tiles per CTA keep every CTA's pipeline busy and leave CTA slots to the neighbours; never
+        // fewer CTAs than SMs, never more than kMaxTilesPerCtaFlagged tiles per CTA (tile_ctl checked n_tiles).
+        const unsigned int tpc = (unsigned int)(ctl.tiles_per_cta > 0 ? ctl.tiles_per_cta : ORX_PIPE_TILES_PER_CTA);
+        unsigned int g = (n_tiles + tpc - 1) / tpc;
+        const unsigned int floor_g = n_tiles < sms ? n_tiles : sms;
+        if (g < floor_g) g = floor_g;
+        if (g < grid) grid = g;
+    }
     alignas(64) CUtensorMap planes5;
-    const int use_map = planes5_map(P, n_tiles, &planes5) ? 1 : 0;
+    int use_map = 0;
+    if (!ctl.no_tensor_map) use_map = planes5_map(P, n_tiles, &planes5) ? 1 : 0;
+    if (!use_map) memset(&planes5, 0, sizeof(planes5));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(kPipeThreads); lc.dynamicSmemBytes = smem; lc.stream = s;
     cudaLaunchAttribute at[1];
@@ -464,16 +551,16 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     lc.attrs = at; lc.numAttrs = ORX_PIPE_PDL ? 1 : 0;
 #ifdef ORX_PIPE_TRACE
     static unsigned int trace_slot = 0;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, events, bots, trace_slot++);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, ctl.counter, ctl.flags, obs, obs_radius, events, bots, trace_slot++);
 #else
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, sched, obs, obs_radius, events, bots);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, ctl.counter, ctl.flags, obs, obs_radius, events, bots);
 #endif
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
 }
 
 template <bool OBS, bool EV = false>
 int launch_tick_pipe(bool empty, int packed, const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t smem,
-                     unsigned int* sched, int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
+                     const TileCtl& sched, int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
 {
     if constexpr (!EV) {
         if (bots != 0 && !packed)
@@ -506,12 +593,12 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
     // Hot variants (plain, with observations, with the event log, or with NPC slots): persistent
     // TMA-pipelined kernel over the full 256-game tiles, the simple kernel for a ragged tail (< 256 games).
     const bool npc_pipe = cfg->n_npc > 0 && ev == nullptr && obs == nullptr && bots == 0 && aligned(st->npc_pos, 16) &&
-                          aligned(st->npc_hp, 16) && aligned(st->npc_depth, 16) && getenv("ORX_NO_NPC_PIPE") == nullptr;
+                          aligned(st->npc_hp, 16) && aligned(st->npc_depth, 16) && !(cfg->path_flags & ORX_PATH_NO_NPC_PIPE);
     if (npc_pipe && n >= kTile && pipe_aligned(st, moves, result)) {
         const unsigned int n_tiles = (unsigned int)(n / kTile);
         const int64_t n_body = (int64_t)n_tiles * kTile;
         const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
-        unsigned int* sched = aligned(st->sched, 4) && getenv("ORX_STATIC_TILES") == nullptr ? st->sched : nullptr;
+        const TileCtl sched = tile_ctl(cfg, st, n_tiles);
         int rc2;
         if (packed) rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES, false, true, false, true>(P, moves, result, n_tiles, 0, sched, nullptr, -1, s)
                                 : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES, false, true, false, true>(P, moves, result, n_tiles, smem, sched, nullptr, -1, s);
@@ -525,12 +612,12 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
         else k_step<ORX_DGEN_FIXED, true, false><<<tgrid, kThreads, smem, s>>>(T, tail, result + n_body, nullptr, max_ev, packed);
         return launch_done();
     }
-    const bool ev_pipe = ev != nullptr && obs == nullptr && bots == 0 && aligned(ev, 16) && getenv("ORX_NO_EVENT_PIPE") == nullptr;
+    const bool ev_pipe = ev != nullptr && obs == nullptr && bots == 0 && aligned(ev, 16) && !(cfg->path_flags & ORX_PATH_NO_EVENT_PIPE);
     if ((ev == nullptr || ev_pipe) && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
         const unsigned int n_tiles = (unsigned int)(n / kTile);
         const int64_t n_body = (int64_t)n_tiles * kTile;
         const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
-        unsigned int* sched = aligned(st->sched, 4) && getenv("ORX_STATIC_TILES") == nullptr ? st->sched : nullptr;
+        const TileCtl sched = tile_ctl(cfg, st, n_tiles);
         const int rc2 = obs != nullptr ? launch_tick_pipe<true>(empty, packed, P, moves, result, n_tiles, smem, sched, obs, obs_radius, s, nullptr, bots)
                         : ev_pipe      ? launch_tick_pipe<false, true>(empty, packed, P, moves, result, n_tiles, smem, sched, nullptr, -1, s, ev)
                                        : launch_tick_pipe<false>(empty, packed, P, moves, result, n_tiles, smem, sched, nullptr, -1, s, nullptr, bots);
@@ -570,7 +657,7 @@ int step_host_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* move
     // stream back the same way, so there is no separate copy launch and the transfer overlaps the
     // compute tile by tile. Pageable buffers fall back to staged cudaMemcpyAsync copies.
     void *mv_map = nullptr, *res_map = nullptr;
-    if (getenv("ORX_HOST_STAGED") == nullptr && host_mapped(moves_host, &mv_map) && host_mapped(result_host, &res_map))
+    if (!(cfg->path_flags & ORX_PATH_HOST_STAGED) && host_mapped(moves_host, &mv_map) && host_mapped(result_host, &res_map))
         return step_impl(cfg, st, static_cast<const uint8_t*>(mv_map), static_cast<uint8_t*>(res_map), nullptr, n,
                          game_id_base, cuda_stream, packed);
     if (moves_dev == nullptr || result_dev == nullptr) return ORX_ERR_BAD_ARG;
@@ -604,6 +691,11 @@ const char* orx_strerror(int code)
     if (code == ORX_ERR_UNSUPPORTED) return "unsupported configuration";
     if (code <= ORX_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(ORX_ERR_CUDA_BASE - code));
     return "unknown error";
+}
+
+size_t orx_sched_words(int64_t n)
+{
+    return (size_t)ORX_SCHED_HEADER_WORDS + 2 * (size_t)((n > 0 ? n : 0) / kTile);
 }
 
 size_t orx_state_bytes(const OrxConfig* cfg)
@@ -640,8 +732,8 @@ int orx_reset(const OrxConfig* cfg, const OrxState* st, const uint8_t* mask, int
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     const int grid = grid_for(n);
     // The scheduler words are zero between launches; a reset re-establishes that after an aborted run.
-    if (st->sched != nullptr && aligned(st->sched, 4)) {
-        const cudaError_t e = cudaMemsetAsync(st->sched, 0, 4 * sizeof(unsigned int), s);
+    if (st->sched != nullptr && aligned(st->sched, 4) && st->sched_words > 0) {
+        const cudaError_t e = cudaMemsetAsync(st->sched, 0, (size_t)st->sched_words * sizeof(unsigned int), s);
         if (e != cudaSuccess) return cuda_fail(e);
     }
     return dispatch_dgen_npc(cfg, [&]<int DGEN, bool NPC>() {
@@ -762,7 +854,7 @@ int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stai
     if (n >= kTile && pipe_aligned(st, obs, obs)) {
         const unsigned int n_tiles = (unsigned int)(n / kTile);
         const int64_t n_body = (int64_t)n_tiles * kTile;
-        unsigned int* sched = aligned(st->sched, 4) && getenv("ORX_STATIC_TILES") == nullptr ? st->sched : nullptr;
+        const TileCtl sched = tile_ctl(cfg, st, n_tiles);
         const int rc2 = launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES, true, false>(P, nullptr, nullptr, n_tiles, 0, sched, obs, stairs_radius, s);
         if (rc2 != ORX_OK || n_body == n) return rc2;
         const Params T = offset_params(P, n_body, n - n_body);

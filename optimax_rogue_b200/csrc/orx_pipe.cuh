@@ -23,8 +23,18 @@
 //             one iteration after its stores were committed (wait_group.read 1), so the producer never
 //             sits out the read-out of the stage it has just handed to the store engine
 //
-// Between launches: PDL lets the next grid's CTAs become resident while this grid drains; until
-// griddepcontrol.wait releases them they prefetch their first two tiles into L2.
+// Between launches (two modes, chosen by the host per state, see launch_pipe):
+//   grid-wait mode  PDL lets the next grid's CTAs become resident while this grid drains; until
+//                   griddepcontrol.wait releases them they prefetch their first two tiles into L2.
+//   flag mode       (flags != NULL) consecutive launches overlap tile by tile. Every 256-game tile of a state
+//                   has two words in OrxState.sched: next (tickets handed out) and serving (passes completed).
+//                   A CTA takes the tickets of ALL its tiles (static stride) before it lets dependents launch,
+//                   so tickets are in launch order; it loads tile t only once serving[t] equals its ticket and
+//                   sets serving[t] = ticket + 1 once its bulk stores of t have COMPLETED. There is no grid-wide
+//                   wait before the first load: step k+1 starts on tile t as soon as step k has written tile t,
+//                   and launches on different states do not wait for each other at all. The producer runs
+//                   griddepcontrol.wait last, before it exits, so that "this grid is complete" still implies
+//                   "every earlier grid in the stream is complete" for whatever the caller enqueues next.
 #pragma once
 #include <cuda.h>             // CUtensorMap (type only; the encoder is looked up at run time)
 #include <cuda_runtime.h>
@@ -56,6 +66,7 @@ constexpr int kTile = ORX_PIPE_TILE;  // games per tile = compute threads per CT
 constexpr int kStages = ORX_PIPE_STAGES;
 constexpr int kPipeThreads = kTile + 32;   // + one producer warp
 constexpr uint32_t kTileIdxBytes = ((uint32_t)kStages * 4u + 15u) & ~15u;   // per-stage tile index words
+constexpr uint32_t kTicketBytes = 4u * 32u;                                   // flag mode: tickets of up to 32 tiles per CTA
 #ifndef ORX_PIPE_OBS_STAGES
 #define ORX_PIPE_OBS_STAGES 3
 #endif
@@ -166,6 +177,16 @@ __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("s
 __device__ __forceinline__ void sts_s32x2(uint32_t a, int x, int y) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// flag mode: per-tile hand-over between consecutive launches on one state
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+#ifndef ORX_PIPE_FLAG_LAG
+#define ORX_PIPE_FLAG_LAG 2          // a tile's flag is published once all but this many later store groups have completed
+#endif
+constexpr int kFlagLag = ORX_PIPE_FLAG_LAG;
+constexpr int kMaxTilesPerCtaFlagged = 32;   // one ticket per lane of the producer warp
 
 #ifdef ORX_PIPE_TRACE
 // Tuning aid (tools/pipetrace.py, separate build): per-CTA %globaltimer stamps of the last 16 launches.
@@ -189,8 +210,8 @@ template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, bool NPC = fa
 __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
 k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap planes5, const int use_map,
             const void* __restrict__ moves_v, uint8_t* __restrict__ result,
-            unsigned int n_tiles, unsigned int* __restrict__ sched, int16_t* __restrict__ obs, int obs_radius,
-            uint2* __restrict__ events, int bots ORX_TRACE_PARAM)
+            unsigned int n_tiles, unsigned int* __restrict__ sched, unsigned int* __restrict__ flags,
+            int16_t* __restrict__ obs, int obs_radius, uint2* __restrict__ events, int bots ORX_TRACE_PARAM)
 {
     static_assert(OBS || TICK, "nothing to do");
     static_assert(!EV || (TICK && !OBS), "the event log rides with the plain tick");
@@ -204,15 +225,18 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stages = smem;                                             // kStages * STAGE_BYTES
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);   // full[kStages], done[kStages]
-    uint8_t* tiles_sm = smem + kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes;
+    uint8_t* tiles_sm = smem + kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes + kTicketBytes;
     const uint32_t full0 = smem_addr(bars), done0 = smem_addr(bars + kStages);
     const uint32_t tidx0 = smem_addr(bars + 2 * kStages);      // tile index published with each stage
+    const uint32_t tk0 = tidx0 + kTileIdxBytes;                // flag mode: this CTA's ticket of each of its tiles
     const uint32_t stage0 = smem_addr(stages);
     const unsigned int tid = threadIdx.x;
-    // Programmatic dependent launch: the next kernel in the stream may begin its prologue (barrier
-    // init, map staging) while this grid is still running; its producer waits for this grid to
-    // complete (griddepcontrol.wait) before it touches any plane.
-    if (ORX_PIPE_PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const bool flagged = flags != nullptr;
+    // Programmatic dependent launch: the next kernel in the stream may begin while this grid is still
+    // running. Grid-wait mode: at once; its producer waits for this grid to complete
+    // (griddepcontrol.wait) before it touches any plane. Flag mode: only after this CTA holds the tickets
+    // of all its tiles (below), which is what keeps the tickets of consecutive launches in launch order.
+    if (ORX_PIPE_PDL && !flagged) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -235,8 +259,34 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
 
     if (tid >= kTile) {
         // ------------------------------------------------------------ producer (one thread)
+        if (flagged) {
+            // Lane k of the producer warp draws the ticket of this CTA's k-th tile (static stride): one atomic
+            // instruction, one round trip for all of them. The value has arrived when the shared-memory store
+            // that depends on it has been issued, i.e. the atomic has been performed at the L2 before any thread
+            // of this CTA lets the dependents go.
+            const unsigned int ln = tid - kTile;
+            const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)ln * gridDim.x;
+            if (t < n_tiles) sts_u32(tk0 + 4u * ln, atomicAdd(flags + 2 * t, 1u));
+            __syncwarp();
+        }
         if (tid != kTile) return;
+        if (ORX_PIPE_PDL && flagged) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (use_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&planes5) : "memory");     // descriptor fetch off the first copy's path
+        // flag mode: tile of this CTA's it-th iteration, its serving word, and the hand-over in both directions
+        auto tile_at = [&](unsigned int it) -> uint32_t {
+            const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
+            return t < n_tiles ? (uint32_t)t : 0xFFFFFFFFu;
+        };
+        auto peek = [&](uint32_t tile) -> uint32_t { return tile != 0xFFFFFFFFu ? ld_acquire_gpu(flags + 2 * (size_t)tile + 1) : 0u; };
+        auto await = [&](uint32_t tile, unsigned int it, uint32_t seen) {      // seen: an earlier peek of the tile's serving word
+            const uint32_t want = lds_u32(tk0 + 4u * it);
+            while (seen != want) seen = ld_acquire_gpu(flags + 2 * (size_t)tile + 1);
+            fence_proxy_async_global();         // the acquire (generic proxy) before the bulk loads (async proxy)
+        };
+        auto publish = [&](unsigned int it) {      // this CTA's stores of its it-th tile have completed
+            fence_proxy_async_global();
+            st_release_gpu(flags + 2 * (size_t)tile_at(it) + 1, lds_u32(tk0 + 4u * it) + 1u);
+        };
         // Publishes tile `tile` (or NONE) in the stage of iteration `it` and starts its loads.
         auto issue = [&](unsigned int it, uint32_t tile) {
             const unsigned int s = it % kStages;
@@ -263,6 +313,23 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             bulk_load(base + OFF_STATUS, P.status + g, T1, bar);
             if (TICK) bulk_load(base + OFF_MOVES, moves + g * (MV_BYTES / kTile), MV_BYTES, bar);
         };
+        bool ended = false;
+        if (flagged) {
+            // Prologue, flag mode: look at the serving words of the first kStages tiles in one go, then start
+            // each tile's loads as soon as the previous launch on this state has handed it over.
+            uint32_t seen[kStages];
+#pragma unroll
+            for (int it = 0; it < kStages; ++it) seen[it] = peek(tile_at((unsigned)it));
+#pragma unroll
+            for (int it = 0; it < kStages; ++it) {
+                if (!ended) {
+                    const uint32_t tile = tile_at((unsigned)it);
+                    if (tile != NONE) await(tile, (unsigned)it, seen[it]);
+                    issue((unsigned)it, tile);
+                    ended = tile == NONE;
+                }
+            }
+        } else {
 #if ORX_PIPE_PREFETCH
         // This CTA became resident when a CTA of the previous grid left, i.e. while that grid is still
         // draining its last tiles, and it now has to sit out the rest of that grid; HBM has little to do
@@ -294,12 +361,12 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
         ORX_TRACE(trace_slot, 1);
         // Prologue: the first kStages tiles of a CTA are fixed, so its loads start without a round trip
         // to the counter.
-        bool ended = false;
         for (unsigned int it = 0; it < (unsigned)kStages && !ended; ++it) {
             const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
             const uint32_t tile = t < n_tiles ? (uint32_t)t : NONE;
             issue(it, tile);
             ended = tile == NONE;
+        }
         }
         // Tiles beyond the fixed prefix come from the counter: ticket t is tile dyn_base + t. Every CTA
         // that got kStages fixed tiles claims until its first miss, so a launch draws exactly
@@ -318,12 +385,16 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             if (ticket == claims - 1u) atomicExch(sched, 0u);
             return ticket;
         };
-        uint32_t held = 0;
-        if (!ended && sched != nullptr) held = draw();
+        uint32_t held = 0;      // grid-wait mode: a ticket of the tile counter; flag mode: a peek at the next tile's serving word
+        if (!ended) {
+            if (flagged) held = peek(tile_at((unsigned)kStages));
+            else if (sched != nullptr) held = draw();
+        }
 #ifdef ORX_PIPE_TRACE
         unsigned int trace_tiles = 0;
         ORX_TRACE(trace_slot, 23);          // prologue loads issued
 #endif
+        unsigned int n_done = 0;      // tiles this CTA has stored
         for (unsigned int it = 0;; ++it) {
             const unsigned int s = it % kStages;
             const uint32_t tile = lds_u32(tidx0 + 4 * s);
@@ -357,6 +428,10 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                 bulk_store(P.npc_depth + g * P.n_npc, base + OFF_NDEPTH, 2u * npc2);
             }
             bulk_commit();
+            if (flagged && it >= (unsigned)kFlagLag) {      // hand the tile of kFlagLag iterations ago to the next launch
+                bulk_wait_group<kFlagLag>();
+                publish(it - (unsigned)kFlagLag);
+            }
             // Refill. With a deep pipeline (>= 5 stages) one iteration late, i.e. the stage whose stores were
             // committed in the PREVIOUS iteration: waiting for the group just committed parks this thread
             // until the bulk-store engine has read the whole stage out of shared memory, and nothing else
@@ -365,18 +440,32 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             constexpr bool kLazy = ORX_PIPE_LAZY_REFILL && kStages >= 5;
             constexpr unsigned int kLag = kLazy ? 1u : 0u;
             if (!ended && (!kLazy || it >= 1u)) {
+                const unsigned int nit = it - kLag + kStages;
                 const uint64_t next = sched != nullptr ? (uint64_t)dyn_base + settle(held)
-                                                       : (uint64_t)blockIdx.x + (uint64_t)(it - kLag + kStages) * gridDim.x;
+                                                       : (uint64_t)blockIdx.x + (uint64_t)nit * gridDim.x;
                 const uint32_t nt = next < n_tiles ? (uint32_t)next : NONE;
                 if (kLazy) bulk_wait_read_but_last();      // every group but the one just committed has been read out
                 else bulk_wait_read_all();                 // the stage has been read out: safe to overwrite
-                issue(it - kLag + kStages, nt);
+                if (flagged && nt != NONE) await(nt, nit, held);
+                issue(nit, nt);
                 ended = nt == NONE;
-                if (!ended && sched != nullptr) held = draw();
+                if (!ended) {
+                    if (flagged) held = peek(tile_at(nit + 1u));
+                    else if (sched != nullptr) held = draw();
+                }
             }
+            ++n_done;
         }
-        bulk_wait_read_all();     // shared memory may be released once the last stores have read it; the
+        if (flagged) {
+            // The last tiles: their stores must have completed before the next launch may read them. Then the
+            // grid dependency, so that the completion of this grid implies the completion of every earlier one.
+            bulk_wait_all();
+            for (unsigned int it = n_done > (unsigned)kFlagLag ? n_done - (unsigned)kFlagLag : 0u; it < n_done; ++it) publish(it);
+            if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+        } else {
+            bulk_wait_read_all(); // shared memory may be released once the last stores have read it; the
                                   // writes themselves complete with the grid (as CUTLASS epilogues do)
+        }
         ORX_TRACE(trace_slot, 3);
 #ifdef ORX_PIPE_TRACE
         bulk_wait_all();
@@ -476,7 +565,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
 template <bool OBS, bool EV = false, bool NPC = false>
 constexpr size_t pipe_smem_bytes(int fixed_tiles)
 {
-    return (size_t)kPipeStages<OBS, EV, NPC> * kPipeStageBytes<OBS, EV, NPC> + 2 * kPipeStages<OBS, EV, NPC> * 8 + kTileIdxBytes + (size_t)fixed_tiles;
+    return (size_t)kPipeStages<OBS, EV, NPC> * kPipeStageBytes<OBS, EV, NPC> + 2 * kPipeStages<OBS, EV, NPC> * 8 + kTileIdxBytes + kTicketBytes + (size_t)fixed_tiles;
 }
 
 }  // namespace orx

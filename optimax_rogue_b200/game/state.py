@@ -139,8 +139,8 @@ class BatchedGameState:
         self.npc_pos = torch.zeros((n, e, 2), dtype=torch.uint8, device=dev)
         self.npc_hp = torch.zeros((n, e), dtype=torch.int16, device=dev)
         self.npc_depth = torch.full((n, e), -1, dtype=torch.int32, device=dev)
-        # tile-scheduler scratch of the tick kernel (OrxState.sched): zero between launches, never shared
-        self.sched = torch.zeros((4,), dtype=torch.int32, device=dev)
+        # scratch of the tick kernel (OrxState.sched): tile counter + per-tile hand-over words, never shared
+        self.sched = torch.zeros((_abi.sched_words(n),), dtype=torch.int32, device=dev)
         # the fixed map (shared by all games) lives beside the state
         self.fixed_tiles = self.fixed_ground = None
         self._fixed_stairs = (_abi.NO_STAIRS, _abi.NO_STAIRS)
@@ -172,6 +172,7 @@ class BatchedGameState:
         for name in self.PLANES:
             setattr(st, name, getattr(self, name).data_ptr())
         st.sched = self.sched.data_ptr() if self.sched.is_cuda else None
+        st.sched_words = int(self.sched.numel())
         return st
 
     def c_config(self, **overrides) -> _abi.OrxConfig:

@@ -87,17 +87,24 @@ class BatchedUpdater:
         self.auto_reset = auto_reset
         self.current_update_order = None
         self.track_order = True        # False: want_events=True returns the records without counting them (saves two passes over them)
+        self.path_flags = 0            # _abi.PATH_* bits OR-ed into the state's: pins a kernel path (tests, A/B runs)
         self._cache = None
 
     # -- plumbing ------------------------------------------------------------------------------
     def _cfg(self, gs: BatchedGameState):
-        key = (id(gs), gs.game_id_base, int(self.despawn_strat), int(self.max_ticks or 0), int(self.auto_reset),
-               gs.sched.data_ptr()) + tuple(id(getattr(gs, name)) for name in gs.PLANES)
+        # Keyed by where the planes ARE (device pointers) and by every config field that reaches the C structs,
+        # not by object identity: CPython reuses ids of freed objects.
+        c = gs.cfg
+        key = (gs.n, gs.game_id_base, int(self.despawn_strat), int(self.max_ticks or 0), int(self.auto_reset),
+               int(self.path_flags) | int(c.path_flags), gs.sched.data_ptr(), int(gs.sched.numel()),
+               c.width, c.height, c.dgen_kind, c.start_kind, tuple(c.start_depth), tuple(c.hp), tuple(c.damage),
+               tuple(c.armor), c.n_npc, c.seed,
+               gs.fixed_tiles.data_ptr() if gs.fixed_tiles is not None else 0) + tuple(getattr(gs, name).data_ptr() for name in gs.PLANES)
         if self._cache is None or self._cache[0] != key:
             if (gs.cfg.width, gs.cfg.height, gs.cfg.dgen_kind) != (self.dgen.width, self.dgen.height, self.dgen.kind):
                 raise ValueError('updater.dgen does not match the generator the game state was built with')
             cfg = gs.c_config(despawn_strat=int(self.despawn_strat), max_ticks=int(self.max_ticks or 0),
-                              auto_reset=int(self.auto_reset))
+                              auto_reset=int(self.auto_reset), path_flags=int(self.path_flags) | int(c.path_flags))
             self._cache = (key, cfg, gs.c_struct())
         return self._cache[1], self._cache[2]
 

@@ -691,7 +691,7 @@ def test_plane_placement_does_not_change_results():
 @pytest.mark.gpu
 def test_event_log_through_the_tile_pipeline_equals_the_simple_kernel():
     """With no NPC slots the event records of full 256-game tiles are staged in shared memory and
-    streamed out by the pipelined tick kernel; ORX_NO_EVENT_PIPE=1 forces the one-thread-per-game
+    streamed out by the pipelined tick kernel; path flag ORX_PATH_NO_EVENT_PIPE forces the one-thread-per-game
     kernel. Same records, same results, same states; and the running update order
     (Updater.get_incr_upd_order, updater.py:71-74) equals the number of records emitted."""
     import os
@@ -705,6 +705,7 @@ def test_event_log_through_the_tile_pipeline_equals_the_simple_kernel():
     cfg = SimConfig(max_ticks=50, seed=23, auto_reset=True, width=12, height=7)     # small room: combat and stairs are frequent
     dg = EmptyDungeonGenerator(12, 7)
     ua, ub = BatchedUpdater(dg, 2, 50, auto_reset=True), BatchedUpdater(dg, 2, 50, auto_reset=True)
+    ub.path_flags = _abi.PATH_NO_EVENT_PIPE
     a = BatchedGameState(cfg, n, dev)
     reset_games(a)
     b = a.clone()
@@ -714,11 +715,7 @@ def test_event_log_through_the_tile_pipeline_equals_the_simple_kernel():
     for t in range(120):
         mv = torch.randint(0, 7, (n, 2), dtype=torch.uint8, generator=g).to(dev)
         ra, ea = ua.update(a, mv, want_events=True)
-        os.environ['ORX_NO_EVENT_PIPE'] = '1'
-        try:
-            rb, eb = ub.update(b, mv, want_events=True)
-        finally:
-            del os.environ['ORX_NO_EVENT_PIPE']
+        rb, eb = ub.update(b, mv, want_events=True)
         assert torch.equal(ra, rb) and torch.equal(ea, eb), t
         k = ea[:, :, 0] & 0xFF
         expect += (k != 0).sum(dim=1)
@@ -815,7 +812,7 @@ def test_device_stepper_equals_update():
 @pytest.mark.parametrize('n_npc', [1, 3, 8])
 def test_npc_slots_through_the_tile_pipeline(n_npc):
     """With NPC slots the slot planes travel through the tile pipeline as three more slices per tile;
-    ORX_NO_NPC_PIPE=1 forces the one-thread-per-game kernel. Both equal the oracle: planes, NPC planes,
+    path flag ORX_PATH_NO_NPC_PIPE forces the one-thread-per-game kernel. Both equal the oracle: planes, NPC planes,
     results; players bump into NPCs, kill them, and descend next to them."""
     import os
     import torch
@@ -834,15 +831,12 @@ def test_npc_slots_through_the_tile_pipeline(n_npc):
     culled0 = int((a.npc_depth < 0).sum())
     b = a.clone()
     upd_b = type(upd)(upd.dgen, upd.despawn_strat, upd.max_ticks, auto_reset=False)
+    upd_b.path_flags = _abi.PATH_NO_NPC_PIPE
     for t in range(70):
         mv = orc.bot_moves(1, 2) if t % 2 else rng.integers(1, 6, size=(n, 2), dtype=np.uint8)
         m = torch.from_numpy(mv).cuda()
         ra, _ = upd.update(a, m)
-        os.environ['ORX_NO_NPC_PIPE'] = '1'
-        try:
-            rb, _ = upd_b.update(b, m)
-        finally:
-            del os.environ['ORX_NO_NPC_PIPE']
+        rb, _ = upd_b.update(b, m)
         ro, _ = orc.step(mv, want_events=False)
         assert torch.equal(ra, rb) and np.array_equal(ra.cpu().numpy(), ro), t
         gu.assert_state_equal(a, orc, f'tick {t} (pipeline)')
