@@ -178,8 +178,23 @@ __device__ __forceinline__ void sts_s32x2(uint32_t a, int x, int y) { asm volati
 __device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // flag mode: per-tile hand-over between consecutive launches on one state
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_release_gpu(unsigned int* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// The hand-over words are read and written with RELAXED gpu-scope accesses, ordered against the bulk copies by
+// completion, not by fences: a tile's serving word is stored only after cp.async.bulk.wait_group has reported
+// the tile's bulk stores complete (performed at the L2, the single point of coherence: every address has one
+// home slice, and neither the bulk engine nor these strong accesses go through an L1), and a tile's bulk loads
+// are issued only after a load of its serving word has returned the awaited ticket. A release store here is
+// MEMBAR.ALL.GPU + ERRBAR in front of the STG and also waits for the CTA's bulk loads in flight: measured
+// 19.0 instead of 12.0 us per 2^20-game step, 3.27 instead of 2.58 us at 2^17 (profiles/r02_ab_flag_fences.log);
+// an acquire load adds a CCTL.IVALL that blocks the thread on the round trip (+1.1 us at 2^20).
+// -DORX_FLAG_STRICT_FENCES builds the release/acquire form (same results, tests/test_gpu_tile_flags.py).
+#ifdef ORX_FLAG_STRICT_FENCES
+__device__ __forceinline__ uint32_t ld_flag(const unsigned int* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_flag(unsigned int* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+#else
+__device__ __forceinline__ uint32_t ld_flag(const unsigned int* p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_flag(unsigned int* p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+#endif
+// generic-proxy flag access <-> async-proxy bulk copies of the tile (CCTL.IVALL + FENCE.VIEW.ASYNC.G: no measurable cost)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 #ifndef ORX_PIPE_FLAG_LAG
@@ -277,15 +292,15 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
             return t < n_tiles ? (uint32_t)t : 0xFFFFFFFFu;
         };
-        auto peek = [&](uint32_t tile) -> uint32_t { return tile != 0xFFFFFFFFu ? ld_acquire_gpu(flags + 2 * (size_t)tile + 1) : 0u; };
+        auto peek = [&](uint32_t tile) -> uint32_t { return tile != 0xFFFFFFFFu ? ld_flag(flags + 2 * (size_t)tile + 1) : 0u; };
         auto await = [&](uint32_t tile, unsigned int it, uint32_t seen) {      // seen: an earlier peek of the tile's serving word
             const uint32_t want = lds_u32(tk0 + 4u * it);
-            while (seen != want) seen = ld_acquire_gpu(flags + 2 * (size_t)tile + 1);
+            while (seen != want) seen = ld_flag(flags + 2 * (size_t)tile + 1);
             fence_proxy_async_global();         // the acquire (generic proxy) before the bulk loads (async proxy)
         };
         auto publish = [&](unsigned int it) {      // this CTA's stores of its it-th tile have completed
             fence_proxy_async_global();
-            st_release_gpu(flags + 2 * (size_t)tile_at(it) + 1, lds_u32(tk0 + 4u * it) + 1u);
+            st_flag(flags + 2 * (size_t)tile_at(it) + 1, lds_u32(tk0 + 4u * it) + 1u);
         };
         // Publishes tile `tile` (or NONE) in the stage of iteration `it` and starts its loads.
         auto issue = [&](unsigned int it, uint32_t tile) {

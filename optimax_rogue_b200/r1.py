@@ -34,6 +34,11 @@ class R1GameState:
         for name, _, _ in _abi.R1_PLANES:
             setattr(self._st, name, getattr(self, name).data_ptr())
 
+    @property
+    def alg_bytes_per_game_tick(self) -> int:
+        """State in + state out + 2 command bytes + 1 result byte (ruleset R1)."""
+        return 2 * _abi.R1_STATE_BYTES + 3
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 

@@ -23,7 +23,20 @@ import numpy as np
 
 from . import philox as px
 
-REFERENCE_ROOT = os.environ.get('ORX_REFERENCE_ROOT', '/root/reference')
+def _find_reference_root():
+    """ORX_REFERENCE_ROOT, else the reference tree of the build container, else the copy oracle/make_ref.py
+    ships to the GPU box (oracle/_ref, git-ignored)."""
+    env = os.environ.get('ORX_REFERENCE_ROOT')
+    if env:
+        return env
+    shipped = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+    for root in ('/root/reference', shipped):
+        if os.path.isdir(os.path.join(root, 'optimax_rogue', 'logic')):
+            return root
+    return '/root/reference'
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 # event codes shared with include/orx.h (ORX_EV_*)
 EV_MOVE, EV_COMBAT, EV_DUNGEON, EV_DEATH, EV_DESCEND = 1, 2, 3, 4, 5

@@ -37,18 +37,51 @@ def test_back_to_back_ticks_on_one_state(n, tpc):
     assert gs.sched.numel() == _abi.sched_words(n)
     rng = np.random.default_rng(n + tpc)
     mv = _moves(rng, ticks, n)
-    dmv = torch.from_numpy(mv).cuda()
-    res = torch.zeros((ticks, n), dtype=torch.uint8, device='cuda')
+    pad = -(-n // 16) * 16            # every tick's command / result rows 16-byte aligned: all launches take the tile pipeline
+    dmv = torch.zeros((ticks, pad, 2), dtype=torch.uint8, device='cuda')
+    dmv[:, :n] = torch.from_numpy(mv).cuda()
+    res = torch.zeros((ticks, pad), dtype=torch.uint8, device='cuda')
     torch.cuda.synchronize()
     for t in range(ticks):
-        upd.update(gs, dmv[t], out=res[t])
+        upd.update(gs, dmv[t, :n], out=res[t, :n])
     torch.cuda.synchronize()
     want = _oracle_run(orc, mv)
-    assert np.array_equal(res.cpu().numpy(), want)
+    assert np.array_equal(res[:, :n].cpu().numpy(), want)
     gu.assert_state_equal(gs, orc, 'after back-to-back ticks')
-    # the hand-over words are balanced again: tickets handed out == passes completed, for every tile
+    # the hand-over words are balanced again: tickets handed out == passes completed == ticks, for every tile
     w = gs.sched.cpu().numpy()[_abi.SCHED_HEADER_WORDS:].reshape(-1, 2)
     assert np.array_equal(w[:, 0], w[:, 1]) and (w[:, 0] == ticks).all()
+
+
+@pytest.mark.parametrize('n,ticks', [(1 << 18, 600), (1 << 20, 160)])
+def test_long_unsynchronised_runs(n, ticks):
+    """Hundreds of ticks in flight behind each other (a CUDA graph replayed without a pause), the state planes of
+    the bigger batch far larger than what is in flight: the end state equals the oracle's after the same commands."""
+    cfg = SimConfig(max_ticks=97, seed=4242, auto_reset=True)
+    gs, upd, orc = gu.make_pair(cfg, n)
+    per = 40
+    g = torch.Generator(device='cuda').manual_seed(n)
+    dmv = torch.randint(1, 6, (per, n, 2), dtype=torch.uint8, device='cuda', generator=g)
+    res = torch.zeros((per, n), dtype=torch.uint8, device='cuda')
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        upd.update(gs, dmv[0], out=res[0])
+        upd.update(gs, dmv[1], out=res[1])
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            for t in range(per):
+                upd.update(gs, dmv[t], out=res[t])
+        for _ in range(ticks // per):
+            graph.replay()
+    torch.cuda.synchronize()
+    mv = dmv.cpu().numpy()
+    _oracle_run(orc, mv[:2])
+    want = None
+    for _ in range(ticks // per):
+        want = _oracle_run(orc, mv)
+    assert np.array_equal(res.cpu().numpy(), want)
+    gu.assert_state_equal(gs, orc, 'long run')
 
 
 def test_graph_of_interleaved_states_replayed():
