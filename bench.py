@@ -364,10 +364,11 @@ def run_b200(args, rank, local_rank, world):
             hc.copy_(pack_moves(m[:, 0], m[:, 1]))
         host_res = [torch.empty((G,), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
 
-        def time_host_loop(cmd_bufs, sync):
+        def time_host_loop(cmd_bufs, sync, res_bufs=None, bits=False):
             # one bound stepper per (batch, command buffer): BatchedUpdater.host_stepper is the public call for
             # host-side loops; each step() = H2D commands + tick + D2H results (+ stream sync when sync=True)
-            steppers = [upd.host_stepper(batches[k % nb], cmd_bufs[k % n_host], host_res[k % 2], sync=sync)
+            res_bufs = res_bufs or host_res
+            steppers = [upd.host_stepper(batches[k % nb], cmd_bufs[k % n_host], res_bufs[k % 2], sync=sync, bits=bits)
                         for k in range(nb * n_host // math.gcd(nb, n_host))]
             evs = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -398,20 +399,28 @@ def run_b200(args, rank, local_rank, world):
             barrier()
             return max_over_ranks(ms) / n, n
 
-        ms_e2e, k_e2e = time_host_loop(host_cmds, True)
-        out['e2e'] = {'value': world * G / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': G, 'd2h_bytes_per_step': G,
+        from optimax_rogue_b200.logic.moves import pack_moves5
+        nb_in, nb_out = _abi.cmd5_bytes(G), _abi.res2_bytes(G)
+        host_cmd5 = [torch.from_numpy(pack_moves5(moves[k][:, 0].cpu().numpy(), moves[k][:, 1].cpu().numpy())).pin_memory() for k in range(n_host)]
+        host_res2 = [torch.empty((nb_out,), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        ms_e2e, k_e2e = time_host_loop(host_cmd5, True, res_bufs=host_res2, bits=True)
+        out['e2e'] = {'value': world * G / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': nb_in, 'd2h_bytes_per_step': nb_out,
                       'steps': k_e2e, 'us_per_step': ms_e2e * 1e3,
-                      'api': 'BatchedUpdater.host_stepper(state, pinned host uint8[N] commands p1|p2<<4, pinned host uint8[N] results)() '
-                             '= orx_step_host_packed_sync: commands and results cross PCIe inside the timed region, stream sync every step'}
+                      'api': 'BatchedUpdater.host_stepper(state, pinned host cmd5 bytes, pinned host res2 bytes, bits=True)() = orx_step_host_bits_sync: '
+                             '5 bits of command pair per game host->device and 2 bits of result per game device->host cross PCIe inside the '
+                             'timed region (read / written by the tick kernel, one bulk copy per CTA each way), stream sync every step'}
         if not args.no_extras:
+            ms_n, k_n = time_host_loop(host_cmds, True)
+            out['e2e']['nibbles'] = {'value': world * G / (ms_n * 1e-3), 'h2d_bytes_per_step': G, 'd2h_bytes_per_step': G, 'steps': k_n,
+                                     'api': 'round-1 format: uint8[N] commands p1|p2<<4 in, uint8[N] results out (orx_step_host_packed_sync)'}
             ms_u, k_u = time_host_loop(host_moves, True)
-            ms_p, k_p = time_host_loop(host_cmds, False)
+            ms_p, k_p = time_host_loop(host_cmd5, False, res_bufs=host_res2, bits=True)
             out['e2e']['unpacked'] = {'value': world * G / (ms_u * 1e-3), 'h2d_bytes_per_step': 2 * G, 'd2h_bytes_per_step': G,
                                       'steps': k_u, 'api': 'same call with uint8[N,2] commands (orx_step_host_sync)'}
-            out['e2e']['pipelined'] = {'value': world * G / (ms_p * 1e-3), 'h2d_bytes_per_step': G, 'd2h_bytes_per_step': G, 'steps': k_p,
-                                       'api': 'host_stepper(..., sync=False) = orx_step_host_packed on two independent batches in flight; '
+            out['e2e']['pipelined'] = {'value': world * G / (ms_p * 1e-3), 'h2d_bytes_per_step': nb_in, 'd2h_bytes_per_step': nb_out, 'steps': k_p,
+                                       'api': 'host_stepper(..., sync=False, bits=True) = orx_step_host_bits on two independent batches in flight; '
                                               'the host waits on step k-1\'s event after enqueueing step k'}
-        del host_moves, host_cmds, host_res
+        del host_moves, host_cmds, host_res, host_cmd5, host_res2
 
         # ---------------------------------------------------------------- weak scaling (N > 1): 2^20 games per GPU
         if world > 1:

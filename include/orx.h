@@ -28,6 +28,8 @@
  *   orx_step_host   orx_step with host command/result buffers (what a remote caller holds);
  *   orx_step_host_packed(_sync)  the host-buffer tick with nibble-packed commands (half the PCIe bytes)
  *   orx_step_host_sync  the same plus a stream synchronisation (Server.update returns the result, server.py:132-138)
+ *   orx_step_bits / orx_step_host_bits(_sync)  the same tick told and answered in the fewest bytes: 5 bits of command
+ *                       pair in, 2 bits of result out per game
  *
  * Integer codes are the reference's enum values and must not change.
  */
@@ -221,6 +223,28 @@ int orx_step_host_packed(const OrxConfig* cfg, const OrxState* st, const uint8_t
 int orx_step_host_packed_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmds_host,
                               uint8_t* result_host, uint8_t* cmds_dev, uint8_t* result_dev, int64_t n,
                               uint64_t game_id_base, void* cuda_stream);
+
+/* Bit-packed command / result streams: the fewest bytes a tick can be told and can answer with, for callers whose
+ * buffers live in HOST memory (a game's command pair is one of 25 states, its result one of 4).
+ *   cmd5: ORX_CMD5_BYTES(n) bytes; game i owns bits [5i, 5i+5) of the little-endian bit stream (bit b of the stream
+ *         = bit b&7 of byte b>>3), value (p1_move - 1) * 5 + (p2_move - 1) with moves 1..5; 25..31 = both Stay.
+ *   res2: ORX_RES2_BYTES(n) bytes; game i owns bits [2i, 2i+2), value ORX_RESULT_* - 1; padding bits are 0.
+ * Both 16-byte aligned. Same tick as orx_step (logic/moves.py:6-12 and updater.py:16-21 are the codes packed here).
+ * orx_step_bits takes device pointers (or device-mapped pinned host pointers); orx_step_host_bits[_sync] take host
+ * buffers like orx_step_host[_sync]: pinned ones are read and written by the tick kernel itself, ONE PCIe
+ * transaction per CTA each way (the commands of all its tiles when it starts, their results when it ends), pageable
+ * ones go through the caller's device staging buffers cmd5_dev / res2_dev (same sizes, else nullable). No NPC slots. */
+#define ORX_FMT_BYTES 0
+#define ORX_FMT_NIBBLES 1
+#define ORX_FMT_BITS 2
+#define ORX_CMD5_BYTES(n) ((size_t)((5 * (uint64_t)(n) + 7) / 8))
+#define ORX_RES2_BYTES(n) ((size_t)((2 * (uint64_t)(n) + 7) / 8))
+int orx_step_bits(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5, uint8_t* res2, int64_t n,
+                  uint64_t game_id_base, void* cuda_stream);
+int orx_step_host_bits(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5_host, uint8_t* res2_host,
+                       uint8_t* cmd5_dev, uint8_t* res2_dev, int64_t n, uint64_t game_id_base, void* cuda_stream);
+int orx_step_host_bits_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5_host, uint8_t* res2_host,
+                            uint8_t* cmd5_dev, uint8_t* res2_dev, int64_t n, uint64_t game_id_base, void* cuda_stream);
 
 /* Command generation for scripted bots; ORX_BOT_NONE leaves that player's byte untouched. */
 int orx_bot_moves(const OrxConfig* cfg, const OrxState* st, int bot_p1, int bot_p2,

@@ -28,6 +28,14 @@ SCHED_HEADER_WORDS = 4
 TILE = 256
 
 
+def cmd5_bytes(n: int) -> int:
+    return (5 * int(n) + 7) // 8
+
+
+def res2_bytes(n: int) -> int:
+    return (2 * int(n) + 7) // 8
+
+
 def sched_words(n: int) -> int:
     """orx_sched_words: scratch words that enable tile-by-tile ordering for n games."""
     return SCHED_HEADER_WORDS + 2 * (max(int(n), 0) // TILE)
@@ -112,6 +120,11 @@ PROTOTYPES = {
                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_step_host_sync': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step_bits': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step_host_bits': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_step_host_bits_sync': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_bot_moves': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_int, C.c_int,
                                 C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_rollout': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_int, C.c_int, C.c_int,

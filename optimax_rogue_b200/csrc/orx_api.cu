@@ -57,7 +57,7 @@ __device__ __forceinline__ const uint8_t* stage_tiles(const Params& P, uint8_t* 
 template <int DGEN, bool NPC, bool EV>
 __global__ void __launch_bounds__(kThreads, 4)
 k_step(const __grid_constant__ Params P, const void* __restrict__ moves, uint8_t* __restrict__ result,
-       uint2* __restrict__ events, int max_ev, int packed, int bots = 0)
+       uint2* __restrict__ events, int max_ev, int fmt, int bots = 0)
 {
     extern __shared__ uint8_t smem[];
     __shared__ CmdEntry lut[256];
@@ -66,47 +66,67 @@ k_step(const __grid_constant__ Params P, const void* __restrict__ moves, uint8_t
     if (DGEN == ORX_DGEN_FIXED) tiles = stage_tiles(P, smem);
     else __syncthreads();
     const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= P.n) return;
-    // Eight independent loads in flight per thread before the first use (asm volatile keeps ptxas
-    // from sinking them below the frozen-lane test, which would serialise two DRAM round trips).
-    const uint32_t pos = ldg_u32(P.pos + i), hpw = ldg_u32(P.hp + i), stw = ldg_u32(P.stairs + i);
-    const uint32_t ep = ldg_u32(P.episode + i);
-    const int tick = (int)ldg_u32(reinterpret_cast<const uint32_t*>(P.tick) + i);
-    const int2 dep = ldg_s32x2(P.depth + i);
-    const int status = (int)ldg_u8(P.status + i);
-    uint32_t mv;
-    if (packed) {     // one byte per game: p1 in the low nibble, p2 in the high nibble
-        const uint32_t c = ldg_u8(static_cast<const uint8_t*>(moves) + i);
-        mv = (c & 15u) | ((c >> 4) << 8);
-    } else {
-        mv = ldg_u16(static_cast<const uint16_t*>(moves) + i);
+    const bool in = i < P.n;
+    int res = 0;
+    if (in) {
+        // Eight independent loads in flight per thread before the first use (asm volatile keeps ptxas
+        // from sinking them below the frozen-lane test, which would serialise two DRAM round trips).
+        const uint32_t pos = ldg_u32(P.pos + i), hpw = ldg_u32(P.hp + i), stw = ldg_u32(P.stairs + i);
+        const uint32_t ep = ldg_u32(P.episode + i);
+        const int tick = (int)ldg_u32(reinterpret_cast<const uint32_t*>(P.tick) + i);
+        const int2 dep = ldg_s32x2(P.depth + i);
+        const int status = (int)ldg_u8(P.status + i);
+        uint32_t mv;
+        if (fmt == ORX_FMT_NIBBLES) {     // one byte per game: p1 in the low nibble, p2 in the high nibble
+            const uint32_t c = ldg_u8(static_cast<const uint8_t*>(moves) + i);
+            mv = (c & 15u) | ((c >> 4) << 8);
+        } else if (fmt == ORX_FMT_BITS) { // five bits per game: (p1 - 1) * 5 + (p2 - 1); 25..31 = both Stay
+            const uint8_t* c = static_cast<const uint8_t*>(moves) + ((size_t)i * 5u >> 3);
+            const uint32_t sh = (i * 5u) & 7u;
+            uint32_t w = ldg_u8(c);
+            if (sh > 3u) w |= ldg_u8(c + 1) << 8;
+            const uint32_t v = (w >> sh) & 31u, p1 = v / 5u;
+            mv = v < 25u ? ((p1 + 1u) | ((v - 5u * p1 + 1u) << 8)) : 0u;
+        } else {
+            mv = ldg_u16(static_cast<const uint16_t*>(moves) + i);
+        }
+        EvSink<EV> ev{EV ? events + (size_t)i * max_ev : nullptr, 0, max_ev};
+        if (status != ORX_RESULT_IN_PROGRESS) {   // finished lanes are frozen until reset
+            res = status;
+            ev.finish();
+        } else {
+            Lane L;
+            unpack_lane(L, pos, hpw, dep, stw, tick, ep);
+            Stream s = make_stream(P, i, ep);
+            const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)tick);
+            if (bots != 0) {                      // scripted players (orx_step_bots): kind of p1 | kind of p2 << 8
+                if ((bots & 255) != ORX_BOT_NONE) mv = (mv & 0xFF00u) | bot_move(bots & 255, L.pos & 0xFFFFu, L.st & 0xFFFFu, blk.x);
+                if ((bots >> 8) != ORX_BOT_NONE) mv = (mv & 0x00FFu) | (bot_move(bots >> 8, L.pos >> 16, L.st >> 16, blk.y) << 8);
+            }
+            Counters cnt{};
+            const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
+            const NpcView* nv = NPC ? &slots : nullptr;
+            res = tick_lane<DGEN, NPC, EV>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
+            ev.finish();
+            int new_status = res;
+            if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
+                s.episode += 1;
+                reset_lane<DGEN, NPC>(P, L, s, nv);
+                new_status = ORX_RESULT_IN_PROGRESS;
+            }
+            store_lane(P, i, L, new_status);
+        }
     }
-    EvSink<EV> ev{EV ? events + (size_t)i * max_ev : nullptr, 0, max_ev};
-    if (status != ORX_RESULT_IN_PROGRESS) {   // finished lanes are frozen until reset
-        result[i] = (uint8_t)status;
-        ev.finish();
-        return;
+    if (fmt == ORX_FMT_BITS) {
+        // two bits per game (result - 1), four games per byte: the lane of a byte's first game gathers the other three
+        const uint32_t r = in ? (uint32_t)(res - 1) & 3u : 0u;
+        const uint32_t lo = __ballot_sync(0xffffffffu, (r & 1u) != 0u), hi = __ballot_sync(0xffffffffu, (r & 2u) != 0u);
+        const uint32_t q = threadIdx.x & 28u;
+        auto spread4 = [](uint32_t x) { return (x & 1u) | ((x & 2u) << 1) | ((x & 4u) << 2) | ((x & 8u) << 3); };
+        if (in && (threadIdx.x & 3u) == 0u) result[i >> 2] = (uint8_t)(spread4((lo >> q) & 15u) | (spread4((hi >> q) & 15u) << 1));
+    } else if (in) {
+        result[i] = (uint8_t)res;
     }
-    Lane L;
-    unpack_lane(L, pos, hpw, dep, stw, tick, ep);
-    Stream s = make_stream(P, i, ep);
-    const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)tick);
-    if (bots != 0) {                      // scripted players (orx_step_bots): kind of p1 | kind of p2 << 8
-        if ((bots & 255) != ORX_BOT_NONE) mv = (mv & 0xFF00u) | bot_move(bots & 255, L.pos & 0xFFFFu, L.st & 0xFFFFu, blk.x);
-        if ((bots >> 8) != ORX_BOT_NONE) mv = (mv & 0x00FFu) | (bot_move(bots >> 8, L.pos >> 16, L.st >> 16, blk.y) << 8);
-    }
-    Counters cnt{};
-    const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
-    const NpcView* nv = NPC ? &slots : nullptr;
-    int res = tick_lane<DGEN, NPC, EV>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
-    ev.finish();
-    result[i] = (uint8_t)res;
-    if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
-        s.episode += 1;
-        reset_lane<DGEN, NPC>(P, L, s, nv);
-        res = ORX_RESULT_IN_PROGRESS;
-    }
-    store_lane(P, i, L, res);
 }
 
 // ------------------------------------------------------------------ K2: masked episode reset
@@ -492,7 +512,8 @@ template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, bool NPC = fa
 int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, const TileCtl& ctl,
                 int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
 {
-    const size_t smem = pipe_smem_bytes<OBS, EV, NPC>((int)tiles_bytes);
+    constexpr bool BITS = CMD == CMD_BITS;
+    const size_t smem = pipe_smem_bytes<OBS, EV, NPC, BITS>((int)tiles_bytes);
     auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK, EV, NPC>;
     // Launch geometry depends only on (device, kernel, smem): looked up once per process, the occupancy query
     // costs more than the launch itself. (A cache of device properties, not state; one per kernel instantiation.)
@@ -510,7 +531,7 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     {
         std::lock_guard<std::mutex> lk(cache_mu);
         if (!attr_set[dev & 63]) {
-            const size_t most = pipe_smem_bytes<OBS, EV, NPC>(kMaxFixedTiles);
+            const size_t most = pipe_smem_bytes<OBS, EV, NPC, BITS>(kMaxFixedTiles);
             if (most > 48 * 1024) {
                 const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
                 if (e != cudaSuccess) return cuda_fail(e);
@@ -539,6 +560,12 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
         if (g < floor_g) g = floor_g;
         if (g < grid) grid = g;
     }
+    unsigned int tiles_per_cta = 0;
+    if (BITS) {      // contiguous runs of tiles per CTA, every CTA at least one; the caller keeps n_tiles <= kBitsMaxTiles * grid
+        tiles_per_cta = (n_tiles + grid - 1) / grid;
+        grid = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+        if (tiles_per_cta > kBitsMaxTiles) return ORX_ERR_UNSUPPORTED;
+    }
     alignas(64) CUtensorMap planes5;
     int use_map = 0;
     if (!ctl.no_tensor_map) use_map = planes5_map(P, n_tiles, &planes5) ? 1 : 0;
@@ -551,9 +578,9 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     lc.attrs = at; lc.numAttrs = ORX_PIPE_PDL ? 1 : 0;
 #ifdef ORX_PIPE_TRACE
     static unsigned int trace_slot = 0;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, ctl.counter, ctl.flags, obs, obs_radius, events, bots, trace_slot++);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, BITS ? nullptr : ctl.counter, ctl.flags, obs, obs_radius, events, bots, tiles_per_cta, trace_slot++);
 #else
-    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, ctl.counter, ctl.flags, obs, obs_radius, events, bots);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, BITS ? nullptr : ctl.counter, ctl.flags, obs, obs_radius, events, bots, tiles_per_cta);
 #endif
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
 }
@@ -641,6 +668,74 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
         if (obs != nullptr) k_observe<<<grid, kThreads, 0, s>>>(P, obs, obs_radius);
         return launch_done();
     });
+}
+
+// One tick with the bit-packed streams: cmd5 = 5 bits per game in, res2 = 2 bits per game out (orx.h). Device
+// pointers, or device-mapped pinned host memory (the kernel then reads / writes it over PCIe, one transaction per
+// CTA each way).
+int step_bits_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5, uint8_t* res2, int64_t n,
+                   uint64_t game_id_base, void* cuda_stream)
+{
+    const int rc = check_common(cfg, st, n);
+    if (rc != ORX_OK) return rc;
+    if (!ids_ok(game_id_base, n)) return ORX_ERR_BAD_ARG;
+    if (cmd5 == nullptr || res2 == nullptr || !aligned(cmd5, 16) || !aligned(res2, 16)) return ORX_ERR_BAD_ARG;
+    if (cfg->n_npc != 0) return ORX_ERR_UNSUPPORTED;
+    if (n == 0) return ORX_OK;
+    const Params P = make_params(cfg, st, n, game_id_base);
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    const size_t smem = tiles_smem(cfg);
+    const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
+    const unsigned int n_tiles = (unsigned int)(n / kTile);
+    const int64_t n_body = (int64_t)n_tiles * kTile;
+    if (n_tiles > 0 && pipe_aligned(st, cmd5, res2)) {
+        const TileCtl ctl = tile_ctl(cfg, st, n_tiles);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        // a CTA holds the commands / results of at most kBitsMaxTiles tiles: batches beyond that many tiles per
+        // resident CTA (only possible in grid-wait mode; flag mode is bounded the same way) go chunk by chunk
+        const unsigned int max_tiles = ctl.flags != nullptr ? n_tiles : (unsigned int)kBitsMaxTiles * (unsigned int)device_sms(dev);
+        for (unsigned int t0 = 0; t0 < n_tiles; t0 += max_tiles) {
+            const unsigned int nt = n_tiles - t0 < max_tiles ? n_tiles - t0 : max_tiles;
+            const Params C = t0 == 0 && nt == n_tiles ? P : offset_params(P, (int64_t)t0 * kTile, (int64_t)nt * kTile);
+            TileCtl c = ctl;
+            if (c.flags != nullptr) c.flags += 2 * (size_t)t0;
+            const uint8_t* cm = cmd5 + (size_t)t0 * kCmdBitsTile;
+            uint8_t* rs = res2 + (size_t)t0 * kResBitsTile;
+            const int rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BITS, false, true>(C, cm, rs, nt, 0, c, nullptr, -1, s)
+                                  : launch_pipe<ORX_DGEN_FIXED, CMD_BITS, false, true>(C, cm, rs, nt, smem, c, nullptr, -1, s);
+            if (rc2 != ORX_OK) return rc2;
+        }
+        if (n_body == n) return ORX_OK;
+        const Params T = offset_params(P, n_body, n - n_body);
+        const int tgrid = grid_for(n - n_body);
+        const uint8_t* cm = cmd5 + (size_t)n_tiles * kCmdBitsTile;
+        uint8_t* rs = res2 + (size_t)n_tiles * kResBitsTile;
+        if (empty) k_step<ORX_DGEN_EMPTY, false, false><<<tgrid, kThreads, 0, s>>>(T, cm, rs, nullptr, ORX_MAX_EVENTS_BASE, ORX_FMT_BITS);
+        else k_step<ORX_DGEN_FIXED, false, false><<<tgrid, kThreads, smem, s>>>(T, cm, rs, nullptr, ORX_MAX_EVENTS_BASE, ORX_FMT_BITS);
+        return launch_done();
+    }
+    const int grid = grid_for(n);
+    if (empty) k_step<ORX_DGEN_EMPTY, false, false><<<grid, kThreads, 0, s>>>(P, cmd5, res2, nullptr, ORX_MAX_EVENTS_BASE, ORX_FMT_BITS);
+    else k_step<ORX_DGEN_FIXED, false, false><<<grid, kThreads, smem, s>>>(P, cmd5, res2, nullptr, ORX_MAX_EVENTS_BASE, ORX_FMT_BITS);
+    return launch_done();
+}
+
+int step_host_bits_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5_host, uint8_t* res2_host,
+                        uint8_t* cmd5_dev, uint8_t* res2_dev, int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    if (cmd5_host == nullptr || res2_host == nullptr || cfg == nullptr) return ORX_ERR_BAD_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    void *cm = nullptr, *rs = nullptr;
+    if (!(cfg->path_flags & ORX_PATH_HOST_STAGED) && host_mapped(cmd5_host, &cm) && host_mapped(res2_host, &rs))
+        return step_bits_impl(cfg, st, static_cast<const uint8_t*>(cm), static_cast<uint8_t*>(rs), n, game_id_base, cuda_stream);
+    if (cmd5_dev == nullptr || res2_dev == nullptr || n < 0) return ORX_ERR_BAD_ARG;
+    cudaError_t e = cudaMemcpyAsync(cmd5_dev, cmd5_host, ORX_CMD5_BYTES(n), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return cuda_fail(e);
+    const int rc = step_bits_impl(cfg, st, cmd5_dev, res2_dev, n, game_id_base, cuda_stream);
+    if (rc != ORX_OK) return rc;
+    e = cudaMemcpyAsync(res2_host, res2_dev, ORX_RES2_BYTES(n), cudaMemcpyDeviceToHost, s);
+    return e == cudaSuccess ? ORX_OK : cuda_fail(e);
 }
 
 int step_host_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
@@ -783,6 +878,27 @@ int orx_step_host_packed_sync(const OrxConfig* cfg, const OrxState* st, const ui
                               uint64_t game_id_base, void* cuda_stream)
 {
     const int rc = step_host_impl(cfg, st, cmds_host, result_host, cmds_dev, result_dev, n, game_id_base, cuda_stream, 1);
+    if (rc != ORX_OK) return rc;
+    const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
+    return e == cudaSuccess ? ORX_OK : cuda_fail(e);
+}
+
+int orx_step_bits(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5, uint8_t* res2, int64_t n,
+                  uint64_t game_id_base, void* cuda_stream)
+{
+    return step_bits_impl(cfg, st, cmd5, res2, n, game_id_base, cuda_stream);
+}
+
+int orx_step_host_bits(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5_host, uint8_t* res2_host,
+                       uint8_t* cmd5_dev, uint8_t* res2_dev, int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    return step_host_bits_impl(cfg, st, cmd5_host, res2_host, cmd5_dev, res2_dev, n, game_id_base, cuda_stream);
+}
+
+int orx_step_host_bits_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5_host, uint8_t* res2_host,
+                            uint8_t* cmd5_dev, uint8_t* res2_dev, int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    const int rc = step_host_bits_impl(cfg, st, cmd5_host, res2_host, cmd5_dev, res2_dev, n, game_id_base, cuda_stream);
     if (rc != ORX_OK) return rc;
     const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
     return e == cudaSuccess ? ORX_OK : cuda_fail(e);

@@ -99,6 +99,17 @@ template <bool OBS, bool EV = false, bool NPC = false> constexpr uint32_t kPipeS
 // Command formats: CMD_BYTES = uint8[n][2] (p1, p2); CMD_NIBBLES = uint8[n], p1 in the low nibble,
 // p2 in the high nibble (halves the command traffic when the commands come over PCIe).
 constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1, CMD_BYTES_BOTS = 2;   // _BOTS: uint8[n][2], scripted players' commands computed in the kernel
+// CMD_BITS: the bit-packed streams of orx_step_bits (orx.h): 5 bits of command pair per game in, 2 bits of result
+// per game out -- what crosses PCIe when the caller's buffers live in host memory. A CTA then owns a CONTIGUOUS
+// run of tiles (tiles_per_cta of them), fetches the commands of all of them with ONE bulk copy when it starts and
+// sends the results of all of them with ONE bulk copy when it ends: two large PCIe transactions per CTA instead of
+// two small ones per tile, none of them on a tile's critical path.
+constexpr int CMD_BITS = 3;
+constexpr uint32_t kCmdBitsTile = 5u * kTile / 8u, kResBitsTile = 2u * kTile / 8u;      // 160 and 64 bytes per tile
+constexpr uint32_t kBitsMaxTiles = 32;                                                    // tiles per CTA in CMD_BITS mode
+constexpr uint32_t kBitsCmdBytes = kBitsMaxTiles * kCmdBitsTile + 16u, kBitsResBytes = kBitsMaxTiles * kResBitsTile;
+constexpr uint32_t kBitsSmemBytes = 16u + kBitsCmdBytes + kBitsResBytes;                 // mbarrier + command block + result block
+static_assert(kCmdBitsTile % 16 == 0 && kResBitsTile % 16 == 0, "bit-packed tiles move as bulk copies");
 static_assert(kTile % 32 == 0 && (T1 % 16) == 0, "bulk copies move multiples of 16 bytes");
 static_assert(OFF_HP == OFF_POS + T4 && OFF_ST == OFF_HP + T4 && OFF_TICK == OFF_ST + T4 && OFF_EP == OFF_TICK + T4 && kTile <= 256,
               "the five 4-byte slices are the rows of the tensor-map box, in plane order");
@@ -226,7 +237,7 @@ __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
 k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap planes5, const int use_map,
             const void* __restrict__ moves_v, uint8_t* __restrict__ result,
             unsigned int n_tiles, unsigned int* __restrict__ sched, unsigned int* __restrict__ flags,
-            int16_t* __restrict__ obs, int obs_radius, uint2* __restrict__ events, int bots ORX_TRACE_PARAM)
+            int16_t* __restrict__ obs, int obs_radius, uint2* __restrict__ events, int bots, unsigned int tiles_per_cta ORX_TRACE_PARAM)
 {
     static_assert(OBS || TICK, "nothing to do");
     static_assert(!EV || (TICK && !OBS), "the event log rides with the plain tick");
@@ -235,12 +246,16 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     constexpr int kStages = kPipeStages<OBS, EV, NPC>;             // shadows the namespace constant on purpose
     constexpr uint32_t STAGE_BYTES = kPipeStageBytes<OBS, EV, NPC>;
     const uint32_t npc2 = NPC ? 2u * (uint32_t)P.n_npc * kTile : 0u;     // bytes of a tile's npc_pos / npc_hp slice; npc_depth: twice that
-    constexpr uint32_t MV_BYTES = CMD == CMD_NIBBLES ? T1 : T2, LOAD_BYTES = PLANE_LOAD_BYTES + (TICK ? MV_BYTES : 0u);
+    constexpr uint32_t MV_BYTES = CMD == CMD_BITS ? 0u : CMD == CMD_NIBBLES ? T1 : T2, LOAD_BYTES = PLANE_LOAD_BYTES + (TICK ? MV_BYTES : 0u);
+    static_assert(CMD != CMD_BITS || (TICK && !OBS && !EV && !NPC), "bit-packed streams ride with the plain tick");
     const uint8_t* moves = static_cast<const uint8_t*>(moves_v);
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stages = smem;                                             // kStages * STAGE_BYTES
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);   // full[kStages], done[kStages]
-    uint8_t* tiles_sm = smem + kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes + kTicketBytes;
+    constexpr uint32_t kBitsBytes = CMD == CMD_BITS ? kBitsSmemBytes : 0u;
+    const uint32_t bits0 = smem_addr(smem + kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes + kTicketBytes);
+    const uint32_t cmdbar = bits0, cmd0 = bits0 + 16u, res0 = cmd0 + kBitsCmdBytes;      // CMD_BITS only
+    uint8_t* tiles_sm = smem + kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes + kTicketBytes + kBitsBytes;
     const uint32_t full0 = smem_addr(bars), done0 = smem_addr(bars + kStages);
     const uint32_t tidx0 = smem_addr(bars + 2 * kStages);      // tile index published with each stage
     const uint32_t tk0 = tidx0 + kTileIdxBytes;                // flag mode: this CTA's ticket of each of its tiles
@@ -258,6 +273,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             mbar_init(full0 + 8 * s, 1);
             mbar_init(done0 + 8 * s, kTile / 32);
         }
+        if (CMD == CMD_BITS) mbar_init(cmdbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __shared__ CmdEntry lut[256];
@@ -271,6 +287,15 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     __syncthreads();
 
     constexpr uint32_t NONE = 0xFFFFFFFFu;    // published instead of a tile index: no more work for this CTA
+    // Static assignment: tile of this CTA's it-th iteration. Strided over the grid, or (CMD_BITS) a contiguous run.
+    auto tile_at = [&](unsigned int it) -> uint32_t {
+        if (CMD == CMD_BITS) {
+            const uint64_t t = (uint64_t)blockIdx.x * tiles_per_cta + it;
+            return it < tiles_per_cta && t < n_tiles ? (uint32_t)t : NONE;
+        }
+        const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
+        return t < n_tiles ? (uint32_t)t : NONE;
+    };
 
     if (tid >= kTile) {
         // ------------------------------------------------------------ producer (one thread)
@@ -280,18 +305,14 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             // that depends on it has been issued, i.e. the atomic has been performed at the L2 before any thread
             // of this CTA lets the dependents go.
             const unsigned int ln = tid - kTile;
-            const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)ln * gridDim.x;
-            if (t < n_tiles) sts_u32(tk0 + 4u * ln, atomicAdd(flags + 2 * t, 1u));
+            const uint32_t t = tile_at(ln);
+            if (t != NONE) sts_u32(tk0 + 4u * ln, atomicAdd(flags + 2 * (size_t)t, 1u));
             __syncwarp();
         }
         if (tid != kTile) return;
         if (ORX_PIPE_PDL && flagged) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (use_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&planes5) : "memory");     // descriptor fetch off the first copy's path
         // flag mode: tile of this CTA's it-th iteration, its serving word, and the hand-over in both directions
-        auto tile_at = [&](unsigned int it) -> uint32_t {
-            const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
-            return t < n_tiles ? (uint32_t)t : 0xFFFFFFFFu;
-        };
         auto peek = [&](uint32_t tile) -> uint32_t { return tile != 0xFFFFFFFFu ? ld_flag(flags + 2 * (size_t)tile + 1) : 0u; };
         auto await = [&](uint32_t tile, unsigned int it, uint32_t seen) {      // seen: an earlier peek of the tile's serving word
             const uint32_t want = lds_u32(tk0 + 4u * it);
@@ -328,8 +349,19 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             bulk_load(base + OFF_STATUS, P.status + g, T1, bar);
             if (TICK) bulk_load(base + OFF_MOVES, moves + g * (MV_BYTES / kTile), MV_BYTES, bar);
         };
+        // CMD_BITS: the commands of ALL this CTA's tiles, one bulk copy (over PCIe when the caller's buffer is pinned
+        // host memory), in flight while the first planes are fetched.
+        auto fetch_commands = [&]() {
+            if (CMD == CMD_BITS) {
+                const uint64_t first = (uint64_t)blockIdx.x * tiles_per_cta;
+                const uint32_t cnt = (uint32_t)(n_tiles - first < tiles_per_cta ? n_tiles - first : tiles_per_cta);
+                mbar_expect_tx(cmdbar, cnt * kCmdBitsTile);
+                bulk_load(cmd0, moves + first * kCmdBitsTile, cnt * kCmdBitsTile, cmdbar);
+            }
+        };
         bool ended = false;
         if (flagged) {
+            fetch_commands();
             // Prologue, flag mode: look at the serving words of the first kStages tiles in one go, then start
             // each tile's loads as soon as the previous launch on this state has handed it over.
             uint32_t seen[kStages];
@@ -353,8 +385,8 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
         // 1: 12.7, 2: 12.4, 3: 12.6, 4: 12.9 -- more than two compete with the previous grid's last loads.)
         if (ORX_PIPE_PDL) {
             for (unsigned int it = 0; it < (unsigned)ORX_PIPE_PREFETCH && it < (unsigned)kStages; ++it) {
-                const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
-                if (t >= n_tiles) break;
+                const uint32_t t = tile_at(it);
+                if (t == NONE) break;
                 const size_t g = (size_t)t * kTile;
                 if (use_map) {
                     tensor_prefetch_l2_2d(&planes5, (uint32_t)g, 0u);
@@ -374,11 +406,11 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
         if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // all earlier work in the stream is complete and visible
 #endif
         ORX_TRACE(trace_slot, 1);
+        fetch_commands();
         // Prologue: the first kStages tiles of a CTA are fixed, so its loads start without a round trip
         // to the counter.
         for (unsigned int it = 0; it < (unsigned)kStages && !ended; ++it) {
-            const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
-            const uint32_t tile = t < n_tiles ? (uint32_t)t : NONE;
+            const uint32_t tile = tile_at(it);
             issue(it, tile);
             ended = tile == NONE;
         }
@@ -433,7 +465,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                 }
                 bulk_store(P.depth + g, base + OFF_DEPTH, T8);
                 bulk_store(P.status + g, base + OFF_STATUS, T1);
-                bulk_store(result + g, base + OFF_RESULT, T1);
+                if (CMD != CMD_BITS) bulk_store(result + g, base + OFF_RESULT, T1);
             }
             if (OBS) bulk_store(obs + g * (2 * ORX_OBS_LEN), base + OFF_OBS, OBS_BYTES);
             if (EV) bulk_store(events + g * ORX_MAX_EVENTS_BASE, base + OFF_EV, EV_BYTES);
@@ -456,9 +488,13 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             constexpr unsigned int kLag = kLazy ? 1u : 0u;
             if (!ended && (!kLazy || it >= 1u)) {
                 const unsigned int nit = it - kLag + kStages;
-                const uint64_t next = sched != nullptr ? (uint64_t)dyn_base + settle(held)
-                                                       : (uint64_t)blockIdx.x + (uint64_t)nit * gridDim.x;
-                const uint32_t nt = next < n_tiles ? (uint32_t)next : NONE;
+                uint32_t nt;
+                if (sched != nullptr) {
+                    const uint64_t next = (uint64_t)dyn_base + settle(held);
+                    nt = next < n_tiles ? (uint32_t)next : NONE;
+                } else {
+                    nt = tile_at(nit);
+                }
                 if (kLazy) bulk_wait_read_but_last();      // every group but the one just committed has been read out
                 else bulk_wait_read_all();                 // the stage has been read out: safe to overwrite
                 if (flagged && nt != NONE) await(nt, nit, held);
@@ -470,6 +506,10 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                 }
             }
             ++n_done;
+        }
+        if (CMD == CMD_BITS && n_done != 0u) {       // every consumer has arrived on the last tile's barrier: the result block is complete
+            bulk_store(result + (size_t)blockIdx.x * tiles_per_cta * kResBitsTile, res0, n_done * kResBitsTile);
+            bulk_commit();
         }
         if (flagged) {
             // The last tiles: their stores must have completed before the next launch may read them. Then the
@@ -518,7 +558,14 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
         unpack_lane(L, pos, hpw, dep, stw, tick, ep);
         if (TICK) {
             uint32_t mv;
-            if (CMD == CMD_NIBBLES) {
+            if (CMD == CMD_BITS) {
+                if (it == 0) mbar_wait(cmdbar, 0u);
+                // game g of the tile: bits [5g, 5g + 5) of the tile's 160 bytes; v = (p1 - 1) * 5 + (p2 - 1), 25..31 = both Stay
+                const uint32_t a = cmd0 + it * kCmdBitsTile + ((tid * 5u) >> 3);
+                const uint32_t v = ((lds_u8(a) | (lds_u8(a + 1u) << 8)) >> ((tid * 5u) & 7u)) & 31u;
+                const uint32_t p1 = v / 5u;
+                mv = v < 25u ? ((p1 + 1u) | ((v - 5u * p1 + 1u) << 8)) : 0u;
+            } else if (CMD == CMD_NIBBLES) {
                 const uint32_t c = lds_u8(b1 + OFF_MOVES);
                 mv = (c & 15u) | ((c >> 4) << 8);
             } else {
@@ -558,7 +605,21 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                 sts_s32x2(b8 + OFF_DEPTH, L.d1, L.d2);
                 sts_u8(b1 + OFF_STATUS, (uint32_t)new_status);
             }
-            sts_u8(b1 + OFF_RESULT, (uint32_t)res);
+            if (CMD == CMD_BITS) {
+                // 2 bits per game (result - 1): two ballots give the low and the high bit of the warp's 32 games,
+                // lanes 0 / 1 interleave one 16-game half each into a word of the CTA's result block
+                const uint32_t r = (uint32_t)(res - 1) & 3u;
+                const uint32_t lo = __ballot_sync(0xffffffffu, (r & 1u) != 0u), hi = __ballot_sync(0xffffffffu, (r & 2u) != 0u);
+                const uint32_t half = tid & 1u;
+                auto spread = [](uint32_t x) {
+                    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu;
+                    x = (x | (x << 2)) & 0x33333333u; return (x | (x << 1)) & 0x55555555u;
+                };
+                const uint32_t word = spread((lo >> (16u * half)) & 0xFFFFu) | (spread((hi >> (16u * half)) & 0xFFFFu) << 1);
+                if ((tid & 31u) < 2u) sts_u32(res0 + it * kResBitsTile + (tid >> 5) * 8u + half * 4u, word);
+            } else {
+                sts_u8(b1 + OFF_RESULT, (uint32_t)res);
+            }
             ev.finish();                             // unused slots (all four of a frozen lane) read ORX_EV_NONE
         }
         if (OBS) {                                   // what each player sees of the state as it now is
@@ -577,10 +638,11 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     if (tid == 0) ORX_TRACE(trace_slot, 6);
 }
 
-template <bool OBS, bool EV = false, bool NPC = false>
+template <bool OBS, bool EV = false, bool NPC = false, bool BITS = false>
 constexpr size_t pipe_smem_bytes(int fixed_tiles)
 {
-    return (size_t)kPipeStages<OBS, EV, NPC> * kPipeStageBytes<OBS, EV, NPC> + 2 * kPipeStages<OBS, EV, NPC> * 8 + kTileIdxBytes + kTicketBytes + (size_t)fixed_tiles;
+    return (size_t)kPipeStages<OBS, EV, NPC> * kPipeStageBytes<OBS, EV, NPC> + 2 * kPipeStages<OBS, EV, NPC> * 8 + kTileIdxBytes + kTicketBytes +
+           (BITS ? kBitsSmemBytes : 0u) + (size_t)fixed_tiles;
 }
 
 }  // namespace orx

@@ -168,6 +168,25 @@ class BatchedUpdater:
             self._advance_order(gs, events)
         return result, events
 
+    def update_bits(self, game_state: BatchedGameState, cmd5: torch.Tensor, out: typing.Optional[torch.Tensor] = None):
+        """One tick told and answered in the fewest bytes (``orx_step_bits``): ``cmd5`` is the CUDA uint8 tensor of
+        ``_abi.cmd5_bytes(N)`` bytes ``logic.moves.pack_moves5`` produces (5 bits per game), the return value the
+        CUDA uint8 tensor of ``_abi.res2_bytes(N)`` bytes ``logic.moves.unpack_results2`` reads (2 bits per game).
+        Same tick as ``update``; no NPC slots."""
+        gs = game_state
+        _require_cuda(gs)
+        nb_in, nb_out = _abi.cmd5_bytes(gs.n), _abi.res2_bytes(gs.n)
+        if (not isinstance(cmd5, torch.Tensor) or not cmd5.is_cuda or cmd5.dtype != torch.uint8 or tuple(cmd5.shape) != (nb_in,)
+                or not cmd5.is_contiguous()):
+            raise ValueError(f'cmd5 must be a contiguous CUDA uint8 tensor of {nb_in} bytes')
+        cfg, st = self._cfg(gs)
+        res2 = out if out is not None else torch.empty((nb_out,), dtype=torch.uint8, device=gs.device)
+        with _on_device(gs.device):
+            rc = _lib.lib().orx_step_bits(C.byref(cfg), C.byref(st), cmd5.data_ptr(), res2.data_ptr(), gs.n,
+                                          gs.game_id_base, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_step_bits')
+        return res2
+
     def _update_host(self, gs, moves_host, out, packed=False):
         cfg, st = self._cfg(gs)
         if not hasattr(self, '_stage') or self._stage[0].shape[0] != gs.n or self._stage[0].device != gs.device:
@@ -183,7 +202,7 @@ class BatchedUpdater:
         return result_host
 
     def host_stepper(self, game_state: BatchedGameState, moves_host: torch.Tensor, result_host: torch.Tensor,
-                     sync: bool = True):
+                     sync: bool = True, bits: bool = False):
         """Binds one game state and a pair of HOST buffers (pin them: ``pin_memory()``) and returns
         ``step()``: one call = one tick with the commands currently in ``moves_host``; when it returns,
         ``result_host`` holds the tick's UpdateResult codes (``orx_step_host_sync``). This is
@@ -193,9 +212,16 @@ class BatchedUpdater:
         ``moves_host`` is uint8[N,2] (p1, p2) or, nibble-packed, uint8[N] with ``p1 | p2 << 4``
         (``orx_step_host_packed_sync``: half the PCIe bytes). ``sync=False`` only enqueues the tick
         (``orx_step_host`` / ``orx_step_host_packed``): the caller synchronises, e.g. with an event,
-        before it reads ``result_host`` -- for loops that keep several independent batches in flight."""
+        before it reads ``result_host`` -- for loops that keep several independent batches in flight.
+
+        ``bits=True``: the bit-packed streams of ``orx_step_host_bits[_sync]`` -- ``moves_host`` holds
+        ``_abi.cmd5_bytes(N)`` bytes from ``logic.moves.pack_moves5`` (5 bits per game), ``result_host`` receives
+        ``_abi.res2_bytes(N)`` bytes for ``logic.moves.unpack_results2`` (2 bits per game): 0.875 bytes per game
+        over PCIe instead of 2 or 3, in one transaction per CTA each way."""
         gs = game_state
         _require_cuda(gs)
+        if bits:
+            return self._host_stepper_bits(gs, moves_host, result_host, sync)
         packed = moves_host.dim() == 1
         if (moves_host.is_cuda or result_host.is_cuda or moves_host.dtype != torch.uint8 or result_host.dtype != torch.uint8
                 or tuple(moves_host.shape) not in ((gs.n, 2), (gs.n,)) or tuple(result_host.shape) != (gs.n,)
@@ -210,6 +236,31 @@ class BatchedUpdater:
                 C.c_void_p(stage[0].data_ptr()), C.c_void_p(stage[1].data_ptr()), C.c_int64(gs.n),
                 C.c_uint64(gs.game_id_base), C.c_void_p(_stream_ptr(gs.device)))
         keep = (cfg, st, stage, moves_host, result_host, gs)
+        dev_index = gs.device.index or 0
+
+        def step():
+            if torch.cuda.current_device() != dev_index:
+                torch.cuda.set_device(dev_index)
+            rc = fn(*args)
+            if rc != 0:
+                _lib.check(rc, name)
+            return keep[4]
+        return step
+
+    def _host_stepper_bits(self, gs, cmd5_host, res2_host, sync):
+        nb_in, nb_out = _abi.cmd5_bytes(gs.n), _abi.res2_bytes(gs.n)
+        if (cmd5_host.is_cuda or res2_host.is_cuda or cmd5_host.dtype != torch.uint8 or res2_host.dtype != torch.uint8
+                or tuple(cmd5_host.shape) != (nb_in,) or tuple(res2_host.shape) != (nb_out,)
+                or not cmd5_host.is_contiguous() or not res2_host.is_contiguous()):
+            raise ValueError(f'need contiguous CPU uint8 tensors of {nb_in} and {nb_out} bytes')
+        cfg, st = self._cfg(gs)
+        stage = (torch.empty((nb_in,), dtype=torch.uint8, device=gs.device), torch.empty((nb_out,), dtype=torch.uint8, device=gs.device))
+        name = 'orx_step_host_bits' + ('_sync' if sync else '')
+        fn = getattr(_lib.lib(), name)
+        args = (C.byref(cfg), C.byref(st), C.c_void_p(cmd5_host.data_ptr()), C.c_void_p(res2_host.data_ptr()),
+                C.c_void_p(stage[0].data_ptr()), C.c_void_p(stage[1].data_ptr()), C.c_int64(gs.n),
+                C.c_uint64(gs.game_id_base), C.c_void_p(_stream_ptr(gs.device)))
+        keep = (cfg, st, stage, cmd5_host, res2_host, gs)
         dev_index = gs.device.index or 0
 
         def step():

@@ -202,3 +202,57 @@ def test_short_scratch_falls_back_to_grid_wait():
     torch.cuda.synchronize()
     assert np.array_equal(res.cpu().numpy(), _oracle_run(orc, mv))
     gu.assert_state_equal(gs, orc, 'header-only scratch')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bit-packed streams (orx_step_bits / orx_step_host_bits): 5 bits of command pair in, 2 bits of result out
+@pytest.mark.parametrize('n', [256 * 37, 256 * 37 + 91, 77, 131072 + 3])
+@pytest.mark.parametrize('flags', [0, _abi.PATH_NO_TILE_FLAGS])
+def test_bit_packed_streams_match_oracle(n, flags):
+    """Device-resident cmd5 / res2 streams, unsynchronised ticks; invalid codes are packed as Stay. Planes and
+    the unpacked results equal the oracle's (which is fed the plain codes)."""
+    from optimax_rogue_b200.logic.moves import pack_moves5, unpack_results2
+    ticks = 24
+    cfg = SimConfig(max_ticks=19, seed=314, auto_reset=True, width=8, height=7, path_flags=flags)
+    gs, upd, orc = gu.make_pair(cfg, n)
+    rng = np.random.default_rng(n)
+    mv = _moves(rng, ticks, n)
+    nb_in, nb_out = _abi.cmd5_bytes(n), _abi.res2_bytes(n)
+    pitch_in, pitch_out = -(-nb_in // 16) * 16, -(-nb_out // 16) * 16
+    cmd = torch.zeros((ticks, pitch_in), dtype=torch.uint8)
+    for t in range(ticks):
+        cmd[t, :nb_in] = torch.from_numpy(pack_moves5(mv[t, :, 0], mv[t, :, 1]))
+    cmd = cmd.cuda()
+    res = torch.full((ticks, pitch_out), 0xEE, dtype=torch.uint8, device='cuda')
+    torch.cuda.synchronize()
+    for t in range(ticks):
+        upd.update_bits(gs, cmd[t, :nb_in], out=res[t, :nb_out])
+    torch.cuda.synchronize()
+    want = _oracle_run(orc, mv)
+    got = res.cpu().numpy()
+    for t in range(ticks):
+        assert np.array_equal(unpack_results2(got[t, :nb_out], n), want[t]), t
+        if (2 * n) % 8:                                   # padding bits of the last byte are zero
+            assert got[t, nb_out - 1] >> ((2 * n) % 8) == 0
+    gu.assert_state_equal(gs, orc, 'bit-packed streams')
+
+
+@pytest.mark.parametrize('n', [256 * 50, 256 * 9 + 17])
+@pytest.mark.parametrize('staged', [False, True])
+def test_bit_packed_host_buffers(n, staged):
+    """The host-buffer tick with bit-packed streams: pinned buffers are read / written by the kernel over PCIe
+    (one bulk copy per CTA each way), ORX_PATH_HOST_STAGED forces the staged-copy path pageable buffers take."""
+    from optimax_rogue_b200.logic.moves import pack_moves5, unpack_results2
+    cfg = SimConfig(max_ticks=23, seed=99, auto_reset=True, path_flags=_abi.PATH_HOST_STAGED if staged else 0)
+    gs, upd, orc = gu.make_pair(cfg, n)
+    rng = np.random.default_rng(5)
+    cmd_host = torch.zeros((_abi.cmd5_bytes(n),), dtype=torch.uint8).pin_memory()
+    res_host = torch.zeros((_abi.res2_bytes(n),), dtype=torch.uint8).pin_memory()
+    step = upd.host_stepper(gs, cmd_host, res_host, sync=True, bits=True)
+    for t in range(30):
+        mv = rng.integers(1, 6, size=(n, 2), dtype=np.uint8)
+        cmd_host.copy_(torch.from_numpy(pack_moves5(mv[:, 0], mv[:, 1])))
+        step()                                            # synchronous: res_host is valid on return
+        want, _ = orc.step(mv, want_events=False)
+        assert np.array_equal(unpack_results2(res_host.numpy(), n), want), t
+    gu.assert_state_equal(gs, orc, 'host bit-packed')
