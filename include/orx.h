@@ -95,7 +95,9 @@ typedef struct OrxConfig {
     int32_t n_npc;              /* NPC slots in use, 0..ORX_MAX_NPC */
     uint64_t seed;              /* Philox key */
     /* ORX_DGEN_FIXED only (device pointers, shared by all games): */
-    const uint8_t* fixed_tiles;   /* uint8[width*height], x-major (tiles[x*height+y]), ORX_TILE_* */
+    const uint8_t* fixed_tiles;   /* uint8[width*height], x-major (tiles[x*height+y]), ORX_TILE_*. Immutable while a
+                                     tick that uses it is enqueued or running: a CTA stages the map when it starts,
+                                     which may be before earlier work in the stream has finished */
     const uint16_t* fixed_ground; /* flat indices of the Ground tiles in ascending (x-major) order */
     int32_t fixed_n_ground;
     int32_t fixed_stairs[2];      /* first StaircaseDown in x-major order, or ORX_NO_STAIRS */

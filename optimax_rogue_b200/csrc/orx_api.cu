@@ -484,6 +484,20 @@ int device_sms(int dev)
     return v;
 }
 
+// Tiles per CTA in flag mode: a function of the state's tile count, the device and the caller's override ONLY (never
+// of the kernel variant), because CTA b must own the same run of tiles in every launch on the state. Default: about
+// one CTA per SM and launch -- consecutive launches share the SMs, so a launch need not fill the machine on its own,
+// and long runs keep each CTA's pipeline full (measured: profiles/r02_batch_sweep.json) -- in whole chunks, at most
+// kBitsMaxTiles tiles (a CTA holds the bit-packed commands of its whole run).
+unsigned int flag_tiles_per_cta(unsigned int n_tiles, int sms, int override_tiles)
+{
+    const unsigned int n_chunks = (n_tiles + kChunk - 1) / kChunk;
+    unsigned int r = override_tiles > 0 ? ((unsigned int)override_tiles + kChunk - 1) / kChunk : (n_chunks + sms - 1) / (unsigned int)sms;
+    if (r < 1) r = 1;
+    if (r > kBitsMaxTiles / kChunk) r = kBitsMaxTiles / kChunk;
+    return r * kChunk;
+}
+
 // Flag mode is a property of the STATE (its scratch size and its number of tiles), never of the kernel variant:
 // every pipelined launch on a state must make the same choice, because a flag-mode launch does not wait for an
 // earlier grid-wait-mode launch on the same planes.
@@ -493,20 +507,18 @@ TileCtl tile_ctl(const OrxConfig* cfg, const OrxState* st, unsigned int n_tiles)
     if (st->sched == nullptr || !aligned(st->sched, 16)) return c;
     int dev = 0;
     cudaGetDevice(&dev);
+    const int sms = device_sms(dev);
     const uint64_t need = (uint64_t)ORX_SCHED_HEADER_WORDS + 2ull * n_tiles;
-    if (!(cfg->path_flags & ORX_PATH_NO_TILE_FLAGS) && st->sched_words >= need &&
-        n_tiles <= (unsigned int)(kMaxTilesPerCtaFlagged * device_sms(dev))) {
+    // beyond kBitsMaxTiles tiles for each of 3 CTAs per SM a launch fills the machine several times over and the
+    // boundary between launches no longer matters: grid-wait mode
+    if (!(cfg->path_flags & ORX_PATH_NO_TILE_FLAGS) && st->sched_words >= need && n_tiles <= (unsigned int)(kBitsMaxTiles * 3 * sms)) {
         c.flags = st->sched + ORX_SCHED_HEADER_WORDS;
-        c.tiles_per_cta = (int)((cfg->path_flags >> ORX_PATH_TILES_PER_CTA_SHIFT) & 255u);
+        c.tiles_per_cta = (int)flag_tiles_per_cta(n_tiles, sms, (int)((cfg->path_flags >> ORX_PATH_TILES_PER_CTA_SHIFT) & 255u));
         return c;
     }
     if (!(cfg->path_flags & ORX_PATH_STATIC_TILES) && st->sched_words >= ORX_SCHED_HEADER_WORDS) c.counter = st->sched;
     return c;
 }
-
-#ifndef ORX_PIPE_TILES_PER_CTA
-#define ORX_PIPE_TILES_PER_CTA 4
-#endif
 
 template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, bool NPC = false>
 int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, const TileCtl& ctl,
@@ -550,22 +562,17 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     const unsigned int sms = (unsigned int)device_sms(dev);
     unsigned int grid = sms * (unsigned int)per_sm;       // persistent: every CTA resident
     if (grid > n_tiles) grid = n_tiles;
-    if (ctl.flags != nullptr) {
-        // Flag mode: a launch need not fill the machine on its own, the launches before and after it run beside
-        // it. A few tiles per CTA keep every CTA's pipeline busy and leave CTA slots to the neighbours; never
-        // fewer CTAs than SMs, never more than kMaxTilesPerCtaFlagged tiles per CTA (tile_ctl checked n_tiles).
-        const unsigned int tpc = (unsigned int)(ctl.tiles_per_cta > 0 ? ctl.tiles_per_cta : ORX_PIPE_TILES_PER_CTA);
-        unsigned int g = (n_tiles + tpc - 1) / tpc;
-        const unsigned int floor_g = n_tiles < sms ? n_tiles : sms;
-        if (g < floor_g) g = floor_g;
-        if (g < grid) grid = g;
-    }
     unsigned int tiles_per_cta = 0;
-    if (BITS) {      // contiguous runs of tiles per CTA, every CTA at least one; the caller keeps n_tiles <= kBitsMaxTiles * grid
+    if (ctl.flags != nullptr) {
+        // Flag mode: contiguous runs of tile_ctl's length, whatever this variant's occupancy (CTAs beyond the
+        // resident ones simply start later; nothing in a launch waits for a CTA of the same launch)
+        tiles_per_cta = (unsigned int)ctl.tiles_per_cta;
+        grid = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    } else if (BITS) {      // contiguous runs, every CTA at least one tile; the caller keeps n_tiles <= kBitsMaxTiles * grid
         tiles_per_cta = (n_tiles + grid - 1) / grid;
         grid = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
-        if (tiles_per_cta > kBitsMaxTiles) return ORX_ERR_UNSUPPORTED;
     }
+    if (BITS && tiles_per_cta > kBitsMaxTiles) return ORX_ERR_UNSUPPORTED;
     alignas(64) CUtensorMap planes5;
     int use_map = 0;
     if (!ctl.no_tensor_map) use_map = planes5_map(P, n_tiles, &planes5) ? 1 : 0;
@@ -699,7 +706,7 @@ int step_bits_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5
             const unsigned int nt = n_tiles - t0 < max_tiles ? n_tiles - t0 : max_tiles;
             const Params C = t0 == 0 && nt == n_tiles ? P : offset_params(P, (int64_t)t0 * kTile, (int64_t)nt * kTile);
             TileCtl c = ctl;
-            if (c.flags != nullptr) c.flags += 2 * (size_t)t0;
+            if (c.flags != nullptr) c.flags += 2 * (size_t)(t0 / kChunk);
             const uint8_t* cm = cmd5 + (size_t)t0 * kCmdBitsTile;
             uint8_t* rs = res2 + (size_t)t0 * kResBitsTile;
             const int rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BITS, false, true>(C, cm, rs, nt, 0, c, nullptr, -1, s)

@@ -26,15 +26,20 @@
 // Between launches (two modes, chosen by the host per state, see launch_pipe):
 //   grid-wait mode  PDL lets the next grid's CTAs become resident while this grid drains; until
 //                   griddepcontrol.wait releases them they prefetch their first two tiles into L2.
-//   flag mode       (flags != NULL) consecutive launches overlap tile by tile. Every 256-game tile of a state
-//                   has two words in OrxState.sched: next (tickets handed out) and serving (passes completed).
-//                   A CTA takes the tickets of ALL its tiles (static stride) before it lets dependents launch,
-//                   so tickets are in launch order; it loads tile t only once serving[t] equals its ticket and
-//                   sets serving[t] = ticket + 1 once its bulk stores of t have COMPLETED. There is no grid-wide
-//                   wait before the first load: step k+1 starts on tile t as soon as step k has written tile t,
-//                   and launches on different states do not wait for each other at all. The producer runs
-//                   griddepcontrol.wait last, before it exits, so that "this grid is complete" still implies
-//                   "every earlier grid in the stream is complete" for whatever the caller enqueues next.
+//   flag mode       (flags != NULL) consecutive launches overlap. A CTA owns a CONTIGUOUS run of tiles_per_cta
+//                   tiles (the same run in every launch on the state), handed over in CHUNKS of kChunk tiles; each
+//                   chunk of the state has two words in OrxState.sched: next (tickets handed out) and serving
+//                   (passes completed). A CTA draws the tickets of ALL its chunks before it lets dependents launch,
+//                   so tickets are in launch order; it loads a chunk once serving equals its ticket and releases
+//                   serving = ticket + 1 (gpu scope) once the chunk's bulk stores have completed. There is no
+//                   grid-wide wait before the first load: tick k+1 follows tick k through the tiles one chunk
+//                   behind, and launches on different states do not wait for each other at all. The producer runs
+//                   griddepcontrol.wait last, before it exits, so that "this grid is complete" still implies "every
+//                   earlier grid in the stream is complete" for whatever the caller enqueues next.
+//                   Why chunks: the release is MEMBAR.ALL.GPU in the one thread that moves data (0.65 us); per tile
+//                   it cost more than the overlap gained (19.0 against 12.5 us per 2^20-game step), and without it
+//                   the completion of a bulk store is only visible to its own thread -- relaxed flags gave wrong
+//                   planes in long unsynchronised runs (profiles/r02_ab_flag_fences.log).
 #pragma once
 #include <cuda.h>             // CUtensorMap (type only; the encoder is looked up at run time)
 #include <cuda_runtime.h>
@@ -66,7 +71,6 @@ constexpr int kTile = ORX_PIPE_TILE;  // games per tile = compute threads per CT
 constexpr int kStages = ORX_PIPE_STAGES;
 constexpr int kPipeThreads = kTile + 32;   // + one producer warp
 constexpr uint32_t kTileIdxBytes = ((uint32_t)kStages * 4u + 15u) & ~15u;   // per-stage tile index words
-constexpr uint32_t kTicketBytes = 4u * 32u;                                   // flag mode: tickets of up to 32 tiles per CTA
 #ifndef ORX_PIPE_OBS_STAGES
 #define ORX_PIPE_OBS_STAGES 3
 #endif
@@ -189,30 +193,20 @@ __device__ __forceinline__ void sts_s32x2(uint32_t a, int x, int y) { asm volati
 __device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // flag mode: per-tile hand-over between consecutive launches on one state
-// The hand-over words are read and written with RELAXED gpu-scope accesses, ordered against the bulk copies by
-// completion, not by fences: a tile's serving word is stored only after cp.async.bulk.wait_group has reported
-// the tile's bulk stores complete (performed at the L2, the single point of coherence: every address has one
-// home slice, and neither the bulk engine nor these strong accesses go through an L1), and a tile's bulk loads
-// are issued only after a load of its serving word has returned the awaited ticket. A release store here is
-// MEMBAR.ALL.GPU + ERRBAR in front of the STG and also waits for the CTA's bulk loads in flight: measured
-// 19.0 instead of 12.0 us per 2^20-game step, 3.27 instead of 2.58 us at 2^17 (profiles/r02_ab_flag_fences.log);
-// an acquire load adds a CCTL.IVALL that blocks the thread on the round trip (+1.1 us at 2^20).
-// -DORX_FLAG_STRICT_FENCES builds the release/acquire form (same results, tests/test_gpu_tile_flags.py).
-#ifdef ORX_FLAG_STRICT_FENCES
-__device__ __forceinline__ uint32_t ld_flag(const unsigned int* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_flag(unsigned int* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-#else
-__device__ __forceinline__ uint32_t ld_flag(const unsigned int* p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_flag(unsigned int* p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-#endif
-// generic-proxy flag access <-> async-proxy bulk copies of the tile (CCTL.IVALL + FENCE.VIEW.ASYNC.G: no measurable cost)
+// flag mode hand-over: acquire / release at gpu scope (LDG.STRONG.GPU + CCTL.IVALL, MEMBAR.ALL.GPU + STG.STRONG.GPU).
+// cp.async.bulk.wait_group makes the bulk stores visible to the WAITING thread only; the release is what makes them
+// visible to the CTA of the next launch (relaxed accesses here gave wrong planes in long unsynchronised runs).
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// generic-proxy flag access <-> async-proxy bulk copies (CCTL.IVALL + FENCE.VIEW.ASYNC.G: no measurable cost)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-#ifndef ORX_PIPE_FLAG_LAG
-#define ORX_PIPE_FLAG_LAG 2          // a tile's flag is published once all but this many later store groups have completed
+#ifndef ORX_PIPE_CHUNK
+#define ORX_PIPE_CHUNK 4             // tiles per hand-over chunk in flag mode
 #endif
-constexpr int kFlagLag = ORX_PIPE_FLAG_LAG;
-constexpr int kMaxTilesPerCtaFlagged = 32;   // one ticket per lane of the producer warp
+constexpr int kChunk = ORX_PIPE_CHUNK;
+constexpr int kMaxChunksPerCta = 32;          // one ticket per lane of the producer warp
+constexpr uint32_t kTicketBytes = 4u * kMaxChunksPerCta;
 
 #ifdef ORX_PIPE_TRACE
 // Tuning aid (tools/pipetrace.py, separate build): per-CTA %globaltimer stamps of the last 16 launches.
@@ -258,7 +252,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     uint8_t* tiles_sm = smem + kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes + kTicketBytes + kBitsBytes;
     const uint32_t full0 = smem_addr(bars), done0 = smem_addr(bars + kStages);
     const uint32_t tidx0 = smem_addr(bars + 2 * kStages);      // tile index published with each stage
-    const uint32_t tk0 = tidx0 + kTileIdxBytes;                // flag mode: this CTA's ticket of each of its tiles
+    const uint32_t tk0 = tidx0 + kTileIdxBytes;                // flag mode: this CTA's ticket of each of its chunks
     const uint32_t stage0 = smem_addr(stages);
     const unsigned int tid = threadIdx.x;
     const bool flagged = flags != nullptr;
@@ -287,9 +281,9 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     __syncthreads();
 
     constexpr uint32_t NONE = 0xFFFFFFFFu;    // published instead of a tile index: no more work for this CTA
-    // Static assignment: tile of this CTA's it-th iteration. Strided over the grid, or (CMD_BITS) a contiguous run.
+    // Static assignment: tile of this CTA's it-th iteration. Strided over the grid, or (flag mode, CMD_BITS) a contiguous run.
     auto tile_at = [&](unsigned int it) -> uint32_t {
-        if (CMD == CMD_BITS) {
+        if (CMD == CMD_BITS || flagged) {
             const uint64_t t = (uint64_t)blockIdx.x * tiles_per_cta + it;
             return it < tiles_per_cta && t < n_tiles ? (uint32_t)t : NONE;
         }
@@ -299,29 +293,32 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
 
     if (tid >= kTile) {
         // ------------------------------------------------------------ producer (one thread)
+        // flag mode: chunk c of this CTA = its tiles [c kChunk, (c+1) kChunk); global chunk index = first tile / kChunk
+        // (tiles_per_cta is a multiple of kChunk, so runs start on chunk boundaries)
+        const size_t chunk0 = (size_t)blockIdx.x * (tiles_per_cta / (unsigned)kChunk);
         if (flagged) {
-            // Lane k of the producer warp draws the ticket of this CTA's k-th tile (static stride): one atomic
-            // instruction, one round trip for all of them. The value has arrived when the shared-memory store
-            // that depends on it has been issued, i.e. the atomic has been performed at the L2 before any thread
-            // of this CTA lets the dependents go.
-            const unsigned int ln = tid - kTile;
-            const uint32_t t = tile_at(ln);
-            if (t != NONE) sts_u32(tk0 + 4u * ln, atomicAdd(flags + 2 * (size_t)t, 1u));
+            // Lane c of the producer warp draws the ticket of this CTA's chunk c: one atomic instruction, one round
+            // trip for all of them. The value has arrived when the shared-memory store that depends on it has been
+            // issued, i.e. the atomic has been performed at the L2 before this CTA lets the dependents go -- which
+            // keeps the tickets of consecutive launches in launch order.
+            const unsigned int c = tid - kTile;
+            if (tile_at(c * (unsigned)kChunk) != NONE) sts_u32(tk0 + 4u * c, atomicAdd(flags + 2 * (chunk0 + c), 1u));
             __syncwarp();
         }
         if (tid != kTile) return;
         if (ORX_PIPE_PDL && flagged) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (use_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&planes5) : "memory");     // descriptor fetch off the first copy's path
-        // flag mode: tile of this CTA's it-th iteration, its serving word, and the hand-over in both directions
-        auto peek = [&](uint32_t tile) -> uint32_t { return tile != 0xFFFFFFFFu ? ld_flag(flags + 2 * (size_t)tile + 1) : 0u; };
-        auto await = [&](uint32_t tile, unsigned int it, uint32_t seen) {      // seen: an earlier peek of the tile's serving word
-            const uint32_t want = lds_u32(tk0 + 4u * it);
-            while (seen != want) seen = ld_flag(flags + 2 * (size_t)tile + 1);
+        auto peek = [&](unsigned int c) -> uint32_t {        // serving word of this CTA's chunk c (0 beyond its run)
+            return tile_at(c * (unsigned)kChunk) != NONE ? ld_acquire_gpu(flags + 2 * (chunk0 + c) + 1) : 0u;
+        };
+        auto await = [&](unsigned int c, uint32_t seen) {    // seen: an earlier peek at the chunk's serving word
+            const uint32_t want = lds_u32(tk0 + 4u * c);
+            while (seen != want) seen = ld_acquire_gpu(flags + 2 * (chunk0 + c) + 1);
             fence_proxy_async_global();         // the acquire (generic proxy) before the bulk loads (async proxy)
         };
-        auto publish = [&](unsigned int it) {      // this CTA's stores of its it-th tile have completed
+        auto publish = [&](unsigned int c) {                 // this CTA's bulk stores of its chunk c have completed
             fence_proxy_async_global();
-            st_flag(flags + 2 * (size_t)tile_at(it) + 1, lds_u32(tk0 + 4u * it) + 1u);
+            st_release_gpu(flags + 2 * (chunk0 + c) + 1, lds_u32(tk0 + 4u * c) + 1u);
         };
         // Publishes tile `tile` (or NONE) in the stage of iteration `it` and starts its loads.
         auto issue = [&](unsigned int it, uint32_t tile) {
@@ -360,22 +357,25 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             }
         };
         bool ended = false;
+        uint32_t held = 0;      // grid-wait mode: a ticket of the tile counter; flag mode: a peek at the next chunk's serving word
         if (flagged) {
             fetch_commands();
-            // Prologue, flag mode: look at the serving words of the first kStages tiles in one go, then start
-            // each tile's loads as soon as the previous launch on this state has handed it over.
-            uint32_t seen[kStages];
+            // Prologue, flag mode: a look at the serving words of the chunks the first kStages tiles belong to, then
+            // each tile's loads as soon as the launch before this one on the state has handed its chunk over.
+            constexpr unsigned int kPeek = (kStages + kChunk - 1) / kChunk;
+            uint32_t seen[kPeek + 1];
 #pragma unroll
-            for (int it = 0; it < kStages; ++it) seen[it] = peek(tile_at((unsigned)it));
+            for (unsigned int c = 0; c <= kPeek; ++c) seen[c] = peek(c);
 #pragma unroll
-            for (int it = 0; it < kStages; ++it) {
+            for (unsigned int it = 0; it < (unsigned)kStages; ++it) {
                 if (!ended) {
-                    const uint32_t tile = tile_at((unsigned)it);
-                    if (tile != NONE) await(tile, (unsigned)it, seen[it]);
-                    issue((unsigned)it, tile);
+                    const uint32_t tile = tile_at(it);
+                    if (tile != NONE && it % (unsigned)kChunk == 0u) await(it / (unsigned)kChunk, seen[it / (unsigned)kChunk]);
+                    issue(it, tile);
                     ended = tile == NONE;
                 }
             }
+            held = seen[kPeek];           // chunk kPeek holds tile kPeek * kChunk >= kStages: awaited in the refill loop
         } else {
 #if ORX_PIPE_PREFETCH
         // This CTA became resident when a CTA of the previous grid left, i.e. while that grid is still
@@ -432,11 +432,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             if (ticket == claims - 1u) atomicExch(sched, 0u);
             return ticket;
         };
-        uint32_t held = 0;      // grid-wait mode: a ticket of the tile counter; flag mode: a peek at the next tile's serving word
-        if (!ended) {
-            if (flagged) held = peek(tile_at((unsigned)kStages));
-            else if (sched != nullptr) held = draw();
-        }
+        if (!ended && !flagged && sched != nullptr) held = draw();
 #ifdef ORX_PIPE_TRACE
         unsigned int trace_tiles = 0;
         ORX_TRACE(trace_slot, 23);          // prologue loads issued
@@ -475,9 +471,11 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                 bulk_store(P.npc_depth + g * P.n_npc, base + OFF_NDEPTH, 2u * npc2);
             }
             bulk_commit();
-            if (flagged && it >= (unsigned)kFlagLag) {      // hand the tile of kFlagLag iterations ago to the next launch
-                bulk_wait_group<kFlagLag>();
-                publish(it - (unsigned)kFlagLag);
+            if (flagged && (it + 1u) % (unsigned)kChunk == 0u && it + 1u > (unsigned)kChunk) {
+                // a chunk's stores have just been committed: hand the chunk BEFORE it to the next launch (its kChunk
+                // store groups are the oldest pending ones; waiting for them does not wait for the current chunk)
+                bulk_wait_group<kChunk>();
+                publish((it + 1u) / (unsigned)kChunk - 2u);
             }
             // Refill. With a deep pipeline (>= 5 stages) one iteration late, i.e. the stage whose stores were
             // committed in the PREVIOUS iteration: waiting for the group just committed parks this thread
@@ -497,13 +495,13 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                 }
                 if (kLazy) bulk_wait_read_but_last();      // every group but the one just committed has been read out
                 else bulk_wait_read_all();                 // the stage has been read out: safe to overwrite
-                if (flagged && nt != NONE) await(nt, nit, held);
+                if (flagged && nt != NONE && nit % (unsigned)kChunk == 0u) {
+                    await(nit / (unsigned)kChunk, held);
+                    held = peek(nit / (unsigned)kChunk + 1u);
+                }
                 issue(nit, nt);
                 ended = nt == NONE;
-                if (!ended) {
-                    if (flagged) held = peek(tile_at(nit + 1u));
-                    else if (sched != nullptr) held = draw();
-                }
+                if (!ended && !flagged && sched != nullptr) held = draw();
             }
             ++n_done;
         }
@@ -512,10 +510,12 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             bulk_commit();
         }
         if (flagged) {
-            // The last tiles: their stores must have completed before the next launch may read them. Then the
+            // The chunks not handed over yet (the last one or two): their stores must have completed first. Then the
             // grid dependency, so that the completion of this grid implies the completion of every earlier one.
             bulk_wait_all();
-            for (unsigned int it = n_done > (unsigned)kFlagLag ? n_done - (unsigned)kFlagLag : 0u; it < n_done; ++it) publish(it);
+            const unsigned int n_chunks = (n_done + (unsigned)kChunk - 1u) / (unsigned)kChunk;
+            const unsigned int handed = n_done / (unsigned)kChunk > 0u ? n_done / (unsigned)kChunk - 1u : 0u;    // chunks published inside the loop
+            for (unsigned int c = handed; c < n_chunks; ++c) publish(c);
             if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
         } else {
             bulk_wait_read_all(); // shared memory may be released once the last stores have read it; the

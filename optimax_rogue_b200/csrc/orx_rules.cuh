@@ -132,6 +132,14 @@ __device__ __forceinline__ NpcView npc_view(const Params& P, unsigned int lane)
     return NpcView{P.npc_pos + 2 * j, P.npc_hp + j, P.npc_depth + j};
 }
 
+// A hit on an NPC slot: the plane is int16, the reference's health a Python int -- saturate instead of wrapping, so
+// that an NPC hit twice in one tick by hits near 32767 cannot come back to life.
+__device__ __forceinline__ void npc_hit(const NpcView* nv, int npc, int dmg)
+{
+    const int h = (int)nv->hp[npc] - dmg;
+    nv->hp[npc] = (int16_t)(h < -32768 ? -32768 : h);
+}
+
 __device__ __forceinline__ int npc_at(const Params& P, const NpcView* nv, int depth, int x, int y)
 {
     for (int k = 0; k < P.n_npc; ++k)
@@ -276,7 +284,7 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
             ev.emit(ORX_EV_COMBAT, idA + 1, idB + 1, dB == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_FLEE, dmgA);
         } else if (NPC && (npc = npc_at(P, nv, depA(), tA & 255u, tA >> 8)) >= 0) {
             const int dmgA = p2_first ? P.dmg1 : P.dmg0;
-            if (dmgA > 0) { nv->hp[npc] -= (int16_t)dmgA; ++cnt.hits; }
+            if (dmgA > 0) { npc_hit(nv, npc, dmgA); ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idA + 1, 3 + npc, ORX_FLAG_BLOCK, dmgA);
         } else if (is_stairs<DGEN>(P, tiles, tA, st & 0xFFFFu)) {
             const int nd = depA() + 1;
@@ -303,7 +311,7 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
             ev.emit(ORX_EV_COMBAT, idB + 1, idA + 1, dA == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_AMBUSH, dmgB);
         } else if (NPC && (npc = npc_at(P, nv, depB(), tB & 255u, tB >> 8)) >= 0) {
             const int dmgB = p2_first ? P.dmg0 : P.dmg1;
-            if (dmgB > 0) { nv->hp[npc] -= (int16_t)dmgB; ++cnt.hits; }
+            if (dmgB > 0) { npc_hit(nv, npc, dmgB); ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idB + 1, 3 + npc, ORX_FLAG_BLOCK, dmgB);
         } else if (is_stairs<DGEN>(P, tiles, tB, st >> 16)) {
             const int nd = depB() + 1;

@@ -212,18 +212,39 @@ class BatchedGameState:
         o.sched = torch.zeros_like(self.sched)
         return o
 
+    def _fingerprint(self):
+        """What a checkpoint must agree on to be loadable into this state (plain ints / tuples)."""
+        c = self.cfg
+        return {'n': self.n, 'seed': int(c.seed), 'width': c.width, 'height': c.height, 'dgen_kind': c.dgen_kind,
+                'start_kind': c.start_kind, 'start_depth': tuple(c.start_depth), 'n_npc': c.n_npc,
+                'hp': tuple(c.hp), 'damage': tuple(c.damage), 'armor': tuple(c.armor)}
+
     def state_dict(self):
-        """Checkpoint: plain tensors + scalars (``torch.save``-able). The planes that share one
-        allocation are copied out (torch cannot serialise views of one storage under different dtypes)."""
-        word = {name for name, _, _ in self.WORD_PLANES}
-        d = {name: getattr(self, name).clone() if name in word else getattr(self, name) for name in self.PLANES}
+        """Checkpoint: a snapshot (every plane is copied, so ticking on does not change it) of plain tensors +
+        scalars, ``torch.save``-able, with the batch size and the configuration the planes belong to."""
+        d = {name: getattr(self, name).detach().clone() for name in self.PLANES}
         d['game_id_base'] = self.game_id_base
+        d['fingerprint'] = self._fingerprint()
         return d
 
     def load_state_dict(self, d):
+        """Restores a ``state_dict()`` snapshot. The checkpoint must come from a state of the same batch size and
+        configuration (seed, room, generator, start, stats, NPC slots): a Philox stream or a plane shape that does
+        not match would silently give other games."""
+        fp = d.get('fingerprint')
+        if fp is not None:
+            mine = self._fingerprint()
+            bad = [k for k in mine if k in fp and (tuple(fp[k]) if isinstance(fp[k], (list, tuple)) else fp[k]) != mine[k]]
+            if bad:
+                raise ValueError('checkpoint does not belong to this state: ' + ', '.join(f'{k}: {fp[k]!r} != {mine[k]!r}' for k in bad))
+        for name in self.PLANES:
+            src, dst = d[name], getattr(self, name)
+            if tuple(src.shape) != tuple(dst.shape) or src.dtype != dst.dtype:
+                raise ValueError(f'checkpoint plane {name}: {tuple(src.shape)} {src.dtype} does not fit {tuple(dst.shape)} {dst.dtype}')
         for name in self.PLANES:
             getattr(self, name).copy_(d[name])
         self.game_id_base = int(d['game_id_base'])
+        self.sched.zero_()          # no launch is in flight across a restore
 
     def set_npc(self, lane: int, slot: int, depth: int, x: int, y: int, health: int):
         """Places a static NPC (an extra Entity after the players, updater.py:116-128)."""

@@ -130,9 +130,12 @@ class BatchedUpdater:
         """One tick for every game (updater.py:76-162).
 
         ``player1_move``/``player2_move``: uint8[N] Move codes, or pass a single uint8[N,2]
-        tensor as ``player1_move`` (fast path, no stacking). CUDA tensors are consumed in place;
-        CPU tensors (pinned for asynchrony) go through ``orx_step_host`` and the result comes
-        back in a CPU tensor. Returns ``(result uint8[N] of UpdateResult codes, events)`` where
+        tensor as ``player1_move`` (fast path, no stacking). CUDA tensors are consumed in place and the
+        tick is only ENQUEUED on the current stream (the result tensor is ordered after it on that stream).
+        CPU tensors go through ``orx_step_host_sync``: the call returns when the tick is done, the result is a
+        CPU tensor that can be read at once, and the moves tensor may be overwritten at once (for an
+        asynchronous host loop use ``host_stepper(..., sync=False)``). Without ``out`` the CPU result is a
+        pinned buffer owned by the updater and overwritten by its next host-side ``update``. Returns ``(result uint8[N] of UpdateResult codes, events)`` where
         events is None or an int32[N, max_events, 2] tensor of raw OrxEvent records
         (see logic/updates.py:decode_events).
 
@@ -192,13 +195,18 @@ class BatchedUpdater:
         if not hasattr(self, '_stage') or self._stage[0].shape[0] != gs.n or self._stage[0].device != gs.device:
             self._stage = (torch.empty((gs.n, 2), dtype=torch.uint8, device=gs.device),
                            torch.empty((gs.n,), dtype=torch.uint8, device=gs.device))
-        result_host = out if out is not None else torch.empty((gs.n,), dtype=torch.uint8, pin_memory=True)
-        fn = _lib.lib().orx_step_host_packed if packed else _lib.lib().orx_step_host
+        if out is not None:
+            result_host = out
+        else:
+            if getattr(self, '_host_result', None) is None or self._host_result.shape[0] != gs.n:
+                self._host_result = torch.empty((gs.n,), dtype=torch.uint8, pin_memory=True)
+            result_host = self._host_result
+        name = 'orx_step_host_packed_sync' if packed else 'orx_step_host_sync'     # synchronous: see update()
         with _on_device(gs.device):
-            rc = fn(C.byref(cfg), C.byref(st), moves_host.data_ptr(), result_host.data_ptr(),
-                    self._stage[0].data_ptr(), self._stage[1].data_ptr(), gs.n, gs.game_id_base,
-                    _stream_ptr(gs.device))
-        _lib.check(rc, 'orx_step_host_packed' if packed else 'orx_step_host')
+            rc = getattr(_lib.lib(), name)(C.byref(cfg), C.byref(st), moves_host.data_ptr(), result_host.data_ptr(),
+                                           self._stage[0].data_ptr(), self._stage[1].data_ptr(), gs.n, gs.game_id_base,
+                                           _stream_ptr(gs.device))
+        _lib.check(rc, name)
         return result_host
 
     def host_stepper(self, game_state: BatchedGameState, moves_host: torch.Tensor, result_host: torch.Tensor,

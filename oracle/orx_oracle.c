@@ -374,13 +374,17 @@ static void load_game(Game* g, const OrxConfig* cfg, const OrxState* st, int64_t
     }
 }
 
+/* health is a Python int in the reference (entities.py:38) and an int16 plane here: a value below the plane's
+ * range (only reachable with hits near 32767) is stored as the lowest one, so that a dead entity stays dead */
+static int16_t health_plane(int h) { return (int16_t)(h < -32768 ? -32768 : h > 32767 ? 32767 : h); }
+
 static void store_game(const Game* g, const OrxState* st, int64_t i)
 {
     st->tick[i] = g->tick; st->status[i] = (uint8_t)g->status; st->episode[i] = g->rng.episode;
     for (int p = 0; p < 2; ++p) {
         const Entity* e = &g->ent[p];
         st->pos[4 * i + 2 * p] = (uint8_t)e->x; st->pos[4 * i + 2 * p + 1] = (uint8_t)e->y;
-        st->depth[2 * i + p] = e->depth; st->hp[2 * i + p] = (int16_t)e->health;
+        st->depth[2 * i + p] = e->depth; st->hp[2 * i + p] = health_plane(e->health);
         st->stairs[4 * i + 2 * p] = (uint8_t)g->stairs[p][0]; st->stairs[4 * i + 2 * p + 1] = (uint8_t)g->stairs[p][1];
     }
     for (int k = 0; k < g->cfg->n_npc; ++k) {
@@ -388,7 +392,7 @@ static void store_game(const Game* g, const OrxState* st, int64_t i)
         int64_t j = i * g->cfg->n_npc + k;
         st->npc_depth[j] = e->present ? e->depth : -1;
         st->npc_pos[2 * j] = (uint8_t)e->x; st->npc_pos[2 * j + 1] = (uint8_t)e->y;
-        st->npc_hp[j] = (int16_t)e->health;
+        st->npc_hp[j] = health_plane(e->health);
     }
 }
 

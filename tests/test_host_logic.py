@@ -209,3 +209,30 @@ def test_tools_and_examples_compile():
     for f in files:
         with open(f) as fh:
             compile(fh.read(), f, 'exec')
+
+
+def test_state_dict_is_a_snapshot_and_checks_what_it_is_loaded_into():
+    """state_dict() copies EVERY plane (mutating the live state afterwards must not leak into the snapshot),
+    carries the batch size + configuration, and load_state_dict() refuses a mismatch instead of broadcasting."""
+    import pytest
+    import torch
+    from optimax_rogue_b200 import SimConfig
+    from optimax_rogue_b200.game.state import BatchedGameState
+    cfg = SimConfig(n_npc=2, seed=5)
+    gs = BatchedGameState(cfg, 300, 'cpu')
+    gs.depth[:] = 3; gs.status[:] = 1; gs.npc_hp[:] = 9; gs.tick[:] = 17
+    sd = gs.state_dict()
+    keep = gs.clone()
+    gs.depth[:] = 8; gs.status[:] = 4; gs.npc_hp[:] = -1; gs.npc_depth[:] = 5; gs.npc_pos[:] = 2; gs.tick[:] = 99      # "tick on"
+    gs.load_state_dict(sd)
+    for name in BatchedGameState.PLANES:
+        assert torch.equal(getattr(gs, name), getattr(keep, name)), name
+    assert sd['fingerprint']['n'] == 300 and sd['fingerprint']['seed'] == 5
+    with pytest.raises(ValueError, match='n:'):
+        BatchedGameState(cfg, 1, 'cpu').load_state_dict(sd)            # would have broadcast before
+    with pytest.raises(ValueError, match='seed'):
+        BatchedGameState(SimConfig(n_npc=2, seed=6), 300, 'cpu').load_state_dict(sd)
+    legacy = {k: v for k, v in sd.items() if k != 'fingerprint'}
+    legacy['tick'] = legacy['tick'][:1]
+    with pytest.raises(ValueError, match='plane tick'):
+        BatchedGameState(cfg, 300, 'cpu').load_state_dict(legacy)
