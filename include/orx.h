@@ -114,6 +114,7 @@ typedef struct OrxConfig {
 #define ORX_PATH_NO_EVENT_PIPE 8u   /* event log: one-thread-per-game kernel */
 #define ORX_PATH_HOST_STAGED 16u    /* host buffers: staged cudaMemcpyAsync instead of in-kernel PCIe access */
 #define ORX_PATH_NO_TILE_FLAGS 32u  /* order consecutive launches by a grid-wide dependency, not tile by tile */
+#define ORX_PATH_FORCE_TILE_FLAGS 64u /* tile-by-tile ordering also for batches of 2^20 games and more */
 #define ORX_PATH_TILES_PER_CTA_SHIFT 8  /* bits 8..15: tiles per CTA in tile-flag mode (0 = built-in default) */
 
 /* Structure-of-arrays game state; game i of the batch is element i of every plane.
@@ -140,9 +141,12 @@ typedef struct OrxState {
      * size the state is ticked with. Two uses (csrc/orx_pipe.cuh):
      *   sched_words >= ORX_SCHED_HEADER_WORDS: word 0 is a tile counter, 256-game tiles are handed out
      *     dynamically (CTAs that run slower take fewer); zero again when a launch completes.
-     *   sched_words >= orx_sched_words(n): words 4.. hold {tickets, completed passes} per tile, and consecutive
-     *     tick launches on the state are ordered tile by tile instead of grid by grid: tick k+1 starts on a
-     *     tile as soon as tick k has written it, and ticks of different states in one stream overlap freely.
+     *   sched_words >= orx_sched_words(n), n < 2^20: words 4.. hold {tickets, completed passes} per chunk of four
+     *     tiles, and consecutive tick launches on the state are ordered chunk by chunk instead of grid by grid: tick
+     *     k+1 starts on a chunk as soon as tick k has written it, and ticks of different states in one stream
+     *     overlap freely. This is the throughput mode for back-to-back ticks (several states in flight, queued
+     *     commands): 1.2-1.7x at 2^17..2^19 games per launch; a loop that waits for every tick's result before it
+     *     enqueues the next gains nothing and pays about a microsecond per tick -- ORX_PATH_NO_TILE_FLAGS opts out.
      *     Stream order towards everything else is kept (a tick completes only after all earlier work has).
      *     In this mode two consecutive tick calls on DIFFERENT states must not share a result / observation /
      *     event buffer unless something else in the stream consumes it in between. */

@@ -22,7 +22,7 @@ EV_NONE, EV_MOVE, EV_COMBAT, EV_DUNGEON, EV_DEATH, EV_DESCEND = 0, 1, 2, 3, 4, 5
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA_BASE = 0, -1, -2, -100
 
 # OrxConfig.path_flags (include/orx.h)
-PATH_NO_TENSOR_MAP, PATH_NO_NPC_PIPE, PATH_STATIC_TILES, PATH_NO_EVENT_PIPE, PATH_HOST_STAGED, PATH_NO_TILE_FLAGS = 1, 2, 4, 8, 16, 32
+PATH_NO_TENSOR_MAP, PATH_NO_NPC_PIPE, PATH_STATIC_TILES, PATH_NO_EVENT_PIPE, PATH_HOST_STAGED, PATH_NO_TILE_FLAGS, PATH_FORCE_TILE_FLAGS = 1, 2, 4, 8, 16, 32, 64
 PATH_TILES_PER_CTA_SHIFT = 8
 SCHED_HEADER_WORDS = 4
 TILE = 256

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "../../include/orx.h"
 #include "orx_rules.cuh"
@@ -15,6 +16,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxFixedTiles = 16384;   // shared-memory staging of the fixed map
+constexpr unsigned int kFlagModeMaxTiles = 4096;   // 2^20 games: from here on grid-wait mode (tile_ctl)
 constexpr int64_t kMaxGamesPerCall = 1ll << 30;   // 32-bit lane index inside the kernels; larger batches: call per chunk
 
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p)
@@ -104,14 +106,15 @@ k_step(const __grid_constant__ Params P, const void* __restrict__ moves, uint8_t
                 if ((bots >> 8) != ORX_BOT_NONE) mv = (mv & 0x00FFu) | (bot_move(bots >> 8, L.pos >> 16, L.st >> 16, blk.y) << 8);
             }
             Counters cnt{};
-            const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
-            const NpcView* nv = NPC ? &slots : nullptr;
-            res = tick_lane<DGEN, NPC, EV>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
+            using NV = std::conditional_t<NPC, NpcView, NoNpc>;
+            NV nv;
+            if constexpr (NPC) nv = npc_view(P, i);
+            res = tick_lane<DGEN, NV, EV>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
             ev.finish();
             int new_status = res;
             if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
                 s.episode += 1;
-                reset_lane<DGEN, NPC>(P, L, s, nv);
+                reset_lane<DGEN, NV>(P, L, s, nv);
                 new_status = ORX_RESULT_IN_PROGRESS;
             }
             store_lane(P, i, L, new_status);
@@ -139,8 +142,10 @@ k_reset(const __grid_constant__ Params P, const uint8_t* __restrict__ mask, int 
     if (mask != nullptr && mask[i] == 0) return;
     Lane L;
     Stream s = make_stream(P, i, P.episode[i] + (bump ? 1u : 0u));
-    const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
-    reset_lane<DGEN, NPC>(P, L, s, NPC ? &slots : nullptr);
+    using NV = std::conditional_t<NPC, NpcView, NoNpc>;
+    NV nv;
+    if constexpr (NPC) nv = npc_view(P, i);
+    reset_lane<DGEN, NV>(P, L, s, nv);
     store_lane(P, i, L, ORX_RESULT_IN_PROGRESS);
 }
 
@@ -197,13 +202,14 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
             load_lane(P, i, L);
             Stream s = make_stream(P, i, L.episode);
             EvSink<false> ev{nullptr, 0, 0};
-            const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
-            const NpcView* nv = NPC ? &slots : nullptr;
+            using NV = std::conditional_t<NPC, NpcView, NoNpc>;
+            NV nv;
+            if constexpr (NPC) nv = npc_view(P, i);
             for (int t = 0; t < n_ticks; ++t) {
                 const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
                 const uint32_t m1 = bot_move(bot1, L.pos & 0xFFFFu, L.st & 0xFFFFu, blk.x);
                 const uint32_t m2 = bot_move(bot2, L.pos >> 16, L.st >> 16, blk.y);
-                const int res = tick_lane<DGEN, NPC, false>(P, tiles, lut, L, m1 | (m2 << 8), blk.z, s, nv, ev, cnt);
+                const int res = tick_lane<DGEN, NV, false>(P, tiles, lut, L, m1 | (m2 << 8), blk.z, s, nv, ev, cnt);
                 ++cnt.ticks;
                 if (res != ORX_RESULT_IN_PROGRESS) {
                     cnt.p1 += res == ORX_RESULT_PLAYER1_WIN;
@@ -211,7 +217,7 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
                     cnt.ties += res == ORX_RESULT_TIE;
                     if (P.auto_reset) {
                         s.episode += 1;
-                        reset_lane<DGEN, NPC>(P, L, s, nv);
+                        reset_lane<DGEN, NV>(P, L, s, nv);
                     } else {
                         status = res;
                         break;
@@ -254,17 +260,18 @@ k_replay(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, u
     Stream s = make_stream(P, i, L.episode);
     EvSink<false> ev{nullptr, 0, 0};
     Counters cnt{};
-    const NpcView slots = NPC ? npc_view(P, i) : NpcView{nullptr, nullptr, nullptr};
-    const NpcView* nv = NPC ? &slots : nullptr;
+    using NV = std::conditional_t<NPC, NpcView, NoNpc>;
+    NV nv;
+    if constexpr (NPC) nv = npc_view(P, i);
     for (int t = 0; t < n_ticks; ++t) {
         const size_t at = (size_t)t * P.n + i;
         if (status != ORX_RESULT_IN_PROGRESS) { results[at] = (uint8_t)status; continue; }   // frozen lane
         const uint32_t mv = moves[at];
         const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
-        const int res = tick_lane<DGEN, NPC, false>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
+        const int res = tick_lane<DGEN, NV, false>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
         results[at] = (uint8_t)res;
         if (res != ORX_RESULT_IN_PROGRESS) {
-            if (P.auto_reset) { s.episode += 1; reset_lane<DGEN, NPC>(P, L, s, nv); }
+            if (P.auto_reset) { s.episode += 1; reset_lane<DGEN, NV>(P, L, s, nv); }
             else status = res;
         }
     }
@@ -509,9 +516,14 @@ TileCtl tile_ctl(const OrxConfig* cfg, const OrxState* st, unsigned int n_tiles)
     cudaGetDevice(&dev);
     const int sms = device_sms(dev);
     const uint64_t need = (uint64_t)ORX_SCHED_HEADER_WORDS + 2ull * n_tiles;
-    // beyond kBitsMaxTiles tiles for each of 3 CTAs per SM a launch fills the machine several times over and the
-    // boundary between launches no longer matters: grid-wait mode
-    if (!(cfg->path_flags & ORX_PATH_NO_TILE_FLAGS) && st->sched_words >= need && n_tiles <= (unsigned int)(kBitsMaxTiles * 3 * sms)) {
+    // Flag mode pays per launch (tickets, acquire, one release fence per chunk in the thread that moves the data)
+    // for not having a grid-wide boundary between launches. Measured with back-to-back launches on rotating states
+    // (profiles/r02_batch_sweep.json): 2.5 against 4.4 us per step at 2^17 games, 3.7 / 5.5 at 2^18, 6.7 / 7.9 at
+    // 2^19, 12.9 / 12.6 at 2^20 -- from kFlagModeMaxTiles tiles on, a launch is long enough for the boundary not to
+    // matter and grid-wait mode (dynamic tile hand-out, L2 prefetch across the boundary) is the faster one.
+    // ORX_PATH_FORCE_TILE_FLAGS lifts the size limit (A/B runs).
+    const bool small = n_tiles < kFlagModeMaxTiles || (cfg->path_flags & ORX_PATH_FORCE_TILE_FLAGS) != 0;
+    if (!(cfg->path_flags & ORX_PATH_NO_TILE_FLAGS) && st->sched_words >= need && small && n_tiles <= (unsigned int)(kBitsMaxTiles * 3 * sms)) {
         c.flags = st->sched + ORX_SCHED_HEADER_WORDS;
         c.tiles_per_cta = (int)flag_tiles_per_cta(n_tiles, sms, (int)((cfg->path_flags >> ORX_PATH_TILES_PER_CTA_SHIFT) & 255u));
         return c;
@@ -520,7 +532,7 @@ TileCtl tile_ctl(const OrxConfig* cfg, const OrxState* st, unsigned int n_tiles)
     return c;
 }
 
-template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, bool NPC = false>
+template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, int NPC = 0>
 int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, const TileCtl& ctl,
                 int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
 {
@@ -592,6 +604,20 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
 }
 
+// The tick with NPC slots: one instantiation per slot count (the slot loops unroll, the stage holds exactly the slots
+// in use, and with few slots more stages fit).
+template <int DGEN, int CMD>
+int launch_npc_pipe(int n_npc, const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes,
+                    const TileCtl& ctl, cudaStream_t s)
+{
+    switch (n_npc) {
+#define ORX_NPC_CASE(N) case N: return launch_pipe<DGEN, CMD, false, true, false, N>(P, mv, result, n_tiles, tiles_bytes, ctl, nullptr, -1, s);
+        ORX_NPC_CASE(1) ORX_NPC_CASE(2) ORX_NPC_CASE(3) ORX_NPC_CASE(4) ORX_NPC_CASE(5) ORX_NPC_CASE(6) ORX_NPC_CASE(7) ORX_NPC_CASE(8)
+#undef ORX_NPC_CASE
+    }
+    return ORX_ERR_BAD_ARG;
+}
+
 template <bool OBS, bool EV = false>
 int launch_tick_pipe(bool empty, int packed, const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t smem,
                      const TileCtl& sched, int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
@@ -634,10 +660,10 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
         const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
         const TileCtl sched = tile_ctl(cfg, st, n_tiles);
         int rc2;
-        if (packed) rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES, false, true, false, true>(P, moves, result, n_tiles, 0, sched, nullptr, -1, s)
-                                : launch_pipe<ORX_DGEN_FIXED, CMD_NIBBLES, false, true, false, true>(P, moves, result, n_tiles, smem, sched, nullptr, -1, s);
-        else rc2 = empty ? launch_pipe<ORX_DGEN_EMPTY, CMD_BYTES, false, true, false, true>(P, moves, result, n_tiles, 0, sched, nullptr, -1, s)
-                         : launch_pipe<ORX_DGEN_FIXED, CMD_BYTES, false, true, false, true>(P, moves, result, n_tiles, smem, sched, nullptr, -1, s);
+        if (packed) rc2 = empty ? launch_npc_pipe<ORX_DGEN_EMPTY, CMD_NIBBLES>(cfg->n_npc, P, moves, result, n_tiles, 0, sched, s)
+                                : launch_npc_pipe<ORX_DGEN_FIXED, CMD_NIBBLES>(cfg->n_npc, P, moves, result, n_tiles, smem, sched, s);
+        else rc2 = empty ? launch_npc_pipe<ORX_DGEN_EMPTY, CMD_BYTES>(cfg->n_npc, P, moves, result, n_tiles, 0, sched, s)
+                         : launch_npc_pipe<ORX_DGEN_FIXED, CMD_BYTES>(cfg->n_npc, P, moves, result, n_tiles, smem, sched, s);
         if (rc2 != ORX_OK || n_body == n) return rc2;
         const Params T = offset_params(P, n_body, n - n_body);
         const int tgrid = grid_for(n - n_body);

@@ -45,6 +45,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "orx_rules.cuh"
 
 namespace orx {
@@ -80,11 +82,10 @@ constexpr uint32_t kTileIdxBytes = ((uint32_t)kStages * 4u + 15u) & ~15u;   // p
 #define ORX_PIPE_EV_STAGES 4
 #endif
 // ... and with the event log its 32 B/game of records (8 KB): four stages.
-#ifndef ORX_PIPE_NPC_STAGES
-#define ORX_PIPE_NPC_STAGES 3
-#endif
-// ... and with NPC slots room for eight of them per game (16 KB per tile): three stages.
-template <bool OBS, bool EV = false, bool NPC = false> constexpr int kPipeStages = NPC ? ORX_PIPE_NPC_STAGES : OBS ? ORX_PIPE_OBS_STAGES : EV ? ORX_PIPE_EV_STAGES : kStages;
+// ... and with N NPC slots per game their three slot planes (8 N bytes per game): as many stages as fit the ~72 KB that
+// keep three CTAs per SM resident, between 3 and 6 (one slot: 6 stages of 10 KB, eight slots: 3 of 24 KB).
+constexpr int npc_stages(int npc) { const int fit = 72 * 1024 / (int)(29u * ORX_PIPE_TILE + 3u * ORX_PIPE_TILE + 8u * (unsigned)npc * ORX_PIPE_TILE); return fit > 6 ? 6 : fit < 3 ? 3 : fit; }
+template <bool OBS, bool EV = false, int NPC = 0> constexpr int kPipeStages = NPC ? npc_stages(NPC) : OBS ? ORX_PIPE_OBS_STAGES : EV ? ORX_PIPE_EV_STAGES : kStages;
 
 // byte offsets of the plane slices inside a stage (all multiples of 16)
 constexpr uint32_t T4 = 4u * kTile, T8 = 8u * kTile, T2 = 2u * kTile, T1 = kTile;   // slice sizes in bytes
@@ -96,10 +97,10 @@ constexpr uint32_t OBS_GAME_BYTES = 2u * ORX_OBS_LEN * 2u, OBS_BYTES = OBS_GAME_
 static_assert(OBS_GAME_BYTES == 48 && (STAGE_BYTES % 128) == 0, "observation block: 12 words per game behind the planes");
 constexpr uint32_t EV_GAME_BYTES = 8u * ORX_MAX_EVENTS_BASE, EV_BYTES = EV_GAME_BYTES * kTile, OFF_EV = STAGE_BYTES;   // event records share the slot behind the planes
 static_assert(EV_GAME_BYTES == 32, "four 8-byte records per game without NPC slots");
-// NPC slot planes of a tile, sized for ORX_MAX_NPC slots: pos 2 B, hp 2 B, depth 4 B per slot
-constexpr uint32_t NPC_POS_MAX = 2u * ORX_MAX_NPC * kTile, NPC_BYTES_MAX = 8u * ORX_MAX_NPC * kTile,
-                   OFF_NPOS = STAGE_BYTES, OFF_NHP = OFF_NPOS + NPC_POS_MAX, OFF_NDEPTH = OFF_NHP + NPC_POS_MAX;
-template <bool OBS, bool EV = false, bool NPC = false> constexpr uint32_t kPipeStageBytes = STAGE_BYTES + (OBS ? OBS_BYTES : 0u) + (EV ? EV_BYTES : 0u) + (NPC ? NPC_BYTES_MAX : 0u);
+// NPC slot planes of a tile with N slots per game (compile time): pos 2 B, hp 2 B, depth 4 B per slot, behind the planes
+constexpr uint32_t OFF_NPOS = STAGE_BYTES;
+template <int NPC> constexpr uint32_t kNpcPosBytes = 2u * (uint32_t)NPC * kTile;          // = hp slice; the depth slice is twice that
+template <bool OBS, bool EV = false, int NPC = 0> constexpr uint32_t kPipeStageBytes = STAGE_BYTES + (OBS ? OBS_BYTES : 0u) + (EV ? EV_BYTES : 0u) + 4u * kNpcPosBytes<NPC>;
 // Command formats: CMD_BYTES = uint8[n][2] (p1, p2); CMD_NIBBLES = uint8[n], p1 in the low nibble,
 // p2 in the high nibble (halves the command traffic when the commands come over PCIe).
 constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1, CMD_BYTES_BOTS = 2;   // _BOTS: uint8[n][2], scripted players' commands computed in the kernel
@@ -191,6 +192,21 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_s32x2(uint32_t a, int x, int y) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
+__device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// The NPC slots of one game inside the shared-memory stage (see NpcView in orx_rules.cuh): N is a compile-time
+// constant, so the tick's slot loops unroll onto constant offsets from three shared-window addresses.
+template <int N>
+struct NpcStage {
+    static constexpr bool kPresent = true;
+    uint32_t pos, hp, depth;      // this game's slot 0 in the stage's npc_pos / npc_hp / npc_depth slices
+    __device__ __forceinline__ static constexpr int count() { return N; }
+    __device__ __forceinline__ int depth_at(int k) const { return (int)lds_u32(depth + 4u * (uint32_t)k); }
+    __device__ __forceinline__ uint32_t xy_at(int k) const { return lds_u16(pos + 2u * (uint32_t)k); }
+    __device__ __forceinline__ int hp_at(int k) const { return lds_s16(hp + 2u * (uint32_t)k); }
+    __device__ __forceinline__ void set_hp(int k, int v) const { sts_u16(hp + 2u * (uint32_t)k, (uint32_t)v & 0xFFFFu); }
+    __device__ __forceinline__ void set_depth(int k, int v) const { sts_u32(depth + 4u * (uint32_t)k, (uint32_t)v); }
+};
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // flag mode: per-tile hand-over between consecutive launches on one state
 // flag mode hand-over: acquire / release at gpu scope (LDG.STRONG.GPU + CCTL.IVALL, MEMBAR.ALL.GPU + STG.STRONG.GPU).
@@ -226,7 +242,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 // EV: also write the tick's replication-log records (OrxEvent[4] per game, no NPC slots), staged like the
 // observations and streamed out with one bulk store per tile.
 // NPC: the game's NPC slot planes (n_npc <= ORX_MAX_NPC slots) travel with the tile as three more slices.
-template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, bool NPC = false>
+template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, int NPC = 0>
 __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
 k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap planes5, const int use_map,
             const void* __restrict__ moves_v, uint8_t* __restrict__ result,
@@ -239,7 +255,8 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     if (threadIdx.x == 0) ORX_TRACE(trace_slot, 0);
     constexpr int kStages = kPipeStages<OBS, EV, NPC>;             // shadows the namespace constant on purpose
     constexpr uint32_t STAGE_BYTES = kPipeStageBytes<OBS, EV, NPC>;
-    const uint32_t npc2 = NPC ? 2u * (uint32_t)P.n_npc * kTile : 0u;     // bytes of a tile's npc_pos / npc_hp slice; npc_depth: twice that
+    constexpr uint32_t npc2 = kNpcPosBytes<NPC>;                   // bytes of a tile's npc_pos / npc_hp slice; npc_depth: twice that
+    constexpr uint32_t OFF_NHP = OFF_NPOS + npc2, OFF_NDEPTH = OFF_NHP + npc2;
     constexpr uint32_t MV_BYTES = CMD == CMD_BITS ? 0u : CMD == CMD_NIBBLES ? T1 : T2, LOAD_BYTES = PLANE_LOAD_BYTES + (TICK ? MV_BYTES : 0u);
     static_assert(CMD != CMD_BITS || (TICK && !OBS && !EV && !NPC), "bit-packed streams ride with the plain tick");
     const uint8_t* moves = static_cast<const uint8_t*>(moves_v);
@@ -329,9 +346,9 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             const size_t g = (size_t)tile * kTile;     // first game of the tile
             mbar_expect_tx(bar, LOAD_BYTES + 4u * npc2);
             if (NPC) {
-                bulk_load(base + OFF_NPOS, P.npc_pos + g * 2u * P.n_npc, npc2, bar);
-                bulk_load(base + OFF_NHP, P.npc_hp + g * P.n_npc, npc2, bar);
-                bulk_load(base + OFF_NDEPTH, P.npc_depth + g * P.n_npc, 2u * npc2, bar);
+                bulk_load(base + OFF_NPOS, P.npc_pos + g * 2u * NPC, npc2, bar);
+                bulk_load(base + OFF_NHP, P.npc_hp + g * NPC, npc2, bar);
+                bulk_load(base + OFF_NDEPTH, P.npc_depth + g * NPC, 2u * npc2, bar);
             }
             if (use_map) {
                 tensor_load_2d(base + OFF_POS, &planes5, (uint32_t)g, 0u, bar);
@@ -466,9 +483,9 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             if (OBS) bulk_store(obs + g * (2 * ORX_OBS_LEN), base + OFF_OBS, OBS_BYTES);
             if (EV) bulk_store(events + g * ORX_MAX_EVENTS_BASE, base + OFF_EV, EV_BYTES);
             if (NPC) {
-                bulk_store(P.npc_pos + g * 2u * P.n_npc, base + OFF_NPOS, npc2);
-                bulk_store(P.npc_hp + g * P.n_npc, base + OFF_NHP, npc2);
-                bulk_store(P.npc_depth + g * P.n_npc, base + OFF_NDEPTH, 2u * npc2);
+                bulk_store(P.npc_pos + g * 2u * NPC, base + OFF_NPOS, npc2);
+                bulk_store(P.npc_hp + g * NPC, base + OFF_NHP, npc2);
+                bulk_store(P.npc_depth + g * NPC, base + OFF_NDEPTH, 2u * npc2);
             }
             bulk_commit();
             if (flagged && (it + 1u) % (unsigned)kChunk == 0u && it + 1u > (unsigned)kChunk) {
@@ -575,13 +592,13 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             // this game's four record slots in the stage (generic pointer into shared memory)
             EvSink<EV> ev{EV ? reinterpret_cast<uint2*>(smem + s * STAGE_BYTES + OFF_EV) + tid * ORX_MAX_EVENTS_BASE : nullptr, 0,
                           ORX_MAX_EVENTS_BASE};
-            // this game's NPC slots in the stage (generic pointers into shared memory)
-            uint8_t* const stage_g = smem + s * STAGE_BYTES;
-            const NpcView slots = NPC ? NpcView{stage_g + OFF_NPOS + tid * 2u * P.n_npc,
-                                                reinterpret_cast<int16_t*>(stage_g + OFF_NHP) + tid * P.n_npc,
-                                                reinterpret_cast<int*>(stage_g + OFF_NDEPTH) + tid * P.n_npc}
-                                      : NpcView{nullptr, nullptr, nullptr};
-            const NpcView* nv = NPC ? &slots : nullptr;
+            // this game's NPC slots in the stage
+            using NV = std::conditional_t<NPC != 0, NpcStage<NPC>, NoNpc>;
+            NV nv;
+            if constexpr (NPC != 0) {
+                const uint32_t sb = stage0 + s * STAGE_BYTES;
+                nv.pos = sb + OFF_NPOS + tid * 2u * NPC; nv.hp = sb + OFF_NHP + tid * 2u * NPC; nv.depth = sb + OFF_NDEPTH + tid * 4u * NPC;
+            }
             if (status == ORX_RESULT_IN_PROGRESS) {          // finished lanes are frozen until reset
                 Stream rs = make_stream(P, lane, ep);
                 const uint4 blk = draw_block(rs, DOM_TICK, SUB_MAIN, (uint32_t)tick);
@@ -590,11 +607,11 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
                     if ((bots >> 8) != ORX_BOT_NONE) mv = (mv & 0x00FFu) | (bot_move(bots >> 8, L.pos >> 16, L.st >> 16, blk.y) << 8);
                 }
                 Counters cnt{};
-                res = tick_lane<DGEN, NPC, EV>(P, tiles, lut, L, mv, blk.z, rs, nv, ev, cnt);
+                res = tick_lane<DGEN, NV, EV>(P, tiles, lut, L, mv, blk.z, rs, nv, ev, cnt);
                 int new_status = res;
                 if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
                     rs.episode += 1;
-                    reset_lane<DGEN, NPC>(P, L, rs, nv);
+                    reset_lane<DGEN, NV>(P, L, rs, nv);
                     new_status = ORX_RESULT_IN_PROGRESS;
                 }
                 sts_u32(b4 + OFF_POS, L.pos);
@@ -638,7 +655,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     if (tid == 0) ORX_TRACE(trace_slot, 6);
 }
 
-template <bool OBS, bool EV = false, bool NPC = false, bool BITS = false>
+template <bool OBS, bool EV = false, int NPC = 0, bool BITS = false>
 constexpr size_t pipe_smem_bytes(int fixed_tiles)
 {
     return (size_t)kPipeStages<OBS, EV, NPC> * kPipeStageBytes<OBS, EV, NPC> + 2 * kPipeStages<OBS, EV, NPC> * 8 + kTileIdxBytes + kTicketBytes +

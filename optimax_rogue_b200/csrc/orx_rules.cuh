@@ -118,33 +118,59 @@ __device__ __forceinline__ void kth_ground(const Params& P, int sx, int sy, int 
     }
 }
 
-// The NPC slots of ONE game: pointers to its slot 0 in the three slot planes (in HBM for the simple kernels,
-// in the shared-memory stage for the pipelined one). Unused (NULL) when the configuration has no NPC slots.
+// The NPC slots of ONE game, behind a small accessor interface so that the tick does not care where they live:
+//   NoNpc        the configuration has no NPC slots (every loop over slots disappears)
+//   NpcView      slot planes in HBM, slot count known at run time (one-thread-per-game kernels)
+//   NpcStage<N>  (orx_pipe.cuh) slot planes of a tile in the shared-memory stage, N known at compile time: the slot
+//                loops unroll onto constant shared-window offsets
+struct NoNpc {
+    static constexpr bool kPresent = false;
+    __device__ __forceinline__ static constexpr int count() { return 0; }
+    __device__ __forceinline__ int depth_at(int) const { return -1; }
+    __device__ __forceinline__ uint32_t xy_at(int) const { return 0u; }
+    __device__ __forceinline__ int hp_at(int) const { return 0; }
+    __device__ __forceinline__ void set_hp(int, int) const {}
+    __device__ __forceinline__ void set_depth(int, int) const {}
+};
+
 struct NpcView {
+    static constexpr bool kPresent = true;
     uint8_t* pos;     // [n_npc][2]
     int16_t* hp;      // [n_npc]
     int* depth;       // [n_npc], -1 = empty slot
+    int n;
+    __device__ __forceinline__ int count() const { return n; }
+    __device__ __forceinline__ int depth_at(int k) const { return depth[k]; }
+    __device__ __forceinline__ uint32_t xy_at(int k) const { return (uint32_t)pos[2 * k] | ((uint32_t)pos[2 * k + 1] << 8); }
+    __device__ __forceinline__ int hp_at(int k) const { return hp[k]; }
+    __device__ __forceinline__ void set_hp(int k, int v) const { hp[k] = (int16_t)v; }
+    __device__ __forceinline__ void set_depth(int k, int v) const { depth[k] = v; }
 };
 
 __device__ __forceinline__ NpcView npc_view(const Params& P, unsigned int lane)
 {
     const size_t j = (size_t)lane * P.n_npc;
-    return NpcView{P.npc_pos + 2 * j, P.npc_hp + j, P.npc_depth + j};
+    return NpcView{P.npc_pos + 2 * j, P.npc_hp + j, P.npc_depth + j, P.n_npc};
 }
 
 // A hit on an NPC slot: the plane is int16, the reference's health a Python int -- saturate instead of wrapping, so
 // that an NPC hit twice in one tick by hits near 32767 cannot come back to life.
-__device__ __forceinline__ void npc_hit(const NpcView* nv, int npc, int dmg)
+template <class NV>
+__device__ __forceinline__ void npc_hit(const NV& nv, int npc, int dmg)
 {
-    const int h = (int)nv->hp[npc] - dmg;
-    nv->hp[npc] = (int16_t)(h < -32768 ? -32768 : h);
+    const int h = nv.hp_at(npc) - dmg;
+    nv.set_hp(npc, h < -32768 ? -32768 : h);
 }
 
-__device__ __forceinline__ int npc_at(const Params& P, const NpcView* nv, int depth, int x, int y)
+// First slot (lowest index, the reference's entity order) standing on (depth, xy), xy = x | y << 8; -1 if none.
+template <class NV>
+__device__ __forceinline__ int npc_at(const NV& nv, int depth, uint32_t xy)
 {
-    for (int k = 0; k < P.n_npc; ++k)
-        if (nv->depth[k] == depth && nv->pos[2 * k] == x && nv->pos[2 * k + 1] == y) return k;
-    return -1;
+    int found = -1;
+#pragma unroll
+    for (int k = nv.count() - 1; k >= 0; --k)
+        if (nv.depth_at(k) == depth && nv.xy_at(k) == xy) found = k;
+    return found;
 }
 
 // Is level `depth` present in World.dungeons when player `pid` descends into it? Only feeds the
@@ -159,9 +185,9 @@ __device__ __forceinline__ bool level_exists(const Params& P, int pid, int depth
 // ---------------------------------------------------------------- rare paths (kept out of line)
 // handle_descend draws: stairs of the new level, then spawn tries until the tile is free
 // (updater.py:282-285). Returns sx | sy<<8 | x<<16 | y<<24  (= new st half | new pos half << 16).
-template <int DGEN, bool NPC>
+template <int DGEN, class NV>
 __device__ __noinline__ uint32_t descend_draw(const Params& P, Stream s, int tick, int pid, int new_depth,
-                                              uint32_t oxy, int odepth, const NpcView* nv)
+                                              uint32_t oxy, int odepth, const NV nv)
 {
     int sx, sy, x, y;
     level_stairs<DGEN>(P, s, new_depth, sx, sy);
@@ -172,7 +198,7 @@ __device__ __noinline__ uint32_t descend_draw(const Params& P, Stream s, int tic
         const int k = (int)seq_bounded(s, DOM_TICK, SUB_DESCEND + 64u * (uint32_t)pid, (uint32_t)tick, q++, (uint32_t)ng);
         kth_ground<DGEN>(P, sx, sy, k, x, y);
         taken = (odepth == new_depth) & (oxy == ((uint32_t)x | ((uint32_t)y << 8)));
-        if (NPC) taken = taken || npc_at(P, nv, new_depth, x, y) >= 0;
+        if (NV::kPresent) taken = taken || npc_at(nv, new_depth, (uint32_t)x | ((uint32_t)y << 8)) >= 0;
     } while (taken);
     return (uint32_t)sx | ((uint32_t)sy << 8) | ((uint32_t)x << 16) | ((uint32_t)y << 24);
 }
@@ -248,11 +274,12 @@ __device__ __forceinline__ bool is_stairs(const Params& P, const uint8_t* tiles,
 
 // One Updater.update. mv = p1 command | p2 command << 8; w_init is word 2 of the tick's main
 // block. Returns the UpdateResult.
-template <int DGEN, bool NPC, bool EV>
+template <int DGEN, class NV, bool EV>
 __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, const CmdEntry* lut, Lane& L, uint32_t mv,
-                                         uint32_t w_init, const Stream& s, const NpcView* nv,
+                                         uint32_t w_init, const Stream& s, const NV& nv,
                                          EvSink<EV>& ev, Counters& cnt)
 {
+    constexpr bool NPC = NV::kPresent;
     const int dl1 = clamped_delta<DGEN>(P, tiles, lut, mv & 255u, L.pos & 0xFFFFu);
     const int dl2 = clamped_delta<DGEN>(P, tiles, lut, (mv >> 8) & 255u, L.pos >> 16);
     // random.shuffle([p1, p2]) (updater.py:114): j = randbelow(2) = w >> 31; j == 0 swaps => p2 first.
@@ -282,13 +309,13 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
             const int dmgA = p2_first ? P.dmg1 : P.dmg0;
             if (dmgA > 0) { if (p2_first) hp1 -= dmgA; else hp2 -= dmgA; ++cnt.hits; }      // the victim is B
             ev.emit(ORX_EV_COMBAT, idA + 1, idB + 1, dB == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_FLEE, dmgA);
-        } else if (NPC && (npc = npc_at(P, nv, depA(), tA & 255u, tA >> 8)) >= 0) {
+        } else if (NPC && (npc = npc_at(nv, depA(), tA)) >= 0) {
             const int dmgA = p2_first ? P.dmg1 : P.dmg0;
             if (dmgA > 0) { npc_hit(nv, npc, dmgA); ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idA + 1, 3 + npc, ORX_FLAG_BLOCK, dmgA);
         } else if (is_stairs<DGEN>(P, tiles, tA, st & 0xFFFFu)) {
             const int nd = depA() + 1;
-            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idA, nd, pos >> 16, depB(), nv);
+            const uint32_t r = descend_draw<DGEN, NV>(P, s, L.tick, idA, nd, pos >> 16, depB(), nv);
             if (!level_exists(P, idA, nd, depB())) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
             ev.emit(ORX_EV_DESCEND, idA + 1, (r >> 16) & 255u, r >> 24, nd);
             if (p2_first) d2 = nd; else d1 = nd;
@@ -309,13 +336,13 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
             const int dmgB = p2_first ? P.dmg0 : P.dmg1;
             if (dmgB > 0) { if (p2_first) hp2 -= dmgB; else hp1 -= dmgB; ++cnt.hits; }      // the victim is A
             ev.emit(ORX_EV_COMBAT, idB + 1, idA + 1, dA == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_AMBUSH, dmgB);
-        } else if (NPC && (npc = npc_at(P, nv, depB(), tB & 255u, tB >> 8)) >= 0) {
+        } else if (NPC && (npc = npc_at(nv, depB(), tB)) >= 0) {
             const int dmgB = p2_first ? P.dmg0 : P.dmg1;
             if (dmgB > 0) { npc_hit(nv, npc, dmgB); ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idB + 1, 3 + npc, ORX_FLAG_BLOCK, dmgB);
         } else if (is_stairs<DGEN>(P, tiles, tB, st >> 16)) {
             const int nd = depB() + 1;
-            const uint32_t r = descend_draw<DGEN, NPC>(P, s, L.tick, idB, nd, pos & 0xFFFFu, depA(), nv);
+            const uint32_t r = descend_draw<DGEN, NV>(P, s, L.tick, idB, nd, pos & 0xFFFFu, depA(), nv);
             if (!level_exists(P, idB, nd, depA())) ev.emit(ORX_EV_DUNGEON, 0, r & 255u, (r >> 8) & 255u, nd);
             ev.emit(ORX_EV_DESCEND, idB + 1, (r >> 16) & 255u, r >> 24, nd);
             if (p2_first) d1 = nd; else d2 = nd;
@@ -333,10 +360,11 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
     L.d1 = d1; L.d2 = d2;
     L.hp1 = hp1; L.hp2 = hp2;
     if (NPC) {   // dead NPCs leave in reverse entity order (updater.py:137-145)
-        for (int k = P.n_npc - 1; k >= 0; --k) {
-            if (nv->depth[k] >= 0 && nv->hp[k] <= 0) {
+#pragma unroll
+        for (int k = nv.count() - 1; k >= 0; --k) {
+            if (nv.depth_at(k) >= 0 && nv.hp_at(k) <= 0) {
                 ev.emit(ORX_EV_DEATH, 3 + k, 0, 0, 0);
-                nv->depth[k] = -1;
+                nv.set_depth(k, -1);
             }
         }
     }
@@ -349,8 +377,8 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
 }
 
 // Re-initialise a lane for the episode already stored in s.episode.
-template <int DGEN, bool NPC>
-__device__ __forceinline__ void reset_lane(const Params& P, Lane& L, const Stream& s, const NpcView* nv)
+template <int DGEN, class NV>
+__device__ __forceinline__ void reset_lane(const Params& P, Lane& L, const Stream& s, const NV& nv)
 {
     const uint2 r = reset_draw<DGEN>(P, s);
     L.pos = r.x; L.st = r.y;
@@ -359,7 +387,10 @@ __device__ __forceinline__ void reset_lane(const Params& P, Lane& L, const Strea
     L.d2 = P.start_kind == ORX_START_SEPARATED ? P.sd1 : P.sd0;
     L.tick = 1;                                                          // worldgen.py:87
     L.episode = s.episode;
-    if (NPC) for (int k = 0; k < P.n_npc; ++k) nv->depth[k] = -1;
+    if (NV::kPresent) {
+#pragma unroll
+        for (int k = 0; k < nv.count(); ++k) nv.set_depth(k, -1);
+    }
 }
 
 __device__ __forceinline__ void unpack_lane(Lane& L, uint32_t pos, uint32_t hp, int2 d, uint32_t st, int tick, uint32_t ep)

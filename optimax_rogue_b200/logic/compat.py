@@ -13,6 +13,10 @@ Differences from the reference, by construction: randomness comes from the Philo
 (seed, game_id), not from the process-global MT19937 generators, and a level is a function of
 (seed, game_id, depth) -- so levels that already exist in ``game_state.world`` are honoured only for
 the depths the players currently stand on.
+
+Entities other than the two players (NPCs, ``updater.py:116-145``) ride in the lane's NPC slots, in the order they
+have in ``game_state.entities`` (which is the order the reference culls the dead in): up to ``ORX_MAX_NPC`` of them,
+with any idens. They never move (``decide_npc_move`` returns Stay), can be hit and die.
 """
 import numpy as np
 import torch
@@ -39,6 +43,7 @@ class SingleGameUpdater:
         self._batched = BatchedUpdater(dgen, self.despawn_strat, max_ticks)
         self._lane = None
         self._moves = None
+        self._idens, self._expected = [1, 2], ()
 
     def get_incr_upd_order(self):
         """updater.py:71-74"""
@@ -48,18 +53,23 @@ class SingleGameUpdater:
     # ------------------------------------------------------------------------------------------
     def _bind(self, game_state):
         p1, p2 = game_state.iden_lookup[game_state.player_1_iden], game_state.iden_lookup[game_state.player_2_iden]
-        if len(game_state.entities) != 2:
-            raise ValueError('SingleGameUpdater drives the two players; NPC entities use BatchedGameState.set_npc')
+        npcs = [e for e in game_state.entities if e.iden not in (game_state.player_1_iden, game_state.player_2_iden)]
+        if len(npcs) > _abi.MAX_NPC:
+            raise ValueError(f'at most {_abi.MAX_NPC} entities besides the two players (got {len(npcs)})')
+        self._idens = [game_state.player_1_iden, game_state.player_2_iden] + [e.iden for e in npcs]   # lane iden k + 1 -> the caller's
         separated = p1.depth != p2.depth
         cfg = SimConfig(width=self.dgen.width, height=self.dgen.height, dgen_kind=self.dgen.kind,
                         start_kind=_abi.START_SEPARATED if separated else _abi.START_TOGETHER,
                         start_depth=(p1.depth, p2.depth) if separated else (p1.depth, p1.depth),
                         hp=(p1.base_max_health, p2.base_max_health), damage=(p1.base_damage, p2.base_damage),
-                        armor=(p1.base_armor, p2.base_armor), seed=self._seed,
+                        armor=(p1.base_armor, p2.base_armor), seed=self._seed, n_npc=len(npcs),
                         fixed_tiles=getattr(self.dgen, 'tiles', None))
         lane = BatchedGameState(cfg, 1, self._device, game_id_base=self._game_id)
         lane.load_game_state(0, game_state)
+        for k, e in enumerate(npcs):
+            lane.set_npc(0, k, e.depth, e.x, e.y, e.health)
         self._lane = lane
+        self._expected = self._alive(game_state)
         self._moves = torch.empty((1, 2), dtype=torch.uint8, device=lane.device)
 
     def _level(self, stairs):
@@ -69,9 +79,10 @@ class SingleGameUpdater:
     def update(self, game_state, player1_move, player2_move):
         """Moves the game state forward in time and returns (UpdateResult, list of GameStateUpdate),
         mutating ``game_state`` exactly as updater.py:76-162 does."""
-        if self._lane is None:
-            self._bind(game_state)
+        if self._lane is None or self._alive(game_state) != self._expected:
+            self._bind(game_state)                 # first tick, or the caller added / removed entities itself
         lane, U = self._lane, self._updates
+        real = self._idens
         self._moves[0, 0], self._moves[0, 1] = int(player1_move), int(player2_move)
         result, ev = self._batched.update(lane, self._moves, want_events=True)
         recs = _updates.unpack_events(ev)[0]
@@ -81,6 +92,8 @@ class SingleGameUpdater:
             if kind == _abi.EV_NONE:
                 break
             order = self.get_incr_upd_order()
+            if kind != _abi.EV_DUNGEON:
+                iden = real[iden - 1]              # lane idens are 1, 2, 3 + slot
             if kind == _abi.EV_DUNGEON:
                 dung = self._level((a, b))
                 world.set_at_depth(depth, dung)                                  # updater.py:276-277
@@ -93,14 +106,31 @@ class SingleGameUpdater:
                 if kind == _abi.EV_DESCEND and self._should_despawn(game_state, old_depth):
                     world.del_at_depth(old_depth)                                # updater.py:295-296
             elif kind == _abi.EV_COMBAT:
-                defender = game_state.iden_lookup[a]
+                defender = game_state.iden_lookup[real[a - 1]]
                 if depth > 0:
                     defender.health -= depth                                     # updater.py:331-332
-                out.append(U.EntityCombatUpdate(order, iden, a, depth, {b}, [], []))
+                out.append(U.EntityCombatUpdate(order, iden, defender.iden, depth, {b}, [], []))
             elif kind == _abi.EV_DEATH:
                 out.append(U.EntityDeathUpdate(order, iden))
+                self._remove_entity(game_state, game_state.iden_lookup[iden])    # updater.py:137-145
         game_state.tick += 1                                                     # updater.py:148
+        self._expected = self._alive(game_state)
         return self._result_enum(int(result[0])), out
+
+    @staticmethod
+    def _alive(game_state):
+        """The idens the lane's NPC slots stand for, as the caller's state has them now."""
+        return tuple(e.iden for e in game_state.entities
+                     if e.iden not in (game_state.player_1_iden, game_state.player_2_iden))
+
+    @staticmethod
+    def _remove_entity(game_state, ent):
+        if hasattr(game_state, 'remove_entity'):
+            game_state.remove_entity(ent)                                        # state.py:84-88
+        else:
+            game_state.pos_lookup.pop((ent.depth, ent.x, ent.y), None)
+            game_state.iden_lookup.pop(ent.iden, None)
+            game_state.entities.remove(ent)
 
     @staticmethod
     def _move_entity(game_state, ent, depth, x, y):

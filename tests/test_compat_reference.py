@@ -33,6 +33,10 @@ class OracleLane:
             sx, sy = game_state.world.dungeons[ent.depth].staircase()
             s.stairs[0, 2 * k], s.stairs[0, 2 * k + 1] = sx, sy
         s.tick[0] = game_state.tick
+        npcs = [e for e in game_state.entities if e.iden not in (game_state.player_1_iden, game_state.player_2_iden)]
+        for k, e in enumerate(npcs):
+            s.npc_depth[0, k], s.npc_hp[0, k] = e.depth, e.health
+            s.npc_pos[0, k] = (e.x, e.y)
 
     def level_tiles(self, stairs):
         return empty_room_tiles(self.cfg.width, self.cfg.height, stairs)
@@ -93,3 +97,57 @@ def test_adapter_equals_reference_updater_on_reference_objects(despawn, bots):
             assert adapter.current_update_order == upd_ref.current_update_order
             if res_ref != ref.updater.UpdateResult.InProgress:
                 break
+
+
+def test_adapter_carries_npc_entities_like_the_reference():
+    """Entities besides the two players (updater.py:116-145) with arbitrary idens: they block tiles, take hits
+    (EntityCombatUpdate with their own iden), die (EntityDeathUpdate, removed from the GameState in reverse
+    entity order) -- tick by tick equal to the reference Updater on a small room where bumping into them is frequent."""
+    ref = rh.load_reference()
+    inj = rh.Injector(SEED)
+    inj.game_id = GID
+    W, H = 7, 6
+    with inj:
+        rdgen = inj.wrap_dgen(ref.worldgen.EmptyDungeonGenerator(W, H))
+        inj.site, inj.q = ('reset',), 0
+        gs_ref = ref.worldgen.TogetherGameStartGenerator(rdgen).setup_game()
+        inj.site = None
+        taken = {(e.x, e.y) for e in gs_ref.entities} | {gs_ref.world.dungeons[0].staircase()}
+        free = [(x, y) for x in range(1, W - 1) for y in range(1, H - 1) if (x, y) not in taken]
+        for iden, (x, y), hp in zip((9, 4, 17), free[::3], (1, 2, 3)):                 # idens neither contiguous nor ordered
+            gs_ref.add_entity(ref.entities.Entity(iden, 0, x, y, hp, hp, 0, 0, [], dict()))
+        gs_ours = ref.state.GameState.from_prims(gs_ref.to_prims())
+        upd_ref = inj.wrap_updater(ref.updater.Updater(rdgen, ref.updater.DungeonDespawningStrategy(1), 400), gs_ref)
+        cfg = SimConfig(width=W, height=H, max_ticks=400, seed=SEED, n_npc=3)
+        adapter = SingleGameUpdater(EmptyDungeonGenerator(W, H), 1, 400, seed=SEED, game_id=GID, device='cpu',
+                                    updates_module=ref.updates, world_module=ref.world, result_enum=ref.updater.UpdateResult)
+        lane = OracleLane(cfg, gs_ours)
+        adapter._lane, adapter._moves, adapter._batched = lane, torch.empty((1, 2), dtype=torch.uint8), lane
+        adapter._idens = [gs_ours.player_1_iden, gs_ours.player_2_iden, 9, 4, 17]
+        adapter._expected = adapter._alive(gs_ours)
+        b = [ref.randombot.RandomBot(1), ref.randombot.RandomBot(2)]
+        deaths = hits = 0
+        for t in range(400):
+            inj.tick, inj.shuffle_calls = gs_ref.tick, 0
+            gs_ref.on_tick()
+            inj.choice_slot = 0
+            m1 = b[0].move(gs_ref)
+            inj.choice_slot = 1
+            m2 = b[1].move(gs_ref)
+            res_ref, ev_ref = upd_ref.update(gs_ref, m1, m2)
+            res_ours, ev_ours = adapter.update(gs_ours, m1, m2)
+            assert res_ours == res_ref
+            assert gs_ours == gs_ref, f'tick {t}: GameStates differ'
+            assert [e.iden for e in gs_ours.entities] == [e.iden for e in gs_ref.entities]
+            assert [type(e) for e in ev_ours] == [type(e) for e in ev_ref]
+            for eo, er in zip(ev_ours, ev_ref):
+                assert eo.order == er.order
+                if isinstance(er, ref.updates.EntityCombatUpdate):
+                    assert (eo.attacker_iden, eo.defender_iden, eo.og_damage) == (er.attacker_iden, er.defender_iden, er.og_damage)
+                    hits += er.defender_iden > 2
+                elif isinstance(er, ref.updates.EntityDeathUpdate):
+                    assert eo.entity_iden == er.entity_iden
+                    deaths += 1
+            if res_ref != ref.updater.UpdateResult.InProgress:
+                break
+        assert hits > 0 and deaths > 0

@@ -58,7 +58,7 @@ def test_back_to_back_ticks_on_one_state(n, tpc):
 def test_long_unsynchronised_runs(n, ticks):
     """Hundreds of ticks in flight behind each other (a CUDA graph replayed without a pause), the state planes of
     the bigger batch far larger than what is in flight: the end state equals the oracle's after the same commands."""
-    cfg = SimConfig(max_ticks=97, seed=4242, auto_reset=True)
+    cfg = SimConfig(max_ticks=97, seed=4242, auto_reset=True, path_flags=_abi.PATH_FORCE_TILE_FLAGS)     # flag mode at 2^20 games too
     gs, upd, orc = gu.make_pair(cfg, n)
     per = 40
     g = torch.Generator(device='cuda').manual_seed(n)

@@ -69,3 +69,51 @@ def test_cuda_equals_live_reference(bots, despawn, start, episodes, max_ticks):
     assert gpu_ticks == ticks
     bad = np.flatnonzero(dg.h != want)
     assert len(bad) == 0, f'{len(bad)} of {episodes} episodes differ from the live reference, first {bad[:5]}'
+
+
+def test_single_game_adapter_on_cuda_equals_reference_updater():
+    """``SingleGameUpdater`` (the drop-in for the reference ``Updater`` on the reference's own GameState objects)
+    with a real CUDA lane behind it, NPC entities included, next to the reference ``Updater`` under the same
+    injected draws: equal results, equal GameStates (GameState.__eq__, game/state.py:134-153) and equal update
+    lists, tick by tick."""
+    from optimax_rogue_b200.logic.compat import SingleGameUpdater
+    ref = rh.load_reference()
+    seed, gid, W, H = 0xFEED, 4242, 7, 6
+    inj = rh.Injector(seed)
+    inj.game_id = gid
+    with inj:
+        rdgen = inj.wrap_dgen(ref.worldgen.EmptyDungeonGenerator(W, H))
+        inj.site, inj.q = ('reset',), 0
+        gs_ref = ref.worldgen.TogetherGameStartGenerator(rdgen).setup_game()
+        inj.site = None
+        taken = {(e.x, e.y) for e in gs_ref.entities} | {gs_ref.world.dungeons[0].staircase()}
+        free = [(x, y) for x in range(1, W - 1) for y in range(1, H - 1) if (x, y) not in taken]
+        for iden, (x, y), hp in zip((9, 4, 17), free[::3], (1, 2, 3)):
+            gs_ref.add_entity(ref.entities.Entity(iden, 0, x, y, hp, hp, 0, 0, [], dict()))
+        gs_ours = ref.state.GameState.from_prims(gs_ref.to_prims())
+        upd_ref = inj.wrap_updater(ref.updater.Updater(rdgen, ref.updater.DungeonDespawningStrategy(1), 400), gs_ref)
+        adapter = SingleGameUpdater(EmptyDungeonGenerator(W, H), 1, 400, seed=seed, game_id=gid, device='cuda',
+                                    updates_module=ref.updates, world_module=ref.world, result_enum=ref.updater.UpdateResult)
+        b = [ref.randombot.RandomBot(1), ref.randombot.RandomBot(2)]
+        deaths = 0
+        for t in range(400):
+            inj.tick, inj.shuffle_calls = gs_ref.tick, 0
+            gs_ref.on_tick()
+            inj.choice_slot = 0
+            m1 = b[0].move(gs_ref)
+            inj.choice_slot = 1
+            m2 = b[1].move(gs_ref)
+            res_ref, ev_ref = upd_ref.update(gs_ref, m1, m2)
+            res_ours, ev_ours = adapter.update(gs_ours, m1, m2)
+            assert res_ours == res_ref
+            assert gs_ours == gs_ref, f'tick {t}: GameStates differ'
+            assert [(type(e), e.order) for e in ev_ours] == [(type(e), e.order) for e in ev_ref]
+            for eo, er in zip(ev_ours, ev_ref):
+                if isinstance(er, ref.updates.EntityCombatUpdate):
+                    assert (eo.attacker_iden, eo.defender_iden, eo.og_damage) == (er.attacker_iden, er.defender_iden, er.og_damage)
+                elif isinstance(er, ref.updates.EntityDeathUpdate):
+                    assert eo.entity_iden == er.entity_iden
+                    deaths += 1
+            if res_ref != ref.updater.UpdateResult.InProgress:
+                break
+        assert deaths > 0

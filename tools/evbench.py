@@ -21,6 +21,13 @@ def run(n_npc, events, track=True, steps=60, reps=5):
         gs = BatchedGameState(cfg, G, dev, game_id_base=b * G)
         reset_games(gs)
         upd.rollout(gs, 1, 1, 17 * (b + 1))
+        if n_npc:      # scatter live NPCs over the first two levels (70% of the slots), as tests/test_gpu_parity.py does
+            gen = torch.Generator(device=dev).manual_seed(b)
+            live = torch.rand((G, n_npc), device=dev, generator=gen) < 0.7
+            gs.npc_depth.copy_(torch.where(live, torch.randint(0, 2, (G, n_npc), device=dev, generator=gen), torch.full((G, n_npc), -1, device=dev)).to(torch.int32))
+            gs.npc_pos[:, :, 0] = torch.randint(1, 59, (G, n_npc), device=dev, generator=gen).to(torch.uint8)
+            gs.npc_pos[:, :, 1] = torch.randint(1, 9, (G, n_npc), device=dev, generator=gen).to(torch.uint8)
+            gs.npc_hp.copy_(torch.randint(1, 7, (G, n_npc), device=dev, generator=gen).to(torch.int16))
         batches.append(gs)
     moves = torch.randint(1, 6, (8, G, 2), dtype=torch.uint8, device=dev)
     res = [torch.empty((G,), dtype=torch.uint8, device=dev) for _ in range(nb)]
@@ -44,6 +51,6 @@ def run(n_npc, events, track=True, steps=60, reps=5):
     return best * 1e3
 
 
-for n_npc, ev, track in ((0, False, False), (0, True, False), (0, True, True), (2, False, False), (8, False, False), (2, True, False)):
+for n_npc, ev, track in ((0, False, False), (0, True, False), (0, True, True), (1, False, False), (2, False, False), (4, False, False), (8, False, False), (2, True, False)):
     us = run(n_npc, ev, track)
     print(f'G={G} npc={n_npc} events={ev} track_order={track}: {us:.1f} us/step (CUDA graph), {G / us * 1e6:.3e} ticks/s', flush=True)
