@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ORX_ABI_VERSION 3
+#define ORX_ABI_VERSION 4
 
 /* logic/moves.py:6-12 */
 enum { ORX_MOVE_UP = 1, ORX_MOVE_RIGHT = 2, ORX_MOVE_DOWN = 3, ORX_MOVE_LEFT = 4, ORX_MOVE_STAY = 5 };
@@ -153,6 +153,15 @@ typedef struct OrxState {
     uint32_t* sched;
     uint32_t sched_words;
     uint32_t reserved;
+    /* Modifier seam (game/modifiers.py:92-108, game/attribles.py:21-43), nullable: int8[n][2][3], per player
+     * { sum of flat_damage, sum of flat_armor, sum of flat_max_health } over the modifiers the entity carries --
+     * what Entity.on_tick folds into damage.value / armor.value / max_health.value. A hit then deals
+     * (base_damage + flat_damage) - (base_armor + flat_armor) of the ATTACKER (updater.py:313); flat_max_health is
+     * carried for the host view only (nothing on the tick path reads max_health). Read-only for the tick, read in
+     * the combat branch only (no cost when NULL); it belongs to the lane, so a caller that models per-episode
+     * modifiers rewrites it when a lane's result says the episode ended. Modifier EVENT hooks (pre/on/post_event)
+     * are arbitrary Python upstream and have no counterpart here. */
+    const int8_t* flat;
 } OrxState;
 
 /* One replication-log record (logic/updates.py); slots of game i at events[i*max_events + k],

@@ -4,7 +4,7 @@ Kept free of torch so that the CPU test-suite can check the ABI without a GPU.
 """
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 MAX_NPC = 8
 MAX_EVENTS_BASE = 4
@@ -70,6 +70,7 @@ class OrxState(C.Structure):
         ('tick', C.c_void_p), ('episode', C.c_void_p), ('status', C.c_void_p),
         ('npc_pos', C.c_void_p), ('npc_hp', C.c_void_p), ('npc_depth', C.c_void_p),
         ('sched', C.c_void_p), ('sched_words', C.c_uint32), ('reserved', C.c_uint32),
+        ('flat', C.c_void_p),
     ]
 
 

@@ -340,7 +340,7 @@ int check_common(const OrxConfig* cfg, const OrxState* st, int64_t n)
     for (int k = 0; k < 2; ++k) {   // health lives in int16 planes; a hit is subtracted from them
         if (cfg->hp[k] < 1 || cfg->hp[k] > 32767) return ORX_ERR_BAD_ARG;
         const int64_t hit = (int64_t)cfg->damage[k] - (int64_t)cfg->armor[k];
-        if (hit < -32767 || hit > 32767) return ORX_ERR_BAD_ARG;
+        if (hit < -32767 + 254 || hit > 32767 - 254) return ORX_ERR_BAD_ARG;      // room for the int8 flat bonuses (OrxState.flat)
     }
     if (cfg->dgen_kind == ORX_DGEN_FIXED) {
         if (cfg->fixed_tiles == nullptr || cfg->fixed_ground == nullptr) return ORX_ERR_BAD_ARG;
@@ -373,6 +373,7 @@ Params make_params(const OrxConfig* c, const OrxState* st, int64_t n, uint64_t g
     P.depth = reinterpret_cast<int2*>(st->depth); P.stairs = reinterpret_cast<uint32_t*>(st->stairs);
     P.tick = st->tick; P.episode = st->episode; P.status = st->status;
     P.npc_pos = st->npc_pos; P.npc_hp = st->npc_hp; P.npc_depth = st->npc_depth;
+    P.flat = st->flat;
     P.n = (unsigned int)n; P.gid_base = gid_base;
     return P;
 }
@@ -412,6 +413,7 @@ Params offset_params(const Params& P, int64_t off, int64_t n)
     Params T = P;
     T.pos += off; T.hp += off; T.depth += off; T.stairs += off; T.tick += off; T.episode += off; T.status += off;
     if (P.n_npc > 0) { T.npc_pos += 2 * off * P.n_npc; T.npc_hp += off * P.n_npc; T.npc_depth += off * P.n_npc; }
+    if (P.flat != nullptr) T.flat += 6 * off;
     T.n = (unsigned int)n; T.gid_base = P.gid_base + (unsigned long long)off;
     return T;
 }

@@ -141,6 +141,8 @@ class BatchedGameState:
         self.npc_depth = torch.full((n, e), -1, dtype=torch.int32, device=dev)
         # scratch of the tick kernel (OrxState.sched): tile counter + per-tile hand-over words, never shared
         self.sched = torch.zeros((_abi.sched_words(n),), dtype=torch.int32, device=dev)
+        # Modifier seam (OrxState.flat): None until enable_flat_bonuses() -- the tick then never looks for it
+        self.flat = None
         # the fixed map (shared by all games) lives beside the state
         self.fixed_tiles = self.fixed_ground = None
         self._fixed_stairs = (_abi.NO_STAIRS, _abi.NO_STAIRS)
@@ -173,6 +175,7 @@ class BatchedGameState:
             setattr(st, name, getattr(self, name).data_ptr())
         st.sched = self.sched.data_ptr() if self.sched.is_cuda else None
         st.sched_words = int(self.sched.numel())
+        st.flat = self.flat.data_ptr() if self.flat is not None else None
         return st
 
     def c_config(self, **overrides) -> _abi.OrxConfig:
@@ -210,6 +213,7 @@ class BatchedGameState:
             else:
                 setattr(o, name, getattr(self, name).clone())
         o.sched = torch.zeros_like(self.sched)
+        o.flat = self.flat.clone() if self.flat is not None else None
         return o
 
     def _fingerprint(self):
@@ -225,6 +229,8 @@ class BatchedGameState:
         d = {name: getattr(self, name).detach().clone() for name in self.PLANES}
         d['game_id_base'] = self.game_id_base
         d['fingerprint'] = self._fingerprint()
+        if self.flat is not None:
+            d['flat'] = self.flat.detach().clone()
         return d
 
     def load_state_dict(self, d):
@@ -244,7 +250,20 @@ class BatchedGameState:
         for name in self.PLANES:
             getattr(self, name).copy_(d[name])
         self.game_id_base = int(d['game_id_base'])
+        if d.get('flat') is not None:
+            self.enable_flat_bonuses().copy_(d['flat'])
+        elif self.flat is not None:
+            self.flat.zero_()
         self.sched.zero_()          # no launch is in flight across a restore
+
+    def enable_flat_bonuses(self) -> torch.Tensor:
+        """Allocates (once) and returns the Modifier seam plane int8[N,2,3]: per player the sums of
+        ``flat_damage``, ``flat_armor``, ``flat_max_health`` over the modifiers its entity carries
+        (game/modifiers.py:102-108, folded in by Entity.on_tick, game/attribles.py:21-43). A hit then deals
+        ``(base_damage + flat_damage) - (base_armor + flat_armor)`` of the attacker. Zero = no modifier."""
+        if self.flat is None:
+            self.flat = torch.zeros((self.n, 2, 3), dtype=torch.int8, device=self.device)
+        return self.flat
 
     def set_npc(self, lane: int, slot: int, depth: int, x: int, y: int, health: int):
         """Places a static NPC (an extra Entity after the players, updater.py:116-128)."""

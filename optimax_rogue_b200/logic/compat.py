@@ -44,6 +44,7 @@ class SingleGameUpdater:
         self._lane = None
         self._moves = None
         self._idens, self._expected = [1, 2], ()
+        self._flat_rows = None
 
     def get_incr_upd_order(self):
         """updater.py:71-74"""
@@ -83,6 +84,7 @@ class SingleGameUpdater:
             self._bind(game_state)                 # first tick, or the caller added / removed entities itself
         lane, U = self._lane, self._updates
         real = self._idens
+        self._sync_flat_bonuses(game_state)
         self._moves[0, 0], self._moves[0, 1] = int(player1_move), int(player2_move)
         result, ev = self._batched.update(lane, self._moves, want_events=True)
         recs = _updates.unpack_events(ev)[0]
@@ -116,6 +118,23 @@ class SingleGameUpdater:
         game_state.tick += 1                                                     # updater.py:148
         self._expected = self._alive(game_state)
         return self._result_enum(int(result[0])), out
+
+    def _sync_flat_bonuses(self, game_state):
+        """The players' modifiers (game/modifiers.py:92-108): their flat bonuses are what Entity.on_tick folds into
+        damage.value / armor.value / max_health.value (game/attribles.py:21-43); the lane takes the sums through
+        OrxState.flat. Modifier event hooks are not run (see include/orx.h)."""
+        rows = []
+        for iden in (game_state.player_1_iden, game_state.player_2_iden):
+            mods = getattr(game_state.iden_lookup[iden], 'modifiers', None) or []
+            rows.append([sum(int(m.flat_damage) for m in mods), sum(int(m.flat_armor) for m in mods),
+                         sum(int(m.flat_max_health) for m in mods)])
+        if self._lane.flat is None and not any(v for row in rows for v in row):
+            return
+        if any(not -128 <= v <= 127 for row in rows for v in row):
+            raise ValueError('flat modifier bonuses must fit int8')
+        if rows != self._flat_rows:
+            self._lane.enable_flat_bonuses()[0] = torch.tensor(rows, dtype=torch.int8)
+            self._flat_rows = rows
 
     @staticmethod
     def _alive(game_state):

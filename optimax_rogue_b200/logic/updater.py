@@ -99,7 +99,8 @@ class BatchedUpdater:
                int(self.path_flags) | int(c.path_flags), gs.sched.data_ptr(), int(gs.sched.numel()),
                c.width, c.height, c.dgen_kind, c.start_kind, tuple(c.start_depth), tuple(c.hp), tuple(c.damage),
                tuple(c.armor), c.n_npc, c.seed,
-               gs.fixed_tiles.data_ptr() if gs.fixed_tiles is not None else 0) + tuple(getattr(gs, name).data_ptr() for name in gs.PLANES)
+               gs.fixed_tiles.data_ptr() if gs.fixed_tiles is not None else 0,
+               gs.flat.data_ptr() if gs.flat is not None else 0) + tuple(getattr(gs, name).data_ptr() for name in gs.PLANES)
         if self._cache is None or self._cache[0] != key:
             if (gs.cfg.width, gs.cfg.height, gs.cfg.dgen_kind) != (self.dgen.width, self.dgen.height, self.dgen.kind):
                 raise ValueError('updater.dgen does not match the generator the game state was built with')

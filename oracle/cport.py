@@ -96,6 +96,12 @@ class HostState:
         self.npc_pos = np.zeros((n, e, 2), np.uint8)
         self.npc_hp = np.zeros((n, e), np.int16)
         self.npc_depth = np.full((n, e), -1, np.int32)
+        self.flat = None            # Modifier seam: int8[n, 2, 3] once enable_flat_bonuses() was called
+
+    def enable_flat_bonuses(self):
+        if self.flat is None:
+            self.flat = np.zeros((self.n, 2, 3), np.int8)
+        return self.flat
 
     PLANES = ('pos', 'hp', 'depth', 'stairs', 'tick', 'episode', 'status',
               'npc_pos', 'npc_hp', 'npc_depth')
@@ -104,6 +110,7 @@ class HostState:
         st = _abi.OrxState()
         for name in self.PLANES:
             setattr(st, name, getattr(self, name).ctypes.data)
+        st.flat = self.flat.ctypes.data if self.flat is not None else None
         return st
 
     def copy(self):
@@ -111,6 +118,7 @@ class HostState:
         o.n, o.n_npc = self.n, self.n_npc
         for name in self.PLANES:
             setattr(o, name, getattr(self, name).copy())
+        o.flat = None if self.flat is None else self.flat.copy()
         return o
 
 

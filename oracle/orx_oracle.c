@@ -106,6 +106,7 @@ typedef struct {
     Entity ent[MAX_ENT];        /* entities list: players then NPC slots */
     int n_ent;
     int stairs[2][2];           /* staircase of each player's level */
+    int flat[2][3];             /* per player: flat damage / armor / max-health bonus of its modifiers (OrxState.flat) */
     OrxEvent* ev;               /* nullable */
     int n_ev, max_ev;
     unsigned long long* stats;  /* nullable */
@@ -204,11 +205,13 @@ static int level_exists(const Game* g, int p, int depth)
     return o_start <= depth && depth <= o->depth;
 }
 
-/* updater.py:298-338; no modifiers exist, so damage = attacker.damage - attacker.armor (:313) */
+/* updater.py:298-338: damage = attacker.damage.value - attacker.armor.value (:313), the attribles being the base
+ * stat plus the flat bonuses of the entity's modifiers (attribles.py:29-43; OrxState.flat, zero when absent).
+ * Modifier event hooks are not modelled (no concrete modifier exists upstream). */
 static void handle_combat(Game* g, int att, int def, int flag)
 {
     int p = att; /* only players ever attack: NPC moves are always Stay (updater.py:165-178) */
-    int og_dmg = g->cfg->damage[p] - g->cfg->armor[p];
+    int og_dmg = (g->cfg->damage[p] + g->flat[p][0]) - (g->cfg->armor[p] + g->flat[p][1]);
     if (og_dmg > 0) {
         g->ent[def].health -= og_dmg;
         if (g->stats) g->stats[ORX_STAT_HITS]++;
@@ -365,6 +368,9 @@ static void load_game(Game* g, const OrxConfig* cfg, const OrxState* st, int64_t
         e->depth = st->depth[2 * i + p]; e->health = st->hp[2 * i + p];
         g->stairs[p][0] = st->stairs[4 * i + 2 * p]; g->stairs[p][1] = st->stairs[4 * i + 2 * p + 1];
     }
+    if (st->flat != NULL)
+        for (int p = 0; p < 2; ++p)
+            for (int k = 0; k < 3; ++k) g->flat[p][k] = st->flat[6 * i + 3 * p + k];
     g->n_ent = 2 + cfg->n_npc;
     for (int k = 0; k < cfg->n_npc; ++k) {
         Entity* e = &g->ent[2 + k];

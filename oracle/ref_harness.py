@@ -209,6 +209,31 @@ def make_fixed_generator(ref, tiles: np.ndarray):
     return FixedDungeonGenerator(tiles)
 
 
+def make_flat_modifier(ref, parent, flat_damage=0, flat_armor=0, flat_max_health=0):
+    """The smallest concrete ``Modifier`` (game/modifiers.py:92-150): only the three flat bonuses that
+    ``Entity.on_tick`` folds into the attribles (game/attribles.py:21-43); its event hooks do nothing."""
+    class FlatBonus(ref.entities.Modifier if hasattr(ref.entities, 'Modifier') else __import__(
+            'optimax_rogue.game.modifiers', fromlist=['Modifier']).Modifier):
+        name = 'flat bonus'
+        description = 'test modifier: flat stat bonuses only'
+
+        def copy(self, ent):
+            return type(self)(ent, self.flat_armor, self.flat_max_health, self.flat_damage)
+
+        def handles(self, event_name):
+            return False
+
+        def pre_event(self, event_name, game_state, args):
+            return None
+
+        def on_event(self, event_name, game_state, args, prevals):
+            return None
+
+        def post_event(self, event_name, game_state, args, prevals):
+            return None
+    return FlatBonus(parent, flat_armor, flat_max_health, flat_damage)
+
+
 class ScriptedBot:
     """Plays a fixed list of move codes (then Stay)."""
     def __init__(self, ref, codes):
@@ -232,7 +257,7 @@ def _event_tuple(ref, ev):
             assert ev.old_depth == ev.depth - 1
         return (code, ev.entity_iden, ev.posx, ev.posy, ev.depth)
     if isinstance(ev, u.EntityCombatUpdate):
-        assert len(ev.tags) == 1 and not ev.attack_prevals and not ev.defend_prevals
+        assert len(ev.tags) == 1 and not any(ev.attack_prevals) and not any(ev.defend_prevals)    # flat-bonus test modifiers return None
         return (EV_COMBAT, ev.attacker_iden, ev.defender_iden, int(next(iter(ev.tags))),
                 ev.og_damage)
     if isinstance(ev, u.DungeonCreatedUpdate):
@@ -268,7 +293,7 @@ def snapshot(gs, result, events):
 def play_episode(seed, game_id, episode=0, *, bots=('random', 'random'), width=60, height=10,
                  start='together', p_depths=(0, 1000), despawn='unreachable', max_ticks=512,
                  fixed_tiles=None, npcs=(), scripts=None, limit_ticks=None,
-                 hp=10, damage=2, armor=1, want_order=False, place=None):
+                 hp=10, damage=2, armor=1, want_order=False, place=None, flat=None):
     """Plays one episode on the live reference under injected draws.
 
     Returns the list of records: record 0 is the post-reset state, record t>0 the
@@ -294,6 +319,9 @@ def play_episode(seed, game_id, episode=0, *, bots=('random', 'random'), width=6
         for k, ent in enumerate((gs.player_1, gs.player_2)):
             ent.health, ent.base_max_health = hp2[k], hp2[k]
             ent.base_damage, ent.base_armor = dmg2[k], arm2[k]
+        if flat is not None:       # ((flat_damage, flat_armor, flat_max_health) of p1, the same of p2): one modifier each
+            for ent, (fd, fa, fm) in zip((gs.player_1, gs.player_2), flat):
+                ent.modifiers.append(make_flat_modifier(ref, ent, fd, fa, fm))
         if place is not None:
             for ent, (px_, py_) in zip((gs.player_1, gs.player_2), place):
                 ent.x, ent.y = int(px_), int(py_)

@@ -38,6 +38,13 @@ class OracleLane:
             s.npc_depth[0, k], s.npc_hp[0, k] = e.depth, e.health
             s.npc_pos[0, k] = (e.x, e.y)
 
+        self.flat = None
+
+    def enable_flat_bonuses(self):
+        if self.flat is None:
+            self.flat = torch.from_numpy(self.orc.state.enable_flat_bonuses())
+        return self.flat
+
     def level_tiles(self, stairs):
         return empty_room_tiles(self.cfg.width, self.cfg.height, stairs)
 
@@ -151,3 +158,51 @@ def test_adapter_carries_npc_entities_like_the_reference():
             if res_ref != ref.updater.UpdateResult.InProgress:
                 break
         assert hits > 0 and deaths > 0
+
+
+def test_adapter_honours_flat_modifiers_on_reference_entities():
+    """Players that carry a Modifier (game/modifiers.py:92-108): the adapter reads the flat bonuses off the reference
+    entities every tick and the hits equal the reference Updater's (updater.py:313 through the attribles)."""
+    ref = rh.load_reference()
+    inj = rh.Injector(SEED)
+    inj.game_id = GID
+    W, H = 5, 5
+    with inj:
+        rdgen = inj.wrap_dgen(ref.worldgen.EmptyDungeonGenerator(W, H))
+        inj.site, inj.q = ('reset',), 0
+        gs_ref = ref.worldgen.TogetherGameStartGenerator(rdgen).setup_game()
+        inj.site = None
+        for ent in (gs_ref.player_1, gs_ref.player_2):
+            ent.health = ent.base_max_health = 40
+        gs_ours = ref.state.GameState.from_prims(gs_ref.to_prims())
+        for gs in (gs_ref, gs_ours):
+            gs.player_1.modifiers.append(rh.make_flat_modifier(ref, gs.player_1, flat_damage=3, flat_max_health=2))
+            gs.player_2.modifiers.append(rh.make_flat_modifier(ref, gs.player_2, flat_armor=-1))
+            gs.player_2.modifiers.append(rh.make_flat_modifier(ref, gs.player_2, flat_damage=1))
+        upd_ref = inj.wrap_updater(ref.updater.Updater(rdgen, ref.updater.DungeonDespawningStrategy(1), 300), gs_ref)
+        cfg = SimConfig(width=W, height=H, max_ticks=300, seed=SEED, hp=(40, 40))
+        adapter = SingleGameUpdater(EmptyDungeonGenerator(W, H), 1, 300, seed=SEED, game_id=GID, device='cpu',
+                                    updates_module=ref.updates, world_module=ref.world, result_enum=ref.updater.UpdateResult)
+        lane = OracleLane(cfg, gs_ours)
+        adapter._lane, adapter._moves, adapter._batched = lane, torch.empty((1, 2), dtype=torch.uint8), lane
+        b = [ref.randombot.RandomBot(1), ref.randombot.RandomBot(2)]
+        dmg = set()
+        for t in range(300):
+            inj.tick, inj.shuffle_calls = gs_ref.tick, 0
+            gs_ref.on_tick()
+            gs_ours.on_tick()
+            inj.choice_slot = 0
+            m1 = b[0].move(gs_ref)
+            inj.choice_slot = 1
+            m2 = b[1].move(gs_ref)
+            res_ref, ev_ref = upd_ref.update(gs_ref, m1, m2)
+            res_ours, ev_ours = adapter.update(gs_ours, m1, m2)
+            assert res_ours == res_ref
+            assert [(e.x, e.y, e.depth, e.health) for e in gs_ours.entities] == [(e.x, e.y, e.depth, e.health) for e in gs_ref.entities], t
+            for eo, er in zip(ev_ours, ev_ref):
+                if isinstance(er, ref.updates.EntityCombatUpdate):
+                    assert (eo.attacker_iden, eo.defender_iden, eo.og_damage) == (er.attacker_iden, er.defender_iden, er.og_damage)
+                    dmg.add((er.attacker_iden, er.og_damage))
+            if res_ref != ref.updater.UpdateResult.InProgress:
+                break
+        assert dmg == {(1, 2 + 3 - 1), (2, 2 + 1 - 1 + 1)}

@@ -843,3 +843,32 @@ def test_npc_slots_through_the_tile_pipeline(n_npc):
         gu.assert_state_equal(a, orc, f'tick {t} (pipeline)')
     gu.assert_state_equal(b, orc, 'simple kernel')
     assert int((a.npc_depth < 0).sum()) > culled0      # some NPCs were killed and culled (updater.py:137-145)
+
+
+@pytest.mark.parametrize('n', [256 * 9 + 31, 200])
+def test_flat_modifier_bonuses_match_oracle(n):
+    """The Modifier seam (OrxState.flat; game/modifiers.py:102-108, game/attribles.py:21-43, updater.py:313): random
+    per-game flat damage / armor bonuses for both players, small rooms so that fights are frequent; tile pipeline
+    and simple kernel (ragged tail / small batch), with the event log (og_damage is part of the record)."""
+    cfg = SimConfig(width=5, height=5, max_ticks=60, seed=77, auto_reset=True, hp=(30, 25), damage=(2, 3), armor=(1, 1))
+    gs, upd, orc = gu.make_pair(cfg, n)
+    rng = np.random.default_rng(n)
+    flat = rng.integers(-4, 9, size=(n, 2, 3)).astype(np.int8)
+    flat[::7] = 0
+    flat[5, 0] = (127, -128, 0)
+    gs.enable_flat_bonuses().copy_(torch.from_numpy(flat))
+    orc.state.enable_flat_bonuses()[:] = flat
+    hits = 0
+    for t in range(90):
+        mv = rng.integers(1, 6, size=(n, 2), dtype=np.uint8)
+        ro, eo = orc.step(mv, want_events=True)
+        want_ev = t % 2 == 0
+        rg, eg = upd.update(gs, torch.from_numpy(mv).cuda(), want_events=want_ev)
+        assert np.array_equal(rg.cpu().numpy(), ro), t
+        if want_ev:
+            assert np.array_equal(eg.cpu().numpy(), eo), t
+            hits += int(((eo[:, :, 0] & 0xFF) == _abi.EV_COMBAT).sum())
+        gu.assert_state_equal(gs, orc, f'tick {t}')
+    assert hits > n // 4
+    c = gs.clone()
+    assert torch.equal(c.flat, gs.flat) and c.flat.data_ptr() != gs.flat.data_ptr()

@@ -117,3 +117,38 @@ def test_single_game_adapter_on_cuda_equals_reference_updater():
             if res_ref != ref.updater.UpdateResult.InProgress:
                 break
         assert deaths > 0
+
+
+def test_cuda_equals_live_reference_with_flat_modifiers():
+    """Entities that carry a Modifier with flat bonuses (the smallest concrete subclass, oracle/ref_harness.make_flat_modifier):
+    the reference folds them into damage.value / armor.value in Entity.on_tick; the CUDA lane takes the same sums through
+    OrxState.flat. One lane per episode, every episode with its own bonuses."""
+    episodes, max_ticks, gid0 = 96, 150, 9_000_000
+    rng = np.random.default_rng(3)
+    flat = rng.integers(-2, 6, size=(episodes, 2, 3)).astype(np.int8)
+    kw = dict(width=5, height=5, max_ticks=max_ticks, hp=(25, 30), damage=(2, 3), armor=(1, 1))
+    want = np.empty(episodes, np.uint64)
+    for k in range(episodes):
+        trace, _ = rh.play_episode(SEED, gid0 + k, bots=('random', 'random'), flat=[tuple(int(v) for v in flat[k, p]) for p in range(2)], **kw)
+        want[k] = rh.digest(trace)
+    cfg = SimConfig(seed=SEED, **kw)
+    gs = BatchedGameState(cfg, episodes, 'cuda', game_id_base=gid0)
+    reset_games(gs)
+    gs.enable_flat_bonuses().copy_(torch.from_numpy(flat))
+    upd = BatchedUpdater(EmptyDungeonGenerator(5, 5), 1, max_ticks)
+    dg = tu.BatchDigest(episodes)
+    active = np.ones(episodes, bool)
+    p = gs.planes_cpu()
+    dg.update(p['pos'], p['hp'], p['depth'], p['stairs'], p['tick'], p['status'], None, active)
+    moves = torch.full((episodes, 2), 5, dtype=torch.uint8, device='cuda')
+    for _ in range(max_ticks):
+        upd.bot_moves(gs, 1, 1, out=moves)
+        res, ev = upd.update(gs, moves, want_events=True)
+        p = gs.planes_cpu()
+        r = res.cpu().numpy()
+        dg.update(p['pos'], p['hp'], p['depth'], p['stairs'], p['tick'], r, ev.cpu().numpy(), active)
+        active &= r == 1
+        if not active.any():
+            break
+    bad = np.flatnonzero(dg.h != want)
+    assert len(bad) == 0, f'{len(bad)} of {episodes} episodes differ from the live reference, first {bad[:5]}'

@@ -75,6 +75,25 @@ def test_npc_slots():
                 dict(width=8, height=6, max_ticks=150, hp=50), npcs=npcs)
 
 
+def test_flat_modifier_bonuses():
+    """The Modifier seam (game/modifiers.py:102-108 -> game/attribles.py:21-43 -> updater.py:313): players that carry
+    a modifier with flat damage / armor / max-health bonuses, in rooms small enough to fight all the time. The oracle
+    takes the same sums through OrxState.flat."""
+    cases = [((3, 0, 2), (0, 1, 0)), ((0, 0, 0), (5, 2, -3)), ((-1, 0, 0), (0, -2, 7)), ((127, 0, 0), (0, 127, -128))]
+    n_hits = 0
+    for gid, flat in enumerate(cases):
+        kw = dict(width=5, height=5, max_ticks=300, hp=(40, 35), damage=(2, 3), armor=(1, 1))
+        tr, mv = rh.play_episode(SEED, gid, bots=('random', 'random'), flat=flat, **kw)
+        to, mo = tu.oracle_episode(SimConfig(seed=SEED, **kw), gid, bots=('random', 'random'), flat=flat)
+        assert [tu.strip(r) for r in tr] == to, flat
+        assert mv == mo
+        hits = [e for r in tr for e in r['events'] if e[0] == rh.EV_COMBAT]
+        want = {1: 2 + flat[0][0] - 1 - flat[0][1], 2: 3 + flat[1][0] - 1 - flat[1][1]}
+        assert all(e[4] == want[e[1]] for e in hits)
+        n_hits += len(hits)
+    assert n_hits > 3
+
+
 from hypothesis import given, settings, strategies as st
 
 

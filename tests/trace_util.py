@@ -31,11 +31,13 @@ def strip(rec):
 
 
 def oracle_episode(cfg, game_id, bots=('random', 'random'), scripts=None, limit_ticks=None,
-                   npcs=(), place=None):
+                   npcs=(), place=None, flat=None):
     """Plays one game on the C oracle; returns (trace, moves_log) like rh.play_episode."""
     orc = cport.Oracle(cfg, 1, game_id_base=game_id)
     orc.reset()
     s = orc.state
+    if flat is not None:
+        s.enable_flat_bonuses()[0] = flat
     if place is not None:
         s.pos[0] = (place[0][0], place[0][1], place[1][0], place[1][1])
     for k, (nd, nx, ny, nhp) in enumerate(npcs):
