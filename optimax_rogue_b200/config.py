@@ -27,6 +27,12 @@ class SimConfig:
     fixed_tiles: typing.Optional[np.ndarray] = None   # uint8[W,H] Tile codes (DGEN_FIXED)
     path_flags: int = 0                 # _abi.PATH_* bits: pins a kernel path for tests / A-B runs, never changes results
 
+    def __setattr__(self, name, value):
+        # every assignment bumps a version number: holders of structs marshalled from this config (BatchedUpdater)
+        # notice a later mutation with one integer compare instead of re-reading fifteen fields per tick
+        object.__setattr__(self, name, value)
+        object.__setattr__(self, '_version', getattr(self, '_version', 0) + 1)
+
     def validate(self):
         if not (4 <= self.width <= _abi.MAX_DIM and 4 <= self.height <= _abi.MAX_DIM):
             raise ValueError(f'width/height must be in [4, {_abi.MAX_DIM}]')

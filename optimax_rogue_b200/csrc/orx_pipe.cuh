@@ -106,14 +106,19 @@ template <bool OBS, bool EV = false, int NPC = 0> constexpr uint32_t kPipeStageB
 constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1, CMD_BYTES_BOTS = 2;   // _BOTS: uint8[n][2], scripted players' commands computed in the kernel
 // CMD_BITS: the bit-packed streams of orx_step_bits (orx.h): 5 bits of command pair per game in, 2 bits of result
 // per game out -- what crosses PCIe when the caller's buffers live in host memory. A CTA then owns a CONTIGUOUS
-// run of tiles (tiles_per_cta of them), fetches the commands of all of them with ONE bulk copy when it starts and
-// sends the results of all of them with ONE bulk copy when it ends: two large PCIe transactions per CTA instead of
-// two small ones per tile, none of them on a tile's critical path.
+// run of tiles (tiles_per_cta of them). It requests the commands of its whole run when it starts, four tiles
+// (640 bytes) per bulk copy, each copy with its own mbarrier: the link serves the requests of all CTAs roughly in
+// the order they were issued, so every CTA has its first tiles' commands within a couple of microseconds and the
+// later ones arrive while it works (one copy for the whole run made a CTA wait for its whole share of the link's
+// 16 us per 2^20 games before its first tile: 27 instead of ~18 us per tick). The results of the run go back with
+// ONE bulk copy when the CTA ends. No PCIe transaction sits on a tile's critical path.
 constexpr int CMD_BITS = 3;
 constexpr uint32_t kCmdBitsTile = 5u * kTile / 8u, kResBitsTile = 2u * kTile / 8u;      // 160 and 64 bytes per tile
 constexpr uint32_t kBitsMaxTiles = 32;                                                    // tiles per CTA in CMD_BITS mode
 constexpr uint32_t kBitsCmdBytes = kBitsMaxTiles * kCmdBitsTile + 16u, kBitsResBytes = kBitsMaxTiles * kResBitsTile;
-constexpr uint32_t kBitsSmemBytes = 16u + kBitsCmdBytes + kBitsResBytes;                 // mbarrier + command block + result block
+constexpr uint32_t kBitsCmdChunk = 4;                                                     // tiles per command fetch
+constexpr uint32_t kBitsBarBytes = 8u * (kBitsMaxTiles / kBitsCmdChunk);                  // one mbarrier per command fetch
+constexpr uint32_t kBitsSmemBytes = kBitsBarBytes + kBitsCmdBytes + kBitsResBytes;       // mbarriers + command block + result block
 static_assert(kCmdBitsTile % 16 == 0 && kResBitsTile % 16 == 0, "bit-packed tiles move as bulk copies");
 static_assert(kTile % 32 == 0 && (T1 % 16) == 0, "bulk copies move multiples of 16 bytes");
 static_assert(OFF_HP == OFF_POS + T4 && OFF_ST == OFF_HP + T4 && OFF_TICK == OFF_ST + T4 && OFF_EP == OFF_TICK + T4 && kTile <= 256,
@@ -265,14 +270,17 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);   // full[kStages], done[kStages]
     constexpr uint32_t kBitsBytes = CMD == CMD_BITS ? kBitsSmemBytes : 0u;
     const uint32_t bits0 = smem_addr(smem + kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes + kTicketBytes);
-    const uint32_t cmdbar = bits0, cmd0 = bits0 + 16u, res0 = cmd0 + kBitsCmdBytes;      // CMD_BITS only
+    const uint32_t cmdbar = bits0, cmd0 = bits0 + kBitsBarBytes, res0 = cmd0 + kBitsCmdBytes;      // CMD_BITS only
     uint8_t* tiles_sm = smem + kStages * STAGE_BYTES + 2 * kStages * 8 + kTileIdxBytes + kTicketBytes + kBitsBytes;
     const uint32_t full0 = smem_addr(bars), done0 = smem_addr(bars + kStages);
     const uint32_t tidx0 = smem_addr(bars + 2 * kStages);      // tile index published with each stage
     const uint32_t tk0 = tidx0 + kTileIdxBytes;                // flag mode: this CTA's ticket of each of its chunks
     const uint32_t stage0 = smem_addr(stages);
     const unsigned int tid = threadIdx.x;
-    const bool flagged = flags != nullptr;
+#ifndef ORX_PIPE_FLAGS
+#define ORX_PIPE_FLAGS 1            // 0: tuning builds without the flag-mode code (code-size A/B)
+#endif
+    const bool flagged = ORX_PIPE_FLAGS && flags != nullptr;
     // Programmatic dependent launch: the next kernel in the stream may begin while this grid is still
     // running. Grid-wait mode: at once; its producer waits for this grid to complete
     // (griddepcontrol.wait) before it touches any plane. Flag mode: only after this CTA holds the tickets
@@ -284,7 +292,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             mbar_init(full0 + 8 * s, 1);
             mbar_init(done0 + 8 * s, kTile / 32);
         }
-        if (CMD == CMD_BITS) mbar_init(cmdbar, 1);
+        if (CMD == CMD_BITS) for (uint32_t c = 0; c < kBitsMaxTiles / kBitsCmdChunk; ++c) mbar_init(cmdbar + 8u * c, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __shared__ CmdEntry lut[256];
@@ -369,8 +377,11 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             if (CMD == CMD_BITS) {
                 const uint64_t first = (uint64_t)blockIdx.x * tiles_per_cta;
                 const uint32_t cnt = (uint32_t)(n_tiles - first < tiles_per_cta ? n_tiles - first : tiles_per_cta);
-                mbar_expect_tx(cmdbar, cnt * kCmdBitsTile);
-                bulk_load(cmd0, moves + first * kCmdBitsTile, cnt * kCmdBitsTile, cmdbar);
+                for (uint32_t t = 0; t < cnt; t += kBitsCmdChunk) {
+                    const uint32_t bytes = (cnt - t < kBitsCmdChunk ? cnt - t : kBitsCmdChunk) * kCmdBitsTile, bar = cmdbar + 8u * (t / kBitsCmdChunk);
+                    mbar_expect_tx(bar, bytes);
+                    bulk_load(cmd0 + t * kCmdBitsTile, moves + (first + t) * kCmdBitsTile, bytes, bar);
+                }
             }
         };
         bool ended = false;
@@ -576,7 +587,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
         if (TICK) {
             uint32_t mv;
             if (CMD == CMD_BITS) {
-                if (it == 0) mbar_wait(cmdbar, 0u);
+                mbar_wait(cmdbar + 8u * (it / kBitsCmdChunk), 0u);         // this tile's commands have arrived (no wait once its fetch is complete)
                 // game g of the tile: bits [5g, 5g + 5) of the tile's 160 bytes; v = (p1 - 1) * 5 + (p2 - 1), 25..31 = both Stay
                 const uint32_t a = cmd0 + it * kCmdBitsTile + ((tid * 5u) >> 3);
                 const uint32_t v = ((lds_u8(a) | (lds_u8(a + 1u) << 8)) >> ((tid * 5u) & 7u)) & 31u;

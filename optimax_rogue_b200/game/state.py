@@ -124,6 +124,14 @@ class BatchedGameState:
 
     PLANES = ('pos', 'hp', 'depth', 'stairs', 'tick', 'episode', 'status',
               'npc_pos', 'npc_hp', 'npc_depth')
+    _LAYOUT = frozenset(PLANES + ('sched', 'flat', 'fixed_tiles', 'fixed_ground', 'cfg', 'game_id_base', 'n'))
+
+    def __setattr__(self, name, value):
+        # (re)binding a plane, the scratch, the bonus plane or the config changes what the C structs must point at:
+        # bump a version so that BatchedUpdater re-marshals them (one integer compare per tick otherwise)
+        object.__setattr__(self, name, value)
+        if name in self._LAYOUT:
+            object.__setattr__(self, '_layout_version', getattr(self, '_layout_version', 0) + 1)
 
     def __init__(self, cfg: SimConfig, n: int, device='cuda', game_id_base: int = 0):
         cfg.validate()

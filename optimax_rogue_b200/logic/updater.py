@@ -5,6 +5,7 @@ in ``liborx.so`` through the C ABI -- there is no CPU path."""
 import ctypes as C
 import enum
 import typing
+import weakref
 
 import torch
 
@@ -92,22 +93,20 @@ class BatchedUpdater:
 
     # -- plumbing ------------------------------------------------------------------------------
     def _cfg(self, gs: BatchedGameState):
-        # Keyed by where the planes ARE (device pointers) and by every config field that reaches the C structs,
-        # not by object identity: CPython reuses ids of freed objects.
-        c = gs.cfg
-        key = (gs.n, gs.game_id_base, int(self.despawn_strat), int(self.max_ticks or 0), int(self.auto_reset),
-               int(self.path_flags) | int(c.path_flags), gs.sched.data_ptr(), int(gs.sched.numel()),
-               c.width, c.height, c.dgen_kind, c.start_kind, tuple(c.start_depth), tuple(c.hp), tuple(c.damage),
-               tuple(c.armor), c.n_npc, c.seed,
-               gs.fixed_tiles.data_ptr() if gs.fixed_tiles is not None else 0,
-               gs.flat.data_ptr() if gs.flat is not None else 0) + tuple(getattr(gs, name).data_ptr() for name in gs.PLANES)
-        if self._cache is None or self._cache[0] != key:
-            if (gs.cfg.width, gs.cfg.height, gs.cfg.dgen_kind) != (self.dgen.width, self.dgen.height, self.dgen.kind):
+        # The marshalled structs are kept per game state, behind a WEAK reference (CPython reuses ids of freed objects:
+        # identity alone is not a key) and two version numbers that the state and its config bump whenever a plane,
+        # the scratch, the bonus plane or a config field is (re)assigned.
+        cached = self._cache
+        key = (gs._layout_version, gs.cfg._version, int(self.despawn_strat), int(self.max_ticks or 0), int(self.auto_reset),
+               int(self.path_flags))
+        if cached is None or cached[0]() is not gs or cached[1] != key:
+            c = gs.cfg
+            if (c.width, c.height, c.dgen_kind) != (self.dgen.width, self.dgen.height, self.dgen.kind):
                 raise ValueError('updater.dgen does not match the generator the game state was built with')
             cfg = gs.c_config(despawn_strat=int(self.despawn_strat), max_ticks=int(self.max_ticks or 0),
                               auto_reset=int(self.auto_reset), path_flags=int(self.path_flags) | int(c.path_flags))
-            self._cache = (key, cfg, gs.c_struct())
-        return self._cache[1], self._cache[2]
+            cached = self._cache = (weakref.ref(gs), key, cfg, gs.c_struct())
+        return cached[2], cached[3]
 
     @staticmethod
     def _as_moves(gs, player1_move, player2_move):
