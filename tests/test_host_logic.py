@@ -236,3 +236,35 @@ def test_state_dict_is_a_snapshot_and_checks_what_it_is_loaded_into():
     legacy['tick'] = legacy['tick'][:1]
     with pytest.raises(ValueError, match='plane tick'):
         BatchedGameState(cfg, 300, 'cpu').load_state_dict(legacy)
+
+
+def test_updater_remarshals_when_the_state_or_its_config_changes():
+    """BatchedUpdater keeps the C structs of the state it last ticked. The cache must notice a different state
+    object (even one that reuses the id of a freed one), a re-bound plane / scratch buffer and a mutated config."""
+    import gc
+    import torch
+    from optimax_rogue_b200 import SimConfig
+    from optimax_rogue_b200.game.state import BatchedGameState
+    from optimax_rogue_b200.logic.updater import BatchedUpdater
+    from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
+    upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, 50)
+    gs = BatchedGameState(SimConfig(seed=1), 64, 'cpu')
+    cfg, st = upd._cfg(gs)
+    assert upd._cfg(gs)[1] is st                                   # hit
+    assert cfg.seed == 1 and st.pos == gs.pos.data_ptr()
+    gs.cfg.seed = 2                                                # config mutated after the first call
+    assert upd._cfg(gs)[0].seed == 2
+    gs.sched = torch.zeros((4,), dtype=torch.int32)                # scratch re-bound
+    assert upd._cfg(gs)[1].sched_words == 4
+    flat = gs.enable_flat_bonuses()                                # bonus plane allocated later
+    assert upd._cfg(gs)[1].flat == flat.data_ptr()
+    seen = set()
+    for k in range(20):                                            # short-lived states: ids get reused, pointers must not go stale
+        tmp = BatchedGameState(SimConfig(seed=100 + k), 64, 'cpu')
+        c, s = upd._cfg(tmp)
+        assert c.seed == 100 + k and s.pos == tmp.pos.data_ptr() and s.tick == tmp.tick.data_ptr()
+        seen.add(id(tmp))
+        del tmp
+        gc.collect()
+    upd.max_ticks = 70
+    assert upd._cfg(gs)[0].max_ticks == 70
