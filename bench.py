@@ -260,7 +260,10 @@ def run_b200(args, rank, local_rank, world):
     _lib.lib()   # fail loudly if the extension is missing
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa = None
     if world > 1:
+        from optimax_rogue_b200.parallel import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local_rank)      # before any pinned host buffer exists: first touch on the GPU's node
         dist.init_process_group('nccl', device_id=dev)
 
     K, W = args.steps, max(args.warmup, 3)
@@ -530,7 +533,8 @@ def run_b200(args, rank, local_rank, world):
             'replays': replays, 'window_ms': window_ms, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, world),
             'measurement': {'l2': f'rotating {nb} independent batches per GPU ({nb * 32 * G / 1e6:.0f} MB of planes > 126 MB L2), no flush needed',
-                            'launch': f'K steps captured in one CUDA graph, replayed {replays}x back to back inside one CUDA-event pair'},
+                            'launch': f'K steps captured in one CUDA graph, replayed {replays}x back to back inside one CUDA-event pair',
+                            'numa': numa if numa is not None else 'process not bound (single NUMA node, one GPU, or topology not exposed)'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (tr or {}).get('dram_bytes_per_launch'), 'peak_source': peak_src,
                          'kernel': 'k_step_pipe<EMPTY,CMD_BYTES>', 'alg_bytes_per_game_tick': B_ALG, 'games_per_launch': G},

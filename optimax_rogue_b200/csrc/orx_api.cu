@@ -534,13 +534,13 @@ TileCtl tile_ctl(const OrxConfig* cfg, const OrxState* st, unsigned int n_tiles)
     return c;
 }
 
-template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, int NPC = 0>
-int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, const TileCtl& ctl,
-                int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
+template <int DGEN, int CMD, bool OBS, bool TICK, bool EV, int NPC, bool FLAGGED>
+int launch_pipe_impl(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, const TileCtl& ctl,
+                     int16_t* obs, int obs_radius, cudaStream_t s, uint2* events, int bots)
 {
     constexpr bool BITS = CMD == CMD_BITS;
     const size_t smem = pipe_smem_bytes<OBS, EV, NPC, BITS>((int)tiles_bytes);
-    auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK, EV, NPC>;
+    auto kernel = k_step_pipe<DGEN, CMD, OBS, TICK, EV, NPC, FLAGGED>;
     // Launch geometry depends only on (device, kernel, smem): looked up once per process, the occupancy query
     // costs more than the launch itself. (A cache of device properties, not state; one per kernel instantiation.)
     // The dynamic shared-memory limit of the kernel is raised ONCE per device to the most any configuration
@@ -604,6 +604,15 @@ int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n
     const cudaError_t e = cudaLaunchKernelEx(&lc, kernel, P, planes5, use_map, mv, result, n_tiles, BITS ? nullptr : ctl.counter, ctl.flags, obs, obs_radius, events, bots, tiles_per_cta);
 #endif
     return e == cudaSuccess ? launch_done() : cuda_fail(e);
+}
+
+// Flag mode and grid-wait mode are separate kernel instantiations (see k_step_pipe).
+template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, int NPC = 0>
+int launch_pipe(const Params& P, const void* mv, uint8_t* result, unsigned int n_tiles, size_t tiles_bytes, const TileCtl& ctl,
+                int16_t* obs, int obs_radius, cudaStream_t s, uint2* events = nullptr, int bots = 0)
+{
+    return ctl.flags != nullptr ? launch_pipe_impl<DGEN, CMD, OBS, TICK, EV, NPC, true>(P, mv, result, n_tiles, tiles_bytes, ctl, obs, obs_radius, s, events, bots)
+                                : launch_pipe_impl<DGEN, CMD, OBS, TICK, EV, NPC, false>(P, mv, result, n_tiles, tiles_bytes, ctl, obs, obs_radius, s, events, bots);
 }
 
 // The tick with NPC slots: one instantiation per slot count (the slot loops unroll, the stage holds exactly the slots
@@ -799,6 +808,17 @@ int step_host_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* move
     return e == cudaSuccess ? ORX_OK : cuda_fail(e);
 }
 
+// The *_sync entry points tick in grid-wait mode whatever the state's scratch allows: the call returns only when the
+// stream has drained, so no later launch can overlap this one, and the hand-over words would be a microsecond or two
+// of overhead for nothing. Safe next to flag-mode launches on the same state: a grid-wait launch waits for everything
+// before it, and everything after it is enqueued after it has completed.
+OrxConfig without_tile_flags(const OrxConfig* cfg)
+{
+    OrxConfig c = *cfg;
+    c.path_flags = (c.path_flags | ORX_PATH_NO_TILE_FLAGS) & ~ORX_PATH_FORCE_TILE_FLAGS;
+    return c;
+}
+
 }  // namespace
 
 extern "C" {
@@ -891,10 +911,13 @@ int orx_step_host(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves
     return step_host_impl(cfg, st, moves_host, result_host, moves_dev, result_dev, n, game_id_base, cuda_stream, 0);
 }
 
-int orx_step_host_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves_host,
+int orx_step_host_sync(const OrxConfig* cfg_in, const OrxState* st, const uint8_t* moves_host,
                        uint8_t* result_host, uint8_t* moves_dev, uint8_t* result_dev, int64_t n,
                        uint64_t game_id_base, void* cuda_stream)
 {
+    if (cfg_in == nullptr) return ORX_ERR_BAD_ARG;
+    const OrxConfig c = without_tile_flags(cfg_in);
+    const OrxConfig* cfg = &c;
     const int rc = step_host_impl(cfg, st, moves_host, result_host, moves_dev, result_dev, n, game_id_base, cuda_stream, 0);
     if (rc != ORX_OK) return rc;
     const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
@@ -908,10 +931,13 @@ int orx_step_host_packed(const OrxConfig* cfg, const OrxState* st, const uint8_t
     return step_host_impl(cfg, st, cmds_host, result_host, cmds_dev, result_dev, n, game_id_base, cuda_stream, 1);
 }
 
-int orx_step_host_packed_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmds_host,
+int orx_step_host_packed_sync(const OrxConfig* cfg_in, const OrxState* st, const uint8_t* cmds_host,
                               uint8_t* result_host, uint8_t* cmds_dev, uint8_t* result_dev, int64_t n,
                               uint64_t game_id_base, void* cuda_stream)
 {
+    if (cfg_in == nullptr) return ORX_ERR_BAD_ARG;
+    const OrxConfig c = without_tile_flags(cfg_in);
+    const OrxConfig* cfg = &c;
     const int rc = step_host_impl(cfg, st, cmds_host, result_host, cmds_dev, result_dev, n, game_id_base, cuda_stream, 1);
     if (rc != ORX_OK) return rc;
     const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
@@ -930,9 +956,12 @@ int orx_step_host_bits(const OrxConfig* cfg, const OrxState* st, const uint8_t* 
     return step_host_bits_impl(cfg, st, cmd5_host, res2_host, cmd5_dev, res2_dev, n, game_id_base, cuda_stream);
 }
 
-int orx_step_host_bits_sync(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5_host, uint8_t* res2_host,
+int orx_step_host_bits_sync(const OrxConfig* cfg_in, const OrxState* st, const uint8_t* cmd5_host, uint8_t* res2_host,
                             uint8_t* cmd5_dev, uint8_t* res2_dev, int64_t n, uint64_t game_id_base, void* cuda_stream)
 {
+    if (cfg_in == nullptr) return ORX_ERR_BAD_ARG;
+    const OrxConfig c = without_tile_flags(cfg_in);
+    const OrxConfig* cfg = &c;
     const int rc = step_host_bits_impl(cfg, st, cmd5_host, res2_host, cmd5_dev, res2_dev, n, game_id_base, cuda_stream);
     if (rc != ORX_OK) return rc;
     const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));

@@ -106,12 +106,11 @@ template <bool OBS, bool EV = false, int NPC = 0> constexpr uint32_t kPipeStageB
 constexpr int CMD_BYTES = 0, CMD_NIBBLES = 1, CMD_BYTES_BOTS = 2;   // _BOTS: uint8[n][2], scripted players' commands computed in the kernel
 // CMD_BITS: the bit-packed streams of orx_step_bits (orx.h): 5 bits of command pair per game in, 2 bits of result
 // per game out -- what crosses PCIe when the caller's buffers live in host memory. A CTA then owns a CONTIGUOUS
-// run of tiles (tiles_per_cta of them). It requests the commands of its whole run when it starts, four tiles
-// (640 bytes) per bulk copy, each copy with its own mbarrier: the link serves the requests of all CTAs roughly in
-// the order they were issued, so every CTA has its first tiles' commands within a couple of microseconds and the
-// later ones arrive while it works (one copy for the whole run made a CTA wait for its whole share of the link's
-// 16 us per 2^20 games before its first tile: 27 instead of ~18 us per tick). The results of the run go back with
-// ONE bulk copy when the CTA ends. No PCIe transaction sits on a tile's critical path.
+// run of tiles (tiles_per_cta of them). The commands arrive four tiles (640 bytes) per bulk copy, each copy with its
+// own mbarrier, requested together with the planes of the chunk's first tile, i.e. kStages tiles before they are
+// needed and in the order they are needed (asking for the whole run at once made a CTA wait for its whole share of
+// the link's 16 us per 2^20 games before its first tile: 27 instead of ~19 us per tick). The results of the run go
+// back with ONE bulk copy when the CTA ends. No PCIe transaction sits on a tile's critical path.
 constexpr int CMD_BITS = 3;
 constexpr uint32_t kCmdBitsTile = 5u * kTile / 8u, kResBitsTile = 2u * kTile / 8u;      // 160 and 64 bytes per tile
 constexpr uint32_t kBitsMaxTiles = 32;                                                    // tiles per CTA in CMD_BITS mode
@@ -247,7 +246,10 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 // EV: also write the tick's replication-log records (OrxEvent[4] per game, no NPC slots), staged like the
 // observations and streamed out with one bulk store per tile.
 // NPC: the game's NPC slot planes (n_npc <= ORX_MAX_NPC slots) travel with the tile as three more slices.
-template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, int NPC = 0>
+// FLAGGED: flag mode (flags != NULL) or grid-wait mode, as separate instantiations: the hand-over code in the same
+// kernel cost grid-wait mode 9 % at 2^20 and 20 % at 2^22 games per launch (1632 -> 2912 SASS instructions, the
+// producer's loops around them; profiles/r02_ab_flag_code_size.log).
+template <int DGEN, int CMD, bool OBS, bool TICK, bool EV = false, int NPC = 0, bool FLAGGED = false>
 __global__ void __launch_bounds__(kPipeThreads, ORX_PIPE_MINBLOCKS)
 k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMap planes5, const int use_map,
             const void* __restrict__ moves_v, uint8_t* __restrict__ result,
@@ -277,10 +279,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     const uint32_t tk0 = tidx0 + kTileIdxBytes;                // flag mode: this CTA's ticket of each of its chunks
     const uint32_t stage0 = smem_addr(stages);
     const unsigned int tid = threadIdx.x;
-#ifndef ORX_PIPE_FLAGS
-#define ORX_PIPE_FLAGS 1            // 0: tuning builds without the flag-mode code (code-size A/B)
-#endif
-    const bool flagged = ORX_PIPE_FLAGS && flags != nullptr;
+    constexpr bool flagged = FLAGGED;
     // Programmatic dependent launch: the next kernel in the stream may begin while this grid is still
     // running. Grid-wait mode: at once; its producer waits for this grid to complete
     // (griddepcontrol.wait) before it touches any plane. Flag mode: only after this CTA holds the tickets
@@ -352,6 +351,16 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             sts_u32(tidx0 + 4 * s, tile);
             if (tile == NONE) { mbar_arrive(bar); return; }
             const size_t g = (size_t)tile * kTile;     // first game of the tile
+            if (CMD == CMD_BITS && it % kBitsCmdChunk == 0u) {
+                // The commands of this tile and the three after it, one 640-byte copy with its own mbarrier, requested
+                // when the tile's planes are (kStages tiles ahead of its tick). Every CTA asks for its first chunk
+                // first and for the later ones as it gets to them, so a link that serves requests in order delivers
+                // them in the order they are needed.
+                const uint32_t left = tiles_per_cta - it, n_here = min(min(left, kBitsCmdChunk), n_tiles - tile);
+                const uint32_t cbar = cmdbar + 8u * (it / kBitsCmdChunk);
+                mbar_expect_tx(cbar, n_here * kCmdBitsTile);
+                bulk_load(cmd0 + it * kCmdBitsTile, moves + (size_t)tile * kCmdBitsTile, n_here * kCmdBitsTile, cbar);
+            }
             mbar_expect_tx(bar, LOAD_BYTES + 4u * npc2);
             if (NPC) {
                 bulk_load(base + OFF_NPOS, P.npc_pos + g * 2u * NPC, npc2, bar);
@@ -371,23 +380,9 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             bulk_load(base + OFF_STATUS, P.status + g, T1, bar);
             if (TICK) bulk_load(base + OFF_MOVES, moves + g * (MV_BYTES / kTile), MV_BYTES, bar);
         };
-        // CMD_BITS: the commands of ALL this CTA's tiles, one bulk copy (over PCIe when the caller's buffer is pinned
-        // host memory), in flight while the first planes are fetched.
-        auto fetch_commands = [&]() {
-            if (CMD == CMD_BITS) {
-                const uint64_t first = (uint64_t)blockIdx.x * tiles_per_cta;
-                const uint32_t cnt = (uint32_t)(n_tiles - first < tiles_per_cta ? n_tiles - first : tiles_per_cta);
-                for (uint32_t t = 0; t < cnt; t += kBitsCmdChunk) {
-                    const uint32_t bytes = (cnt - t < kBitsCmdChunk ? cnt - t : kBitsCmdChunk) * kCmdBitsTile, bar = cmdbar + 8u * (t / kBitsCmdChunk);
-                    mbar_expect_tx(bar, bytes);
-                    bulk_load(cmd0 + t * kCmdBitsTile, moves + (first + t) * kCmdBitsTile, bytes, bar);
-                }
-            }
-        };
         bool ended = false;
         uint32_t held = 0;      // grid-wait mode: a ticket of the tile counter; flag mode: a peek at the next chunk's serving word
         if (flagged) {
-            fetch_commands();
             // Prologue, flag mode: a look at the serving words of the chunks the first kStages tiles belong to, then
             // each tile's loads as soon as the launch before this one on the state has handed its chunk over.
             constexpr unsigned int kPeek = (kStages + kChunk - 1) / kChunk;
@@ -434,7 +429,6 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
         if (ORX_PIPE_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // all earlier work in the stream is complete and visible
 #endif
         ORX_TRACE(trace_slot, 1);
-        fetch_commands();
         // Prologue: the first kStages tiles of a CTA are fixed, so its loads start without a round trip
         // to the counter.
         for (unsigned int it = 0; it < (unsigned)kStages && !ended; ++it) {
