@@ -316,7 +316,14 @@ typedef struct OrxR1Config {
     int32_t auto_reset;
     int32_t wall_density;           /* interior tile is a wall iff mix(x, y, key) & 255 < wall_density */
     uint64_t seed;
+    uint32_t path_flags;            /* ORX_R1_PATH_*; 0 = default kernels. Results never depend on it */
+    uint32_t reserved;
 } OrxR1Config;
+
+#define ORX_R1_PATH_HALFWARP 1u     /* the sixteen-lanes-per-game kernels instead of one thread per game */
+#define ORX_R1_PATH_NO_FLAGS 2u     /* order consecutive ticks grid by grid even when OrxR1State.sched is given */
+#define ORX_R1_BLOCK 128            /* games per hand-over block of orx_r1_step */
+#define ORX_R1_SCHED_WORDS(n) (2 * (((size_t)(n) + ORX_R1_BLOCK - 1) / ORX_R1_BLOCK))
 
 typedef struct OrxR1State {
     uint32_t* ent_loc;     /* [n][16]  x | y<<8 | alive<<16 | item kind<<17 */
@@ -331,6 +338,13 @@ typedef struct OrxR1State {
     int32_t* tick;         /* [n] */
     uint32_t* episode;     /* [n] */
     uint8_t* status;       /* [n]      ORX_RESULT_* */
+    /* Nullable scratch of orx_r1_step for this state, device uint32[sched_words >= ORX_R1_SCHED_WORDS(n)], zeroed by
+     * the caller (orx_r1_reset zeroes it again): {tickets, completed passes} per block of ORX_R1_BLOCK games. With it,
+     * consecutive orx_r1_step launches are ordered block by block instead of grid by grid (same protocol and same
+     * caveats as OrxState.sched: never shared between states; stream order towards everything else is kept). */
+    uint32_t* sched;
+    uint32_t sched_words;
+    uint32_t reserved;
 } OrxR1State;
 
 int orx_r1_reset(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mask, int bump_episode,

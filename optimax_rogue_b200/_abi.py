@@ -86,7 +86,14 @@ R1_LANES, R1_ENEMIES, R1_ITEMS, MOVE_HEAL, R1_STATE_BYTES, R1_OBS_LEN = 16, 8, 4
 class OrxR1Config(C.Structure):
     _fields_ = [('struct_size', C.c_uint32), ('width', C.c_int32), ('height', C.c_int32),
                 ('max_ticks', C.c_int32), ('auto_reset', C.c_int32), ('wall_density', C.c_int32),
-                ('seed', C.c_uint64)]
+                ('seed', C.c_uint64), ('path_flags', C.c_uint32), ('reserved', C.c_uint32)]
+
+
+R1_PATH_HALFWARP, R1_PATH_NO_FLAGS, R1_BLOCK = 1, 2, 128
+
+
+def r1_sched_words(n: int) -> int:
+    return 2 * ((int(n) + R1_BLOCK - 1) // R1_BLOCK)
 
 
 R1_PLANES = (('ent_loc', 'int32', (16,)), ('ent_depth', 'int32', (16,)), ('ent_stat', 'int32', (16,)),
@@ -96,7 +103,8 @@ R1_PLANES = (('ent_loc', 'int32', (16,)), ('ent_depth', 'int32', (16,)), ('ent_s
 
 
 class OrxR1State(C.Structure):
-    _fields_ = [(name, C.c_void_p) for name, _, _ in R1_PLANES]
+    _fields_ = [(name, C.c_void_p) for name, _, _ in R1_PLANES] + [('sched', C.c_void_p), ('sched_words', C.c_uint32),
+                                                                    ('reserved', C.c_uint32)]
 
 
 # name -> (restype, argtypes); every symbol include/orx.h declares

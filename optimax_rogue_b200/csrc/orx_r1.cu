@@ -576,6 +576,10 @@ int orx_r1_reset(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* ma
     if (rc != ORX_OK) return rc;
     if ((game_id_base >> 54) != 0 || ((game_id_base + (uint64_t)n) >> 54) != 0) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
+    if (st->sched != nullptr && st->sched_words > 0) {      // the hand-over words are balanced between launches; a reset re-establishes zero
+        const cudaError_t e = cudaMemsetAsync(st->sched, 0, (size_t)st->sched_words * sizeof(unsigned int), static_cast<cudaStream_t>(cuda_stream));
+        if (e != cudaSuccess) return ORX_ERR_CUDA_BASE - (int)e;
+    }
     k_r1_reset<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), mask, bump_episode);
     return r1_done();
 }
@@ -588,14 +592,31 @@ int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mov
     if ((game_id_base >> 54) != 0 || ((game_id_base + (uint64_t)n) >> 54) != 0) return ORX_ERR_BAD_ARG;
     if (moves == nullptr || result == nullptr || (reinterpret_cast<uintptr_t>(moves) & 1)) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
-    // Default: one thread per game (orx_r1t.cuh). ORX_R1_HALFWARP=1 selects the sixteen-lanes-per-game
+    // Default: one thread per game (orx_r1t.cuh). ORX_R1_PATH_HALFWARP selects the sixteen-lanes-per-game
     // kernels instead (same results; kept as the warp-primitive formulation and as a cross-check).
-    if (getenv("ORX_R1_HALFWARP") != nullptr)
-        k_r1_step<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), moves, result);
-    else
-        r1t::k_step<<<(unsigned)((n + r1t::kThreads - 1) / r1t::kThreads), r1t::kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-            r1_params(cfg, st, n, game_id_base), reinterpret_cast<const uint16_t*>(moves), result);
-    return r1_done();
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    if (cfg->path_flags & ORX_R1_PATH_HALFWARP) {
+        k_r1_step<<<r1_grid(n), kThreadsR1, 0, s>>>(r1_params(cfg, st, n, game_id_base), moves, result);
+        return r1_done();
+    }
+    static_assert(r1t::kThreads == ORX_R1_BLOCK, "a hand-over block is the games of one CTA");
+    const unsigned int grid = (unsigned)((n + r1t::kThreads - 1) / r1t::kThreads);
+    const R1Params P = r1_params(cfg, st, n, game_id_base);
+    const uint16_t* mv = reinterpret_cast<const uint16_t*>(moves);
+    const bool flagged = st->sched != nullptr && (reinterpret_cast<uintptr_t>(st->sched) & 3) == 0 &&
+                         st->sched_words >= ORX_R1_SCHED_WORDS(n) && !(cfg->path_flags & ORX_R1_PATH_NO_FLAGS);
+    if (!flagged) {
+        r1t::k_step<false><<<grid, r1t::kThreads, 0, s>>>(P, mv, result, nullptr);
+        return r1_done();
+    }
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(r1t::kThreads); lc.dynamicSmemBytes = 0; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&lc, r1t::k_step<true>, P, mv, result, st->sched);
+    return e == cudaSuccess ? r1_done() : ORX_ERR_CUDA_BASE - (int)e;
 }
 
 int orx_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, unsigned long long* stats,
@@ -606,7 +627,7 @@ int orx_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, un
     if ((game_id_base >> 54) != 0 || ((game_id_base + (uint64_t)n) >> 54) != 0) return ORX_ERR_BAD_ARG;
     if (n_ticks < 0) return ORX_ERR_BAD_ARG;
     if (n == 0 || n_ticks == 0) return ORX_OK;
-    if (getenv("ORX_R1_HALFWARP") != nullptr)
+    if (cfg->path_flags & ORX_R1_PATH_HALFWARP)
         k_r1_rollout<<<r1_grid(n), kThreadsR1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), n_ticks, stats);
     else
         r1t::k_rollout<<<(unsigned)((n + r1t::kThreads - 1) / r1t::kThreads), r1t::kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(

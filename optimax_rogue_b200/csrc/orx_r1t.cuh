@@ -369,28 +369,58 @@ __device__ __forceinline__ void store_game(const R1Params& P, unsigned int game,
 #endif
 constexpr int kThreads = ORX_R1T_THREADS;
 
+// FLAGGED: consecutive launches on one state are ordered block by block (a block = the kThreads games of a CTA; the
+// protocol of orx_pipe.cuh's flag mode with a CTA's games as the only chunk): the CTA draws a ticket for its block
+// before it lets dependents launch (programmatic dependent launch), touches the state once the block's serving word
+// equals the ticket, releases serving = ticket + 1 at gpu scope after the barrier that follows its last store, and
+// waits for the grid dependency last, so that the completion of this grid implies that of every earlier one.
+template <bool FLAGGED>
 __global__ void __launch_bounds__(kThreads, ORX_R1T_MINBLOCKS)
-k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result)
+k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result, unsigned int* __restrict__ flags)
 {
-    const unsigned int game = blockIdx.x * kThreads + threadIdx.x;
-    if (game >= P.n) return;
-    Game G;
-    load_game(P, game, G);
-    uint32_t mvw, status;
-    asm volatile("ld.global.u16 %0, [%1];" : "=r"(mvw) : "l"(moves + game));
-    asm volatile("ld.global.u8 %0, [%1];" : "=r"(status) : "l"(P.status + game));
-    if (status != ORX_RESULT_IN_PROGRESS) { result[game] = (uint8_t)status; return; }
-    Stream s = make_stream(P, game, G.episode);
-    R1Counters cnt{};
-    int res = tick(P, G, s, (int)(mvw & 255u), (int)(mvw >> 8), cnt);
-    result[game] = (uint8_t)res;
-    if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
-        G.episode += 1;
-        s.episode = G.episode;
-        setup_game(P, G, s);
-        res = ORX_RESULT_IN_PROGRESS;
+    __shared__ unsigned int s_ticket;
+    if (FLAGGED) {
+        if (threadIdx.x == 0) {
+            unsigned int* f = flags + 2 * (size_t)blockIdx.x;
+            const unsigned int ticket = atomicAdd(f, 1u);
+            unsigned int serving;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(serving) : "l"(f + 1) : "memory");
+            asm volatile("griddepcontrol.launch_dependents;" ::"r"(ticket) : "memory");      // the ticket has been drawn
+            while (serving != ticket) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(serving) : "l"(f + 1) : "memory");
+            s_ticket = ticket;
+        }
+        __syncthreads();
     }
-    store_game(P, game, G, res);
+    const unsigned int game = blockIdx.x * kThreads + threadIdx.x;
+    if (game < P.n) {
+        Game G;
+        load_game(P, game, G);
+        uint32_t mvw, status;
+        asm volatile("ld.global.u16 %0, [%1];" : "=r"(mvw) : "l"(moves + game));
+        asm volatile("ld.global.u8 %0, [%1];" : "=r"(status) : "l"(P.status + game));
+        if (status != ORX_RESULT_IN_PROGRESS) {
+            result[game] = (uint8_t)status;
+        } else {
+            Stream s = make_stream(P, game, G.episode);
+            R1Counters cnt{};
+            int res = tick(P, G, s, (int)(mvw & 255u), (int)(mvw >> 8), cnt);
+            result[game] = (uint8_t)res;
+            if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
+                G.episode += 1;
+                s.episode = G.episode;
+                setup_game(P, G, s);
+                res = ORX_RESULT_IN_PROGRESS;
+            }
+            store_game(P, game, G, res);
+        }
+    }
+    if (FLAGGED) {
+        __syncthreads();                       // every store of the block has been issued
+        if (threadIdx.x == 0) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + 2 * (size_t)blockIdx.x + 1), "r"(s_ticket + 1u) : "memory");
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, ORX_R1T_MINBLOCKS)

@@ -18,7 +18,7 @@ class R1GameState:
     plus per-player and per-game planes (include/orx.h:OrxR1State)."""
 
     def __init__(self, n: int, *, width=60, height=10, max_ticks=0, auto_reset=False, wall_density=26,
-                 seed=0, device='cuda', game_id_base=0):
+                 seed=0, device='cuda', game_id_base=0, path_flags=0):
         self.n, self.device, self.game_id_base = int(n), torch.device(device), int(game_id_base)
         if self.device.type != 'cuda':
             raise RuntimeError('R1GameState must live on a CUDA device: there is no CPU fallback')
@@ -27,12 +27,16 @@ class R1GameState:
         self.cfg.width, self.cfg.height, self.cfg.max_ticks = width, height, int(max_ticks or 0)
         self.cfg.auto_reset, self.cfg.wall_density = int(auto_reset), wall_density
         self.cfg.seed = seed & 0xFFFFFFFFFFFFFFFF
+        self.cfg.path_flags = int(path_flags)      # _abi.R1_PATH_*: pins a kernel path (tests, A/B runs)
         for name, dt, shape in _abi.R1_PLANES:
             setattr(self, name, torch.zeros((self.n,) + shape, dtype=getattr(torch, dt), device=self.device))
         self.status.fill_(1)
         self._st = _abi.OrxR1State()
         for name, _, _ in _abi.R1_PLANES:
             setattr(self._st, name, getattr(self, name).data_ptr())
+        # hand-over words of orx_r1_step (OrxR1State.sched): consecutive ticks overlap block by block
+        self.sched = torch.zeros((_abi.r1_sched_words(self.n),), dtype=torch.int32, device=self.device)
+        self._st.sched, self._st.sched_words = self.sched.data_ptr(), int(self.sched.numel())
 
     @property
     def alg_bytes_per_game_tick(self) -> int:

@@ -12,19 +12,23 @@ from optimax_rogue_b200.r1 import R1GameState
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['thread_per_game', 'half_warp'], autouse=True)
-def r1_kernel_flavour(request, monkeypatch):
-    """Both device formulations of the R1 tick (orx_r1t.cuh: one thread per game, the default;
-    orx_r1.cu: sixteen lanes per game with warp primitives) must match the oracle bit for bit."""
-    if request.param == 'half_warp':
-        monkeypatch.setenv('ORX_R1_HALFWARP', '1')
-    else:
-        monkeypatch.delenv('ORX_R1_HALFWARP', raising=False)
+FLAVOUR = {'flags': 0}
+
+
+@pytest.fixture(params=['thread_per_game', 'thread_per_game_grid_ordered', 'half_warp'], autouse=True)
+def r1_kernel_flavour(request):
+    """Both device formulations of the R1 tick (orx_r1t.cuh: one thread per game, the default, with and without the
+    block-by-block ordering of consecutive launches; orx_r1.cu: sixteen lanes per game with warp primitives) must
+    match the oracle bit for bit."""
+    from optimax_rogue_b200 import _abi
+    FLAVOUR['flags'] = {'thread_per_game': 0, 'thread_per_game_grid_ordered': _abi.R1_PATH_NO_FLAGS,
+                        'half_warp': _abi.R1_PATH_HALFWARP}[request.param]
     yield request.param
+    FLAVOUR['flags'] = 0
 
 
 def pair(n, base=0, **cfg):
-    gs = R1GameState(n, game_id_base=base, **cfg).reset()
+    gs = R1GameState(n, game_id_base=base, path_flags=FLAVOUR['flags'], **cfg).reset()
     orc = cport.R1Oracle(n, game_id_base=base, **cfg)
     orc.reset()
     return gs, orc
@@ -111,3 +115,35 @@ def test_r1_observation_parity(radius):
     assert (got[:, :, 23:47:3] >= 0).any(), 'some enemy is visible'
     if radius == 0:
         assert (got[:, :, 20] == 0).all()      # nobody ever stands on the staircase
+
+
+def test_r1_unsynchronised_ticks_in_a_graph():
+    """Ticks enqueued back to back (a CUDA graph replayed several times, two states interleaved): with the hand-over
+    words consecutive launches overlap block by block; every result and both end states equal the oracle's."""
+    n, per, replays = 128 * 37 + 50, 12, 5
+    a, oa = pair(n, 0, max_ticks=40, auto_reset=True, seed=5)
+    b, ob = pair(n, 10 * n, max_ticks=40, auto_reset=True, seed=6)
+    g = torch.Generator(device='cuda').manual_seed(2)
+    mv = torch.randint(0, 8, (per, n, 2), dtype=torch.uint8, device='cuda', generator=g)
+    ra = torch.zeros((per, n), dtype=torch.uint8, device='cuda')
+    rb = torch.zeros_like(ra)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        a.update(mv[0], out=ra[0]); b.update(mv[0], out=rb[0])
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            for t in range(per):
+                a.update(mv[t], out=ra[t])
+                b.update(mv[t], out=rb[t])
+        for _ in range(replays):
+            graph.replay()
+    torch.cuda.synchronize()
+    m = mv.cpu().numpy()
+    for gs, orc, res in ((a, oa, ra), (b, ob, rb)):
+        orc.step(m[0])
+        want = None
+        for _ in range(replays):
+            want = np.stack([orc.step(m[t]) for t in range(per)])
+        assert np.array_equal(res.cpu().numpy(), want)
+        assert_equal(gs, orc, 'after the replayed graph')

@@ -20,6 +20,7 @@ ap.add_argument('--rollout', type=int, default=0, help='also time orx_rollout wi
 ap.add_argument('--json', default=None, help='write the sweep (one row per batch size) to this file')
 ap.add_argument('--path-flags', type=int, default=0, help='OrxConfig.path_flags (include/orx.h ORX_PATH_*)')
 ap.add_argument('--tpc', type=int, default=0, help='tiles per CTA in tile-flag mode (0 = built-in default)')
+ap.add_argument('--isolate', action='store_true', help='a tiny ordinary kernel between consecutive steps (what a policy network in the loop does: no overlap between ticks)')
 ap.add_argument('--batches', type=int, default=0, help='rotating batches (0 = enough to exceed the L2; 1 = the same state every step)')
 args = ap.parse_args()
 dev = torch.device('cuda')
@@ -42,9 +43,12 @@ for G in args.games:
             upd.update(batches[k % nb], moves[k % 8], out=res[k % nb])
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        dummy = torch.zeros((1,), device=dev)
         with torch.cuda.graph(g, stream=st):
             for k in range(args.steps):
                 upd.update(batches[k % nb], moves[k % 8], out=res[k % nb])
+                if args.isolate:
+                    dummy.add_(1.0)
         g.replay()
         torch.cuda.synchronize()
         best = 1e9
@@ -68,7 +72,7 @@ for G in args.games:
                 torch.cuda.synchronize()
                 rbest = min(rbest, e0.elapsed_time(e1) / min(nb, 4))
         print(f'games={G} rollout T={args.rollout}: {rbest * 1e3:.1f} us/launch, {G * args.rollout / rbest * 1e3:.3e} ticks/s', flush=True)
-    print(f'path_flags={args.path_flags} tpc={args.tpc} games={G} batches={nb} us/step={best * 1e3:.2f} ticks/s={G / best * 1e3:.3e} GB/s(61B)={61 * G / best / 1e6:.0f}', flush=True)
+    print(f'path_flags={args.path_flags} tpc={args.tpc} isolate={int(args.isolate)} games={G} batches={nb} us/step={best * 1e3:.2f} ticks/s={G / best * 1e3:.3e} GB/s(61B)={61 * G / best / 1e6:.0f}', flush=True)
     rows.append({'path_flags': args.path_flags, 'tiles_per_cta': args.tpc, 'games_per_launch': G, 'rotating_batches': nb, 'us_per_step': round(best * 1e3, 2),
                  'game_ticks_per_s': float(f'{G / best * 1e3:.4g}'), 'alg_GBps_61B': round(61 * G / best / 1e6),
                  'frac_of_measured_hbm_peak': round(61 * G / best / 1e6 / 6548.2, 3)})
