@@ -144,9 +144,9 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(smax), 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def sim_config(auto_reset=True):
+def sim_config(auto_reset=True, overlap_ticks=False):
     from optimax_rogue_b200 import SimConfig
-    return SimConfig(width=60, height=10, max_ticks=MAX_TICKS, seed=SEED, auto_reset=auto_reset)
+    return SimConfig(width=60, height=10, max_ticks=MAX_TICKS, seed=SEED, auto_reset=auto_reset, overlap_ticks=overlap_ticks)
 
 
 # ------------------------------------------------------------------------------------------ CPU side
@@ -269,7 +269,10 @@ def run_b200(args, rank, local_rank, world):
     K, W = args.steps, max(args.warmup, 3)
     G_total = args.games
     G = G_total // world                     # this rank's shard (strong scaling: the total is fixed)
-    cfg = sim_config()
+    # Every device-timed leg enqueues its ticks back to back (K steps in one CUDA graph): the states opt into the
+    # throughput mode (SimConfig.overlap_ticks = ORX_PATH_TILE_FLAGS), in which consecutive tick launches overlap chunk
+    # by chunk. The e2e legs synchronise after every tick; their *_sync entry points run in grid-wait mode regardless.
+    cfg = sim_config(overlap_ticks=True)
     upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, MAX_TICKS, auto_reset=True)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -367,12 +370,13 @@ def run_b200(args, rank, local_rank, world):
             hc.copy_(pack_moves(m[:, 0], m[:, 1]))
         host_res = [torch.empty((G,), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
 
-        def time_host_loop(cmd_bufs, sync, res_bufs=None, bits=False):
+        def time_host_loop(cmd_bufs, sync, res_bufs=None, bits=False, states=None):
             # one bound stepper per (batch, command buffer): BatchedUpdater.host_stepper is the public call for
             # host-side loops; each step() = H2D commands + tick + D2H results (+ stream sync when sync=True)
             res_bufs = res_bufs or host_res
-            steppers = [upd.host_stepper(batches[k % nb], cmd_bufs[k % n_host], res_bufs[k % 2], sync=sync, bits=bits)
-                        for k in range(nb * n_host // math.gcd(nb, n_host))]
+            states = states or batches
+            steppers = [upd.host_stepper(states[k % len(states)], cmd_bufs[k % n_host], res_bufs[k % 2], sync=sync, bits=bits)
+                        for k in range(len(states) * n_host // math.gcd(len(states), n_host))]
             evs = [torch.cuda.Event(), torch.cuda.Event()]
 
             def run(n):
@@ -436,7 +440,13 @@ def run_b200(args, rank, local_rank, world):
             out['weak_scaling'] = {'value': world * Gw / (ms_w * 1e-3), 'unit': UNIT, 'games_per_gpu': Gw, 'global_games': world * Gw,
                                    'us_per_step': ms_w * 1e3, 'steps': K, 'replays': rep_w,
                                    'note': 'the same leg with 2^20 games PER GPU (the batch grows with the box)'}
-            del wb, wmoves, wres
+            w_cmd5 = [torch.from_numpy(pack_moves5(wmoves[k][:, 0].cpu().numpy(), wmoves[k][:, 1].cpu().numpy())).pin_memory() for k in range(n_host)]
+            w_res2 = [torch.empty((_abi.res2_bytes(Gw),), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+            ms_we, k_we = time_host_loop(w_cmd5, True, res_bufs=w_res2, bits=True, states=wb)
+            out['weak_scaling']['e2e'] = {'value': world * Gw / (ms_we * 1e-3), 'unit': UNIT, 'us_per_step': ms_we * 1e3, 'steps': k_we,
+                                          'h2d_bytes_per_step': _abi.cmd5_bytes(Gw), 'd2h_bytes_per_step': _abi.res2_bytes(Gw),
+                                          'note': 'the e2e call (bit-packed host buffers, sync every step) with 2^20 games per GPU'}
+            del wb, wmoves, wres, w_cmd5, w_res2
 
         if not args.no_extras:
             # ------------------------------------------------------------ step + observe: the self-play tick, one pass
@@ -488,7 +498,7 @@ def run_b200(args, rank, local_rank, world):
             rng = np.random.default_rng(0)
             t = np.full((60, 10), 1, np.uint8); t[[0, -1], :] = 2; t[:, [0, -1]] = 2
             t[1:-1, 1:-1][rng.random((58, 8)) < 0.10] = 2
-            c2 = SimConfig(dgen_kind=_abi.DGEN_FIXED, fixed_tiles=t, max_ticks=MAX_TICKS, seed=SEED, auto_reset=True)
+            c2 = SimConfig(dgen_kind=_abi.DGEN_FIXED, fixed_tiles=t, max_ticks=MAX_TICKS, seed=SEED, auto_reset=True, overlap_ticks=True)
             u2 = BatchedUpdater(FixedDungeonGenerator(t), 1, MAX_TICKS, auto_reset=True)
             G2, nb2 = 4096, 64
             b2 = []
@@ -508,7 +518,7 @@ def run_b200(args, rank, local_rank, world):
             # ------------------------------------------------------------ ruleset R1 (README-only rules, parity unpinned)
             from optimax_rogue_b200.r1 import R1GameState
             G1, nb1 = 1 << 16, 18
-            r1_batches = [R1GameState(G1, max_ticks=MAX_TICKS, auto_reset=True, seed=SEED, device=dev,
+            r1_batches = [R1GameState(G1, max_ticks=MAX_TICKS, auto_reset=True, seed=SEED, device=dev, overlap_ticks=True,
                                       game_id_base=(rank * nb1 + b) * G1).reset() for b in range(nb1)]
             r1_moves = torch.randint(1, 7, (4, G1, 2), dtype=torch.uint8, device=dev, generator=gen)
             r1_res = [torch.empty((G1,), dtype=torch.uint8, device=dev) for _ in range(nb1)]
@@ -534,6 +544,8 @@ def run_b200(args, rank, local_rank, world):
             'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, world),
             'measurement': {'l2': f'rotating {nb} independent batches per GPU ({nb * 32 * G / 1e6:.0f} MB of planes > 126 MB L2), no flush needed',
                             'launch': f'K steps captured in one CUDA graph, replayed {replays}x back to back inside one CUDA-event pair',
+                            'ordering': 'throughput mode (SimConfig.overlap_ticks / ORX_PATH_TILE_FLAGS): consecutive tick launches are ordered chunk by chunk, '
+                                        'not grid by grid; every tick of a state still sees the previous one complete, chunk for chunk',
                             'numa': numa if numa is not None else 'process not bound (single NUMA node, one GPU, or topology not exposed)'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (tr or {}).get('dram_bytes_per_launch'), 'peak_source': peak_src,

@@ -106,15 +106,19 @@ typedef struct OrxConfig {
                                      process-wide switches (the library reads no environment variables). */
 } OrxConfig;
 
-/* OrxConfig.path_flags. NO_TILE_FLAGS and STATIC_TILES choose how launches on ONE state are ordered; keep them
- * constant for a state between two operations that serialise the stream (orx_reset, any non-step kernel). */
+/* OrxConfig.path_flags. TILE_FLAGS and STATIC_TILES choose how launches on ONE state are ordered; keep them
+ * constant for a state between two operations that serialise the stream (orx_reset, any non-step kernel, a sync). */
 #define ORX_PATH_NO_TENSOR_MAP 1u   /* move the five 4-byte planes as five 1-D bulk copies */
 #define ORX_PATH_NO_NPC_PIPE 2u     /* NPC slots: one-thread-per-game kernel instead of the tile pipeline */
 #define ORX_PATH_STATIC_TILES 4u    /* grid-wait mode: static tile striding instead of the dynamic counter */
 #define ORX_PATH_NO_EVENT_PIPE 8u   /* event log: one-thread-per-game kernel */
 #define ORX_PATH_HOST_STAGED 16u    /* host buffers: staged cudaMemcpyAsync instead of in-kernel PCIe access */
-#define ORX_PATH_NO_TILE_FLAGS 32u  /* order consecutive launches by a grid-wide dependency, not tile by tile */
-#define ORX_PATH_FORCE_TILE_FLAGS 64u /* tile-by-tile ordering also for batches of 2^20 games and more */
+#define ORX_PATH_TILE_FLAGS 32u     /* THROUGHPUT MODE (opt-in): order consecutive tick launches on a state chunk by
+                                       chunk through OrxState.sched instead of grid by grid, so that ticks enqueued back
+                                       to back overlap (see OrxState.sched). For queued command streams and for several
+                                       states in flight; a loop that runs other kernels between two ticks (a policy
+                                       network) is faster without it. Needs sched_words >= orx_sched_words(n); batches
+                                       above 2^20 games are ticked grid by grid regardless (faster there). */
 #define ORX_PATH_TILES_PER_CTA_SHIFT 8  /* bits 8..15: tiles per CTA in tile-flag mode (0 = built-in default) */
 
 /* Structure-of-arrays game state; game i of the batch is element i of every plane.
@@ -141,12 +145,13 @@ typedef struct OrxState {
      * size the state is ticked with. Two uses (csrc/orx_pipe.cuh):
      *   sched_words >= ORX_SCHED_HEADER_WORDS: word 0 is a tile counter, 256-game tiles are handed out
      *     dynamically (CTAs that run slower take fewer); zero again when a launch completes.
-     *   sched_words >= orx_sched_words(n), n < 2^20: words 4.. hold {tickets, completed passes} per chunk of four
-     *     tiles, and consecutive tick launches on the state are ordered chunk by chunk instead of grid by grid: tick
-     *     k+1 starts on a chunk as soon as tick k has written it, and ticks of different states in one stream
-     *     overlap freely. This is the throughput mode for back-to-back ticks (several states in flight, queued
-     *     commands): 1.2-1.7x at 2^17..2^19 games per launch; a loop that waits for every tick's result before it
-     *     enqueues the next gains nothing and pays about a microsecond per tick -- ORX_PATH_NO_TILE_FLAGS opts out.
+     *   sched_words >= orx_sched_words(n) and ORX_PATH_TILE_FLAGS set: words 4.. hold {tickets, completed passes} per
+     *     chunk of four tiles, and consecutive tick launches on the state are ordered chunk by chunk instead of grid
+     *     by grid: tick k+1 starts on a chunk as soon as tick k has written it, and ticks of different states in one
+     *     stream overlap freely. Measured per step with ticks enqueued back to back (rotating states): 2.5 against
+     *     4.2 us at 2^17 games, 3.8 / 5.5 at 2^18, 6.2 / 7.9 at 2^19, 11.6 / 12.2 at 2^20. The protocol costs about
+     *     2.5 us of latency per launch, so with an ordinary kernel between two ticks the same launches take 9.1 / 6.7,
+     *     12.4 / 8.4, 18.9 / 11.0 and 26.8 / 15.5 us: opt in only where ticks really follow each other.
      *     Stream order towards everything else is kept (a tick completes only after all earlier work has).
      *     In this mode two consecutive tick calls on DIFFERENT states must not share a result / observation /
      *     event buffer unless something else in the stream consumes it in between. */
@@ -321,8 +326,10 @@ typedef struct OrxR1Config {
 } OrxR1Config;
 
 #define ORX_R1_PATH_HALFWARP 1u     /* the sixteen-lanes-per-game kernels instead of one thread per game */
-#define ORX_R1_PATH_NO_FLAGS 2u     /* order consecutive ticks grid by grid even when OrxR1State.sched is given */
-#define ORX_R1_BLOCK 128            /* games per hand-over block of orx_r1_step */
+#define ORX_R1_PATH_BLOCK_FLAGS 2u  /* throughput mode (opt-in): order consecutive orx_r1_step launches block by block through OrxR1State.sched */
+#ifndef ORX_R1_BLOCK
+#define ORX_R1_BLOCK 128            /* games per hand-over block of orx_r1_step (= threads per CTA of its kernel) */
+#endif
 #define ORX_R1_SCHED_WORDS(n) (2 * (((size_t)(n) + ORX_R1_BLOCK - 1) / ORX_R1_BLOCK))
 
 typedef struct OrxR1State {
@@ -339,9 +346,9 @@ typedef struct OrxR1State {
     uint32_t* episode;     /* [n] */
     uint8_t* status;       /* [n]      ORX_RESULT_* */
     /* Nullable scratch of orx_r1_step for this state, device uint32[sched_words >= ORX_R1_SCHED_WORDS(n)], zeroed by
-     * the caller (orx_r1_reset zeroes it again): {tickets, completed passes} per block of ORX_R1_BLOCK games. With it,
-     * consecutive orx_r1_step launches are ordered block by block instead of grid by grid (same protocol and same
-     * caveats as OrxState.sched: never shared between states; stream order towards everything else is kept). */
+     * the caller (orx_r1_reset zeroes it again): {tickets, completed passes} per block of ORX_R1_BLOCK games. With it
+     * and ORX_R1_PATH_BLOCK_FLAGS, consecutive orx_r1_step launches are ordered block by block instead of grid by
+     * grid (same protocol, same trade-off and same caveats as ORX_PATH_TILE_FLAGS / OrxState.sched). */
     uint32_t* sched;
     uint32_t sched_words;
     uint32_t reserved;

@@ -22,7 +22,7 @@ EV_NONE, EV_MOVE, EV_COMBAT, EV_DUNGEON, EV_DEATH, EV_DESCEND = 0, 1, 2, 3, 4, 5
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA_BASE = 0, -1, -2, -100
 
 # OrxConfig.path_flags (include/orx.h)
-PATH_NO_TENSOR_MAP, PATH_NO_NPC_PIPE, PATH_STATIC_TILES, PATH_NO_EVENT_PIPE, PATH_HOST_STAGED, PATH_NO_TILE_FLAGS, PATH_FORCE_TILE_FLAGS = 1, 2, 4, 8, 16, 32, 64
+PATH_NO_TENSOR_MAP, PATH_NO_NPC_PIPE, PATH_STATIC_TILES, PATH_NO_EVENT_PIPE, PATH_HOST_STAGED, PATH_TILE_FLAGS = 1, 2, 4, 8, 16, 32
 PATH_TILES_PER_CTA_SHIFT = 8
 SCHED_HEADER_WORDS = 4
 TILE = 256
@@ -89,11 +89,12 @@ class OrxR1Config(C.Structure):
                 ('seed', C.c_uint64), ('path_flags', C.c_uint32), ('reserved', C.c_uint32)]
 
 
-R1_PATH_HALFWARP, R1_PATH_NO_FLAGS, R1_BLOCK = 1, 2, 128
+R1_PATH_HALFWARP, R1_PATH_BLOCK_FLAGS, R1_BLOCK = 1, 2, 128
 
 
 def r1_sched_words(n: int) -> int:
-    return 2 * ((int(n) + R1_BLOCK - 1) // R1_BLOCK)
+    """ORX_R1_SCHED_WORDS(n), sized for 64-game blocks so that tuning builds with smaller CTAs fit as well."""
+    return 2 * ((int(n) + 63) // 64)
 
 
 R1_PLANES = (('ent_loc', 'int32', (16,)), ('ent_depth', 'int32', (16,)), ('ent_stat', 'int32', (16,)),

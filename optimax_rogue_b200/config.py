@@ -26,6 +26,9 @@ class SimConfig:
     seed: int = 0
     fixed_tiles: typing.Optional[np.ndarray] = None   # uint8[W,H] Tile codes (DGEN_FIXED)
     path_flags: int = 0                 # _abi.PATH_* bits: pins a kernel path for tests / A-B runs, never changes results
+    overlap_ticks: bool = False         # throughput mode (ORX_PATH_TILE_FLAGS): ticks enqueued back to back on this state (and
+                                        # on others in the same stream) overlap chunk by chunk. For queued command streams /
+                                        # several states in flight; slower when other kernels run between two ticks
 
     def __setattr__(self, name, value):
         # every assignment bumps a version number: holders of structs marshalled from this config (BatchedUpdater)
@@ -82,5 +85,5 @@ class SimConfig:
         c.fixed_ground = ground_ptr or None
         c.fixed_n_ground = n_ground
         c.fixed_stairs[0], c.fixed_stairs[1] = stairs
-        c.path_flags = int(self.path_flags)
+        c.path_flags = int(self.path_flags) | (_abi.PATH_TILE_FLAGS if self.overlap_ticks else 0)
         return c

@@ -16,7 +16,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxFixedTiles = 16384;   // shared-memory staging of the fixed map
-constexpr unsigned int kFlagModeMaxTiles = 4096;   // 2^20 games: from here on grid-wait mode (tile_ctl)
+constexpr unsigned int kFlagModeMaxTiles = 4096;   // 2^20 games: the largest batch ticked in flag mode (tile_ctl)
 constexpr int64_t kMaxGamesPerCall = 1ll << 30;   // 32-bit lane index inside the kernels; larger batches: call per chunk
 
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p)
@@ -518,14 +518,12 @@ TileCtl tile_ctl(const OrxConfig* cfg, const OrxState* st, unsigned int n_tiles)
     cudaGetDevice(&dev);
     const int sms = device_sms(dev);
     const uint64_t need = (uint64_t)ORX_SCHED_HEADER_WORDS + 2ull * n_tiles;
-    // Flag mode pays per launch (tickets, acquire, one release fence per chunk in the thread that moves the data)
-    // for not having a grid-wide boundary between launches. Measured with back-to-back launches on rotating states
-    // (profiles/r02_batch_sweep.json): 2.5 against 4.4 us per step at 2^17 games, 3.7 / 5.5 at 2^18, 6.7 / 7.9 at
-    // 2^19, 12.9 / 12.6 at 2^20 -- from kFlagModeMaxTiles tiles on, a launch is long enough for the boundary not to
-    // matter and grid-wait mode (dynamic tile hand-out, L2 prefetch across the boundary) is the faster one.
-    // ORX_PATH_FORCE_TILE_FLAGS lifts the size limit (A/B runs).
-    const bool small = n_tiles < kFlagModeMaxTiles || (cfg->path_flags & ORX_PATH_FORCE_TILE_FLAGS) != 0;
-    if (!(cfg->path_flags & ORX_PATH_NO_TILE_FLAGS) && st->sched_words >= need && small && n_tiles <= (unsigned int)(kBitsMaxTiles * 3 * sms)) {
+    // Flag mode is the caller's choice (ORX_PATH_TILE_FLAGS): it pays about 2.5 us of latency per launch (tickets,
+    // acquire, completion + release fence per chunk) for not having a grid-wide boundary between launches, which is a
+    // gain for ticks enqueued back to back and a loss for a tick that runs alone (profiles/r02_batch_sweep.json).
+    // Above kFlagModeMaxTiles tiles (2^20 games) a launch is long enough for the boundary not to matter and grid-wait
+    // mode (dynamic tile hand-out, L2 prefetch across the boundary) is the faster one again: 21.5 against 23.2 us at 2^21.
+    if ((cfg->path_flags & ORX_PATH_TILE_FLAGS) && st->sched_words >= need && n_tiles <= kFlagModeMaxTiles) {
         c.flags = st->sched + ORX_SCHED_HEADER_WORDS;
         c.tiles_per_cta = (int)flag_tiles_per_cta(n_tiles, sms, (int)((cfg->path_flags >> ORX_PATH_TILES_PER_CTA_SHIFT) & 255u));
         return c;
@@ -815,7 +813,7 @@ int step_host_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* move
 OrxConfig without_tile_flags(const OrxConfig* cfg)
 {
     OrxConfig c = *cfg;
-    c.path_flags = (c.path_flags | ORX_PATH_NO_TILE_FLAGS) & ~ORX_PATH_FORCE_TILE_FLAGS;
+    c.path_flags &= ~ORX_PATH_TILE_FLAGS;
     return c;
 }
 

@@ -604,7 +604,7 @@ int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mov
     const R1Params P = r1_params(cfg, st, n, game_id_base);
     const uint16_t* mv = reinterpret_cast<const uint16_t*>(moves);
     const bool flagged = st->sched != nullptr && (reinterpret_cast<uintptr_t>(st->sched) & 3) == 0 &&
-                         st->sched_words >= ORX_R1_SCHED_WORDS(n) && !(cfg->path_flags & ORX_R1_PATH_NO_FLAGS);
+                         st->sched_words >= ORX_R1_SCHED_WORDS(n) && (cfg->path_flags & ORX_R1_PATH_BLOCK_FLAGS) != 0;
     if (!flagged) {
         r1t::k_step<false><<<grid, r1t::kThreads, 0, s>>>(P, mv, result, nullptr);
         return r1_done();

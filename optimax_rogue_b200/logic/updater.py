@@ -104,7 +104,7 @@ class BatchedUpdater:
             if (c.width, c.height, c.dgen_kind) != (self.dgen.width, self.dgen.height, self.dgen.kind):
                 raise ValueError('updater.dgen does not match the generator the game state was built with')
             cfg = gs.c_config(despawn_strat=int(self.despawn_strat), max_ticks=int(self.max_ticks or 0),
-                              auto_reset=int(self.auto_reset), path_flags=int(self.path_flags) | int(c.path_flags))
+                              auto_reset=int(self.auto_reset), path_flags=int(self.path_flags) | int(c.path_flags) | (_abi.PATH_TILE_FLAGS if c.overlap_ticks else 0))
             cached = self._cache = (weakref.ref(gs), key, cfg, gs.c_struct())
         return cached[2], cached[3]
 

@@ -18,7 +18,7 @@ class R1GameState:
     plus per-player and per-game planes (include/orx.h:OrxR1State)."""
 
     def __init__(self, n: int, *, width=60, height=10, max_ticks=0, auto_reset=False, wall_density=26,
-                 seed=0, device='cuda', game_id_base=0, path_flags=0):
+                 seed=0, device='cuda', game_id_base=0, path_flags=0, overlap_ticks=False):
         self.n, self.device, self.game_id_base = int(n), torch.device(device), int(game_id_base)
         if self.device.type != 'cuda':
             raise RuntimeError('R1GameState must live on a CUDA device: there is no CPU fallback')
@@ -27,7 +27,9 @@ class R1GameState:
         self.cfg.width, self.cfg.height, self.cfg.max_ticks = width, height, int(max_ticks or 0)
         self.cfg.auto_reset, self.cfg.wall_density = int(auto_reset), wall_density
         self.cfg.seed = seed & 0xFFFFFFFFFFFFFFFF
-        self.cfg.path_flags = int(path_flags)      # _abi.R1_PATH_*: pins a kernel path (tests, A/B runs)
+        # _abi.R1_PATH_*: pins a kernel path (tests, A/B runs); overlap_ticks = throughput mode (ORX_R1_PATH_BLOCK_FLAGS):
+        # ticks enqueued back to back overlap block by block -- slower when other kernels run between two ticks
+        self.cfg.path_flags = int(path_flags) | (_abi.R1_PATH_BLOCK_FLAGS if overlap_ticks else 0)
         for name, dt, shape in _abi.R1_PLANES:
             setattr(self, name, torch.zeros((self.n,) + shape, dtype=getattr(torch, dt), device=self.device))
         self.status.fill_(1)

@@ -354,7 +354,6 @@ def test_dynamic_tile_scheduler_equals_static_assignment(n):
     static.sched = torch.zeros((4,), dtype=torch.int32)          # not on the device -> OrxState.sched = NULL
     assert static.c_struct().sched is None and gs.c_struct().sched is not None
     upd_static = type(upd)(upd.dgen, upd.despawn_strat, upd.max_ticks, auto_reset=True)
-    upd.path_flags = _abi.PATH_NO_TILE_FLAGS      # grid-wait mode: the counter in sched[0] hands the tiles out
     rng = np.random.default_rng(1)
     for t in range(24):
         mv = torch.from_numpy(rng.integers(1, 6, size=(n, 2), dtype=np.uint8)).cuda()

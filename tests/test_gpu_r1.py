@@ -15,13 +15,13 @@ pytestmark = pytest.mark.gpu
 FLAVOUR = {'flags': 0}
 
 
-@pytest.fixture(params=['thread_per_game', 'thread_per_game_grid_ordered', 'half_warp'], autouse=True)
+@pytest.fixture(params=['thread_per_game', 'thread_per_game_overlapped', 'half_warp'], autouse=True)
 def r1_kernel_flavour(request):
     """Both device formulations of the R1 tick (orx_r1t.cuh: one thread per game, the default, with and without the
     block-by-block ordering of consecutive launches; orx_r1.cu: sixteen lanes per game with warp primitives) must
     match the oracle bit for bit."""
     from optimax_rogue_b200 import _abi
-    FLAVOUR['flags'] = {'thread_per_game': 0, 'thread_per_game_grid_ordered': _abi.R1_PATH_NO_FLAGS,
+    FLAVOUR['flags'] = {'thread_per_game': 0, 'thread_per_game_overlapped': _abi.R1_PATH_BLOCK_FLAGS,
                         'half_warp': _abi.R1_PATH_HALFWARP}[request.param]
     yield request.param
     FLAVOUR['flags'] = 0

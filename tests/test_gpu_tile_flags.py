@@ -1,5 +1,5 @@
-"""-m gpu: tile-by-tile ordering of consecutive tick launches (OrxState.sched with orx_sched_words(n)
-words, csrc/orx_pipe.cuh "flag mode"). The other parity tests read the state back after every tick, which
+"""-m gpu: chunk-by-chunk ordering of consecutive tick launches (ORX_PATH_TILE_FLAGS = SimConfig.overlap_ticks,
+OrxState.sched with orx_sched_words(n) words, csrc/orx_pipe.cuh "flag mode"). The other parity tests read the state back after every tick, which
 serialises the stream; here many ticks are enqueued back to back, eagerly and as a CUDA graph, on one state
 and on interleaved states, so that consecutive launches really overlap -- and the outcome must still be the
 oracle's, tick for tick (the tick is Updater.update, optimax_rogue/logic/updater.py:76-162)."""
@@ -31,7 +31,7 @@ def test_back_to_back_ticks_on_one_state(n, tpc):
     """T ticks enqueued without any synchronisation between them: tick k+1 may start on a tile as soon as
     tick k has written it. Every result and the final planes equal the oracle's."""
     ticks = 48
-    cfg = SimConfig(max_ticks=29, seed=77, auto_reset=True, width=11, height=6,
+    cfg = SimConfig(max_ticks=29, seed=77, auto_reset=True, width=11, height=6, overlap_ticks=True,
                     path_flags=tpc << _abi.PATH_TILES_PER_CTA_SHIFT)
     gs, upd, orc = gu.make_pair(cfg, n)
     assert gs.sched.numel() == _abi.sched_words(n)
@@ -58,7 +58,7 @@ def test_back_to_back_ticks_on_one_state(n, tpc):
 def test_long_unsynchronised_runs(n, ticks):
     """Hundreds of ticks in flight behind each other (a CUDA graph replayed without a pause), the state planes of
     the bigger batch far larger than what is in flight: the end state equals the oracle's after the same commands."""
-    cfg = SimConfig(max_ticks=97, seed=4242, auto_reset=True, path_flags=_abi.PATH_FORCE_TILE_FLAGS)     # flag mode at 2^20 games too
+    cfg = SimConfig(max_ticks=97, seed=4242, auto_reset=True, overlap_ticks=True)
     gs, upd, orc = gu.make_pair(cfg, n)
     per = 40
     g = torch.Generator(device='cuda').manual_seed(n)
@@ -89,7 +89,7 @@ def test_graph_of_interleaved_states_replayed():
     """Three states ticked round-robin inside one CUDA graph (launches on different states do not wait for
     each other), the graph replayed several times back to back; each state equals its oracle."""
     n, per_replay, replays = 256 * 24, 15, 4
-    cfgs = [SimConfig(max_ticks=40, seed=5 + k, auto_reset=True, width=9, height=7) for k in range(3)]
+    cfgs = [SimConfig(max_ticks=40, seed=5 + k, auto_reset=True, width=9, height=7, overlap_ticks=True) for k in range(3)]
     trios = [gu.make_pair(c, n, game_id_base=k * n) for k, c in enumerate(cfgs)]
     rng = np.random.default_rng(3)
     mv = _moves(rng, per_replay, n)
@@ -122,7 +122,7 @@ def test_graph_of_interleaved_states_replayed():
 def test_other_kernels_between_flagged_ticks(n):
     """Observation passes (same pipeline, no tick), the fused step+observe, a fused rollout and a masked
     reset between unsynchronised ticks of one state: all ordered correctly against the tile hand-over."""
-    cfg = SimConfig(max_ticks=33, seed=12, auto_reset=True)
+    cfg = SimConfig(max_ticks=33, seed=12, auto_reset=True, overlap_ticks=True)
     gs, upd, orc = gu.make_pair(cfg, n)
     rng = np.random.default_rng(8)
     mv = _moves(rng, 30, n)
@@ -168,13 +168,13 @@ def test_other_kernels_between_flagged_ticks(n):
 
 
 def test_flag_mode_equals_grid_wait_mode():
-    """The same command stream through both ordering modes (path flag ORX_PATH_NO_TILE_FLAGS) and with the
+    """The same command stream through both ordering modes (path flag ORX_PATH_TILE_FLAGS) and with the
     static / dynamic tile hand-out of grid-wait mode: identical planes and results."""
     n, ticks = 256 * 31 + 200, 40
     rng = np.random.default_rng(21)
     mv = torch.from_numpy(_moves(rng, ticks, n)).cuda()
     outs = []
-    for flags in (0, _abi.PATH_NO_TILE_FLAGS, _abi.PATH_NO_TILE_FLAGS | _abi.PATH_STATIC_TILES, _abi.PATH_NO_TENSOR_MAP):
+    for flags in (_abi.PATH_TILE_FLAGS, 0, _abi.PATH_STATIC_TILES, _abi.PATH_NO_TENSOR_MAP, _abi.PATH_TILE_FLAGS | _abi.PATH_NO_TENSOR_MAP):
         cfg = SimConfig(max_ticks=25, seed=31, auto_reset=True, path_flags=flags)
         gs, upd, _ = gu.make_pair(cfg, n)
         res = torch.zeros((ticks, n), dtype=torch.uint8, device='cuda')
@@ -189,9 +189,10 @@ def test_flag_mode_equals_grid_wait_mode():
 
 
 def test_short_scratch_falls_back_to_grid_wait():
-    """A caller that only provides the 4 header words (the round-1 layout) still gets correct ticks."""
+    """A caller that asks for the throughput mode but only provides the 4 header words (the round-1 layout) gets
+    grid-wait mode and correct ticks."""
     n = 256 * 9
-    cfg = SimConfig(max_ticks=25, seed=2, auto_reset=True)
+    cfg = SimConfig(max_ticks=25, seed=2, auto_reset=True, overlap_ticks=True)
     gs, upd, orc = gu.make_pair(cfg, n)
     gs.sched = torch.zeros((_abi.SCHED_HEADER_WORDS,), dtype=torch.int32, device='cuda')
     rng = np.random.default_rng(1)
@@ -208,7 +209,7 @@ def test_short_scratch_falls_back_to_grid_wait():
 # ---------------------------------------------------------------------------------------------------------
 # bit-packed streams (orx_step_bits / orx_step_host_bits): 5 bits of command pair in, 2 bits of result out
 @pytest.mark.parametrize('n', [256 * 37, 256 * 37 + 91, 77, 131072 + 3])
-@pytest.mark.parametrize('flags', [0, _abi.PATH_NO_TILE_FLAGS])
+@pytest.mark.parametrize('flags', [_abi.PATH_TILE_FLAGS, 0])
 def test_bit_packed_streams_match_oracle(n, flags):
     """Device-resident cmd5 / res2 streams, unsynchronised ticks; invalid codes are packed as Stay. Planes and
     the unpacked results equal the oracle's (which is fed the plain codes)."""

@@ -20,13 +20,14 @@ ap.add_argument('--rollout', type=int, default=0, help='also time orx_rollout wi
 ap.add_argument('--json', default=None, help='write the sweep (one row per batch size) to this file')
 ap.add_argument('--path-flags', type=int, default=0, help='OrxConfig.path_flags (include/orx.h ORX_PATH_*)')
 ap.add_argument('--tpc', type=int, default=0, help='tiles per CTA in tile-flag mode (0 = built-in default)')
+ap.add_argument('--overlap', action='store_true', help='throughput mode: SimConfig.overlap_ticks (ORX_PATH_TILE_FLAGS)')
 ap.add_argument('--isolate', action='store_true', help='a tiny ordinary kernel between consecutive steps (what a policy network in the loop does: no overlap between ticks)')
 ap.add_argument('--batches', type=int, default=0, help='rotating batches (0 = enough to exceed the L2; 1 = the same state every step)')
 args = ap.parse_args()
 dev = torch.device('cuda')
 rows = []
 for G in args.games:
-    cfg = SimConfig(max_ticks=1000, seed=1, auto_reset=True, path_flags=args.path_flags | (args.tpc << 8))
+    cfg = SimConfig(max_ticks=1000, seed=1, auto_reset=True, path_flags=args.path_flags | (args.tpc << 8), overlap_ticks=args.overlap)
     nb = args.batches or max(2, min(64, -(-300_000_000 // (32 * G))))
     upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, 1000, auto_reset=True)
     batches = []
@@ -72,8 +73,8 @@ for G in args.games:
                 torch.cuda.synchronize()
                 rbest = min(rbest, e0.elapsed_time(e1) / min(nb, 4))
         print(f'games={G} rollout T={args.rollout}: {rbest * 1e3:.1f} us/launch, {G * args.rollout / rbest * 1e3:.3e} ticks/s', flush=True)
-    print(f'path_flags={args.path_flags} tpc={args.tpc} isolate={int(args.isolate)} games={G} batches={nb} us/step={best * 1e3:.2f} ticks/s={G / best * 1e3:.3e} GB/s(61B)={61 * G / best / 1e6:.0f}', flush=True)
-    rows.append({'path_flags': args.path_flags, 'tiles_per_cta': args.tpc, 'games_per_launch': G, 'rotating_batches': nb, 'us_per_step': round(best * 1e3, 2),
+    print(f'overlap={int(args.overlap)} path_flags={args.path_flags} tpc={args.tpc} isolate={int(args.isolate)} games={G} batches={nb} us/step={best * 1e3:.2f} ticks/s={G / best * 1e3:.3e} GB/s(61B)={61 * G / best / 1e6:.0f}', flush=True)
+    rows.append({'overlap_ticks': bool(args.overlap), 'isolated': bool(args.isolate), 'path_flags': args.path_flags, 'tiles_per_cta': args.tpc, 'games_per_launch': G, 'rotating_batches': nb, 'us_per_step': round(best * 1e3, 2),
                  'game_ticks_per_s': float(f'{G / best * 1e3:.4g}'), 'alg_GBps_61B': round(61 * G / best / 1e6),
                  'frac_of_measured_hbm_peak': round(61 * G / best / 1e6 / 6548.2, 3)})
     del batches, moves, res

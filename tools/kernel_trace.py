@@ -13,7 +13,7 @@ from optimax_rogue_b200.logic.updater import BatchedUpdater, reset_games
 from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
 G = int(sys.argv[1]); out = sys.argv[2]; K = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 dev = torch.device('cuda')
-cfg = SimConfig(max_ticks=1000, seed=0x0A11CE, auto_reset=True)
+cfg = SimConfig(max_ticks=1000, seed=0x0A11CE, auto_reset=True, overlap_ticks=True)      # as bench.py's value leg
 upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, 1000, auto_reset=True)
 nb = max(2, min(64, -(-300_000_000 // (32 * G))))
 bs = []

@@ -5,7 +5,7 @@ python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/p_bench_pla
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_r02.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/p_ncu_list.log 2>&1
 tail -n 2 gpurun_out/p_ncu_list.log
-for spec in "1048576 8 0 pipe2p20" "131072 12 0 pipe2p17" "16777216 4 0 pipe2p24"; do
+for spec in "1048576 8 0 pipe2p20" "131072 12 32 pipe2p17" "16777216 4 0 pipe2p24"; do
   set -- $spec
   python tools/profile_targets2.py $1 $2 $3 > gpurun_out/p_targets_$4.log 2>&1 || { echo "plain targets $4 failed"; continue; }
   ncu --set full --clock-control none --import-source on -k regex:^k_step_pipe$ --launch-skip 2 --launch-count 2 -f \

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from optimax_rogue_b200.r1 import R1GameState
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 16
-flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0     # _abi.R1_PATH_*
+flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0     # _abi.R1_PATH_* (2 = block hand-over, the throughput mode)
 nb = max(2, min(18, (300_000_000 // (244 * G)) + 1))
 K = 4 * nb
 bs = [R1GameState(G, max_ticks=1000, auto_reset=True, seed=3, game_id_base=b * G, path_flags=flags).reset() for b in range(nb)]
