@@ -307,10 +307,12 @@ def run_b200(args, rank, local_rank, world):
         return out
 
     def timed_graph(step_fn, k_steps, nb, min_ms=MIN_WINDOW_MS):
-        """Captures ``m * k_steps`` steps (m >= 1 so that every rotating batch is part of the graph) and replays
-        the graph R times back to back inside one event pair, R such that the window lasts >= min_ms.
+        """Captures ``m * k_steps`` steps -- m >= 1 the smallest count that makes the graph a whole number of turns
+        through the nb rotating batches, so that step k ticks batch k % nb across replays as well and no batch is
+        ticked again before the nb - 1 others -- and replays the graph R times back to back inside one event pair, R
+        such that the window lasts >= min_ms.
         Returns (ms per step, replays of the K-step sequence, window ms, wall-clock bounds of the window)."""
-        m = max(1, -(-nb // k_steps))
+        m = nb // math.gcd(k_steps, nb)
         for k in range(W):
             step_fn(k)
         torch.cuda.synchronize(dev)

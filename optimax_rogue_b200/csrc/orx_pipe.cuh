@@ -71,7 +71,10 @@ constexpr int kTile = ORX_PIPE_TILE;  // games per tile = compute threads per CT
 #define ORX_PIPE_PREFETCH 2          // fixed first tiles per CTA whose planes are prefetched into L2 ahead of the grid dependency
 #endif
 constexpr int kStages = ORX_PIPE_STAGES;
-constexpr int kPipeThreads = kTile + 32;   // + one producer warp
+#ifndef ORX_PIPE_HELPER_WARPS
+#define ORX_PIPE_HELPER_WARPS 1
+#endif
+constexpr int kPipeThreads = kTile + 32 * ORX_PIPE_HELPER_WARPS;   // + the producer warp (tuning builds: more helper warps, idle, to see what the register cap costs)
 constexpr uint32_t kTileIdxBytes = ((uint32_t)kStages * 4u + 15u) & ~15u;   // per-stage tile index words
 #ifndef ORX_PIPE_OBS_STAGES
 #define ORX_PIPE_OBS_STAGES 3
