@@ -495,13 +495,15 @@ int device_sms(int dev)
 
 // Tiles per CTA in flag mode: a function of the state's tile count, the device and the caller's override ONLY (never
 // of the kernel variant), because CTA b must own the same run of tiles in every launch on the state. Default: about
-// one CTA per SM and launch -- consecutive launches share the SMs, so a launch need not fill the machine on its own,
-// and long runs keep each CTA's pipeline full (measured: profiles/r02_batch_sweep.json) -- in whole chunks, at most
-// kBitsMaxTiles tiles (a CTA holds the bit-packed commands of its whole run).
+// HALF a CTA per SM and launch -- in this mode a launch never has the machine to itself (several launches are in
+// flight, that is the point), long runs keep each CTA's pipeline full and amortise the hand-over protocol (measured at
+// 2^17 games: 2.52 us per step with 4 tiles per CTA, 2.29 with 8, 2.27 with 16; at 2^18: 3.72 / 3.50 / 3.42 with 8 /
+// 16 / 32) -- in whole chunks, at most kBitsMaxTiles tiles (a CTA holds the bit-packed commands of its whole run).
 unsigned int flag_tiles_per_cta(unsigned int n_tiles, int sms, int override_tiles)
 {
     const unsigned int n_chunks = (n_tiles + kChunk - 1) / kChunk;
-    unsigned int r = override_tiles > 0 ? ((unsigned int)override_tiles + kChunk - 1) / kChunk : (n_chunks + sms - 1) / (unsigned int)sms;
+    const unsigned int target_ctas = (unsigned int)(sms > 1 ? sms / 2 : 1);
+    unsigned int r = override_tiles > 0 ? ((unsigned int)override_tiles + kChunk - 1) / kChunk : (n_chunks + target_ctas - 1) / target_ctas;
     if (r < 1) r = 1;
     if (r > kBitsMaxTiles / kChunk) r = kBitsMaxTiles / kChunk;
     return r * kChunk;
