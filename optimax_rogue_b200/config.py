@@ -58,6 +58,11 @@ class SimConfig:
         for v in (*self.hp, *self.damage, *self.armor):
             if not -32768 <= v <= 32767:
                 raise ValueError('entity stats must fit int16')
+        # what include/orx.h's check_common enforces: health lives in int16 planes and a hit is subtracted from them
+        if not all(1 <= v <= 32767 for v in self.hp):
+            raise ValueError('hp must be in [1, 32767]')
+        if not all(abs(d - a) <= 32767 - 254 for d, a in zip(self.damage, self.armor)):
+            raise ValueError('|damage - armor| must leave room for the int8 flat bonuses in an int16 hit')
 
     def fixed_tables(self):
         """(tiles uint8[W*H] x-major, ground uint16[#Ground], stairs (x, y)) for DGEN_FIXED."""

@@ -48,6 +48,7 @@ while time.time() - t0 < budget:
         kw.update(n_npc=n_npc)
     else:
         n_npc = 0
+    kw.update(overlap_ticks=bool(rng.integers(0, 2)))          # throughput mode: consecutive launches ordered chunk by chunk
     cfg = SimConfig(**kw)
     size_class = int(rng.integers(0, 4))
     n = int(rng.integers(1, 700)) if size_class == 0 else int(rng.integers(700, 40000)) if size_class < 3 else int(rng.integers(40000, 300000))
@@ -68,7 +69,23 @@ while time.time() - t0 < budget:
             gs.npc_depth.copy_(torch.from_numpy(orc.state.npc_depth))
             gs.npc_pos.copy_(torch.from_numpy(orc.state.npc_pos))
             gs.npc_hp.copy_(torch.from_numpy(orc.state.npc_hp))
-    if rng.integers(0, 2):
+    flat = rng.integers(0, 3) == 0                              # the Modifier seam: random flat bonuses per game and player
+    if flat:
+        frng = np.random.default_rng(int(rng.integers(0, 2**31)))
+        inner = setup
+
+        def setup(gs, orc, inner=inner, frng=frng):
+            if inner is not None:
+                inner(gs, orc)
+            f = frng.integers(-3, 7, size=(orc.n, 2, 3)).astype(np.int8)
+            orc.state.enable_flat_bonuses()[:] = f
+            gs.enable_flat_bonuses().copy_(torch.from_numpy(f))
+    mode = int(rng.integers(0, 4))
+    if mode == 3:                                               # a burst of unsynchronised ticks (overlapping launches when in throughput mode)
+        bits = n_npc == 0 and bool(rng.integers(0, 2))
+        gu.run_burst(cfg, n, min(n_ticks, 48), game_id_base=base, setup=setup, bits=bits, seed=int(rng.integers(0, 2**31)))
+        kind, events = 'burst, bit-packed streams' if bits else 'burst', False
+    elif mode == 2:
         gu.run_parity(cfg, n, n_ticks, bots=bots, events=events, game_id_base=base, setup=setup)
         kind = 'bots'
     else:
@@ -76,7 +93,8 @@ while time.time() - t0 < budget:
         gu.run_parity(cfg, n, n_ticks, events=events, game_id_base=base, setup=setup,
                       moves_fn=lambda t, orc: mrng.integers(0, 8, size=(orc.n, 2), dtype=np.uint8))
         kind = 'random bytes'
-    key = (kind, 'fixed map' if fixed else 'empty rooms', 'events' if events else 'no events', 'NPC slots' if n_npc else 'players only')
+    key = (kind, 'fixed map' if fixed else 'empty rooms', 'events' if events else 'no events', 'NPC slots' if n_npc else 'players only',
+           'throughput mode' if cfg.overlap_ticks else 'grid-wait mode', 'flat bonuses' if flat else 'no modifiers')
     kinds[key] = kinds.get(key, 0) + 1
     runs += 1
     games += n

@@ -59,3 +59,42 @@ def run_parity(cfg, n, ticks, bots=(1, 1), events=True, game_id_base=0, moves_fn
                 assert np.array_equal(ev_g.cpu().numpy(), ev_o), f'tick {t}: events differ'
             assert_state_equal(gs, orc, f'tick {t}')
     return gs, upd, orc
+
+
+def run_burst(cfg, n, ticks, game_id_base=0, setup=None, bits=False, seed=0):
+    """``ticks`` ticks enqueued back to back WITHOUT synchronisation (random command bytes, invalid codes included),
+    results into a [ticks, n] buffer, then every result and the final planes against the oracle. With
+    ``cfg.overlap_ticks`` consecutive launches overlap chunk by chunk; ``bits``: the bit-packed streams."""
+    from optimax_rogue_b200.logic.moves import pack_moves5, unpack_results2
+    gs, upd, orc = make_pair(cfg, n, game_id_base)
+    if setup is not None:
+        setup(gs, orc)
+    rng = np.random.default_rng(seed)
+    mv = rng.integers(0, 8, size=(ticks, n, 2), dtype=np.uint8)
+    if bits:
+        nb_in, nb_out = _abi.cmd5_bytes(n), _abi.res2_bytes(n)
+        pin, pout = -(-nb_in // 16) * 16, -(-nb_out // 16) * 16
+        cmd = torch.zeros((ticks, pin), dtype=torch.uint8)
+        for t in range(ticks):
+            cmd[t, :nb_in] = torch.from_numpy(pack_moves5(mv[t, :, 0], mv[t, :, 1]))
+        cmd = cmd.to(gs.device)
+        res = torch.zeros((ticks, pout), dtype=torch.uint8, device=gs.device)
+        torch.cuda.synchronize()
+        for t in range(ticks):
+            upd.update_bits(gs, cmd[t, :nb_in], out=res[t, :nb_out])
+    else:
+        pad = -(-n // 16) * 16
+        dmv = torch.zeros((ticks, pad, 2), dtype=torch.uint8, device=gs.device)
+        dmv[:, :n] = torch.from_numpy(mv).to(gs.device)
+        res = torch.zeros((ticks, pad), dtype=torch.uint8, device=gs.device)
+        torch.cuda.synchronize()
+        for t in range(ticks):
+            upd.update(gs, dmv[t, :n], out=res[t, :n])
+    torch.cuda.synchronize()
+    got = res.cpu().numpy()
+    for t in range(ticks):
+        want, _ = orc.step(mv[t], want_events=False)
+        have = unpack_results2(got[t, :_abi.res2_bytes(n)], n) if bits else got[t, :n]
+        assert np.array_equal(have, want), f'burst tick {t}: results differ'
+    assert_state_equal(gs, orc, 'after the burst')
+    return gs, upd, orc

@@ -467,6 +467,19 @@ def test_bad_arguments_fail_loudly():
     # n == 0 is a no-op
     c = gs.c_config()
     assert lib.orx_reset(C.byref(c), C.byref(st), None, 0, 0, 0, None) == 0
+    # stats the int16 planes cannot hold are refused at the boundary (not wrapped)
+    for field, val in (('hp', 40000), ('hp', 0), ('damage', 40000)):
+        c = gs.c_config()
+        getattr(c, field)[0] = val
+        assert lib.orx_reset(C.byref(c), C.byref(st), None, 0, 16, 0, None) == _abi.ERR_BAD_ARG, (field, val)
+    # the bit-packed streams: null / misaligned buffers, NPC slots
+    c = gs.c_config()
+    buf = torch.zeros((64,), dtype=torch.uint8, device='cuda')
+    assert lib.orx_step_bits(C.byref(c), C.byref(st), None, buf.data_ptr(), 16, 0, None) == _abi.ERR_BAD_ARG
+    assert lib.orx_step_bits(C.byref(c), C.byref(st), buf.data_ptr() + 1, buf.data_ptr() + 32, 16, 0, None) == _abi.ERR_BAD_ARG
+    gn = BatchedGameState(SimConfig(seed=1, n_npc=2), 16, 'cuda')
+    assert lib.orx_step_bits(C.byref(gn.c_config()), C.byref(gn.c_struct()), buf.data_ptr(), buf.data_ptr() + 32, 16, 0, None) == _abi.ERR_UNSUPPORTED
+    assert lib.orx_sched_words(1 << 20) == _abi.sched_words(1 << 20) and lib.orx_abi_version() == _abi.ABI_VERSION
 
 
 def test_full_size_batch_properties():
