@@ -162,8 +162,9 @@ typedef struct OrxState {
      * { sum of flat_damage, sum of flat_armor, sum of flat_max_health } over the modifiers the entity carries --
      * what Entity.on_tick folds into damage.value / armor.value / max_health.value. A hit then deals
      * (base_damage + flat_damage) - (base_armor + flat_armor) of the ATTACKER (updater.py:313); flat_max_health is
-     * carried for the host view only (nothing on the tick path reads max_health). Read-only for the tick, read in
-     * the combat branch only (no cost when NULL); it belongs to the lane, so a caller that models per-episode
+     * carried for the host view only (nothing on the tick path reads max_health). Read-only for the tick. A state
+     * that carries it is ticked by the one-thread-per-game kernels (the tile pipeline is compiled without the
+     * look-up, so a state without modifiers pays nothing); it belongs to the lane, so a caller that models per-episode
      * modifiers rewrites it when a lane's result says the episode ended. Modifier EVENT hooks (pre/on/post_event)
      * are arbitrary Python upstream and have no counterpart here. */
     const int8_t* flat;

@@ -109,7 +109,7 @@ k_step(const __grid_constant__ Params P, const void* __restrict__ moves, uint8_t
             using NV = std::conditional_t<NPC, NpcView, NoNpc>;
             NV nv;
             if constexpr (NPC) nv = npc_view(P, i);
-            res = tick_lane<DGEN, NV, EV>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
+            res = tick_lane<DGEN, NV, EV, true>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
             ev.finish();
             int new_status = res;
             if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
@@ -209,7 +209,7 @@ k_rollout(const __grid_constant__ Params P, int bot1, int bot2, int n_ticks, uns
                 const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
                 const uint32_t m1 = bot_move(bot1, L.pos & 0xFFFFu, L.st & 0xFFFFu, blk.x);
                 const uint32_t m2 = bot_move(bot2, L.pos >> 16, L.st >> 16, blk.y);
-                const int res = tick_lane<DGEN, NV, false>(P, tiles, lut, L, m1 | (m2 << 8), blk.z, s, nv, ev, cnt);
+                const int res = tick_lane<DGEN, NV, false, true>(P, tiles, lut, L, m1 | (m2 << 8), blk.z, s, nv, ev, cnt);
                 ++cnt.ticks;
                 if (res != ORX_RESULT_IN_PROGRESS) {
                     cnt.p1 += res == ORX_RESULT_PLAYER1_WIN;
@@ -268,7 +268,7 @@ k_replay(const __grid_constant__ Params P, const uint16_t* __restrict__ moves, u
         if (status != ORX_RESULT_IN_PROGRESS) { results[at] = (uint8_t)status; continue; }   // frozen lane
         const uint32_t mv = moves[at];
         const uint4 blk = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)L.tick);
-        const int res = tick_lane<DGEN, NV, false>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
+        const int res = tick_lane<DGEN, NV, false, true>(P, tiles, lut, L, mv, blk.z, s, nv, ev, cnt);
         results[at] = (uint8_t)res;
         if (res != ORX_RESULT_IN_PROGRESS) {
             if (P.auto_reset) { s.episode += 1; reset_lane<DGEN, NV>(P, L, s, nv); }
@@ -497,16 +497,15 @@ int device_sms(int dev)
 // of the kernel variant), because CTA b must own the same run of tiles in every launch on the state. Default: about
 // HALF a CTA per SM and launch -- in this mode a launch never has the machine to itself (several launches are in
 // flight, that is the point), long runs keep each CTA's pipeline full and amortise the hand-over protocol (measured at
-// 2^17 games: 2.52 us per step with 4 tiles per CTA, 2.29 with 8, 2.27 with 16; at 2^18: 3.72 / 3.50 / 3.42 with 8 /
-// 16 / 32) -- in whole chunks, at most kBitsMaxTiles tiles (a CTA holds the bit-packed commands of its whole run).
+// 2^17 games: 2.52 us per step with 4 tiles per CTA, 2.29 with 8, 2.27 with 16) -- and at most kBitsMaxTiles tiles (a
+// CTA holds the bit-packed commands of its whole run, and the run is one hand-over chunk).
 unsigned int flag_tiles_per_cta(unsigned int n_tiles, int sms, int override_tiles)
 {
-    const unsigned int n_chunks = (n_tiles + kChunk - 1) / kChunk;
     const unsigned int target_ctas = (unsigned int)(sms > 1 ? sms / 2 : 1);
-    unsigned int r = override_tiles > 0 ? ((unsigned int)override_tiles + kChunk - 1) / kChunk : (n_chunks + target_ctas - 1) / target_ctas;
-    if (r < 1) r = 1;
-    if (r > kBitsMaxTiles / kChunk) r = kBitsMaxTiles / kChunk;
-    return r * kChunk;
+    unsigned int m = override_tiles > 0 ? (unsigned int)override_tiles : (n_tiles + target_ctas - 1) / target_ctas;
+    if (m < 1) m = 1;
+    if (m > kBitsMaxTiles) m = kBitsMaxTiles;
+    return m;
 }
 
 // Flag mode is a property of the STATE (its scratch size and its number of tiles), never of the kernel variant:
@@ -663,7 +662,8 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
     const int max_ev = orx_max_events(cfg);
     // Hot variants (plain, with observations, with the event log, or with NPC slots): persistent
     // TMA-pipelined kernel over the full 256-game tiles, the simple kernel for a ragged tail (< 256 games).
-    const bool npc_pipe = cfg->n_npc > 0 && ev == nullptr && obs == nullptr && bots == 0 && aligned(st->npc_pos, 16) &&
+    const bool no_flat = st->flat == nullptr;      // a bonus plane (Modifier seam) is read by the one-thread-per-game kernels only
+    const bool npc_pipe = no_flat && cfg->n_npc > 0 && ev == nullptr && obs == nullptr && bots == 0 && aligned(st->npc_pos, 16) &&
                           aligned(st->npc_hp, 16) && aligned(st->npc_depth, 16) && !(cfg->path_flags & ORX_PATH_NO_NPC_PIPE);
     if (npc_pipe && n >= kTile && pipe_aligned(st, moves, result)) {
         const unsigned int n_tiles = (unsigned int)(n / kTile);
@@ -684,7 +684,7 @@ int step_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, ui
         return launch_done();
     }
     const bool ev_pipe = ev != nullptr && obs == nullptr && bots == 0 && aligned(ev, 16) && !(cfg->path_flags & ORX_PATH_NO_EVENT_PIPE);
-    if ((ev == nullptr || ev_pipe) && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
+    if (no_flat && (ev == nullptr || ev_pipe) && cfg->n_npc == 0 && n >= kTile && pipe_aligned(st, moves, result)) {
         const unsigned int n_tiles = (unsigned int)(n / kTile);
         const int64_t n_body = (int64_t)n_tiles * kTile;
         const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
@@ -732,7 +732,7 @@ int step_bits_impl(const OrxConfig* cfg, const OrxState* st, const uint8_t* cmd5
     const bool empty = cfg->dgen_kind == ORX_DGEN_EMPTY;
     const unsigned int n_tiles = (unsigned int)(n / kTile);
     const int64_t n_body = (int64_t)n_tiles * kTile;
-    if (n_tiles > 0 && pipe_aligned(st, cmd5, res2)) {
+    if (n_tiles > 0 && st->flat == nullptr && pipe_aligned(st, cmd5, res2)) {
         const TileCtl ctl = tile_ctl(cfg, st, n_tiles);
         int dev = 0;
         cudaGetDevice(&dev);

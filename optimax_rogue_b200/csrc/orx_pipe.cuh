@@ -27,19 +27,21 @@
 //   grid-wait mode  PDL lets the next grid's CTAs become resident while this grid drains; until
 //                   griddepcontrol.wait releases them they prefetch their first two tiles into L2.
 //   flag mode       (flags != NULL) consecutive launches overlap. A CTA owns a CONTIGUOUS run of tiles_per_cta
-//                   tiles (the same run in every launch on the state), handed over in CHUNKS of kChunk tiles; each
-//                   chunk of the state has two words in OrxState.sched: next (tickets handed out) and serving
-//                   (passes completed). A CTA draws the tickets of ALL its chunks before it lets dependents launch,
-//                   so tickets are in launch order; it loads a chunk once serving equals its ticket and releases
-//                   serving = ticket + 1 (gpu scope) once the chunk's bulk stores have completed. There is no
-//                   grid-wide wait before the first load: tick k+1 follows tick k through the tiles one chunk
-//                   behind, and launches on different states do not wait for each other at all. The producer runs
+//                   tiles (the same run in every launch on the state), handed over in chunks of kChunk tiles -- as
+//                   shipped ONE chunk, the whole run (runs are at most 32 tiles). Each chunk of the state has two
+//                   words in OrxState.sched: next (tickets handed out) and serving (passes completed). A CTA draws
+//                   the tickets of its chunks before it lets dependents launch, so tickets are in launch order; it
+//                   loads a chunk once serving equals its ticket and releases serving = ticket + 1 (gpu scope) once
+//                   the chunk's bulk stores have completed. There is no grid-wide wait before the first load: CTA b
+//                   of tick k+1 starts as soon as CTA b of tick k is done, whatever the rest of tick k is doing, and
+//                   launches on different states do not wait for each other at all. The producer runs
 //                   griddepcontrol.wait last, before it exits, so that "this grid is complete" still implies "every
 //                   earlier grid in the stream is complete" for whatever the caller enqueues next.
-//                   Why chunks: the release is MEMBAR.ALL.GPU in the one thread that moves data (0.65 us); per tile
-//                   it cost more than the overlap gained (19.0 against 12.5 us per 2^20-game step), and without it
-//                   the completion of a bulk store is only visible to its own thread -- relaxed flags gave wrong
-//                   planes in long unsynchronised runs (profiles/r02_ab_flag_fences.log).
+//                   Why not finer: the release is MEMBAR.ALL.GPU in the one thread that moves data (0.65 us). Per
+//                   tile it cost more than the overlap gained (19.0 against 12.5 us per 2^20-game step), per 4 / 8 /
+//                   16 / 32 tiles a step took 11.7 / 10.8 / 10.3 / 10.1 us; and without the fence the completion of a
+//                   bulk store is only visible to its own thread -- relaxed flags gave wrong planes in long
+//                   unsynchronised runs (profiles/r02_ab_flag_fences.log, r02_ab_chunk_size.log).
 #pragma once
 #include <cuda.h>             // CUtensorMap (type only; the encoder is looked up at run time)
 #include <cuda_runtime.h>
@@ -225,7 +227,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned int* p, uint32_t v) { as
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 #ifndef ORX_PIPE_CHUNK
-#define ORX_PIPE_CHUNK 4             // tiles per hand-over chunk in flag mode
+#define ORX_PIPE_CHUNK 32            // tiles per hand-over chunk in flag mode: with runs of at most 32 tiles, ONE chunk = the CTA's whole run
 #endif
 constexpr int kChunk = ORX_PIPE_CHUNK;
 constexpr int kMaxChunksPerCta = 32;          // one ticket per lane of the producer warp
@@ -320,9 +322,9 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
 
     if (tid >= kTile) {
         // ------------------------------------------------------------ producer (one thread)
-        // flag mode: chunk c of this CTA = its tiles [c kChunk, (c+1) kChunk); global chunk index = first tile / kChunk
-        // (tiles_per_cta is a multiple of kChunk, so runs start on chunk boundaries)
-        const size_t chunk0 = (size_t)blockIdx.x * (tiles_per_cta / (unsigned)kChunk);
+        // flag mode: chunk c of this CTA = its tiles [c kChunk, (c+1) kChunk) (the last one may be shorter); chunks are
+        // numbered CTA by CTA, so a chunk is the same tiles in every launch on the state
+        const size_t chunk0 = (size_t)blockIdx.x * ((tiles_per_cta + (unsigned)kChunk - 1u) / (unsigned)kChunk);
         if (flagged) {
             // Lane c of the producer warp draws the ticket of this CTA's chunk c: one atomic instruction, one round
             // trip for all of them. The value has arrived when the shared-memory store that depends on it has been

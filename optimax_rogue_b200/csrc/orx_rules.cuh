@@ -275,10 +275,14 @@ __device__ __forceinline__ bool is_stairs(const Params& P, const uint8_t* tiles,
 
 // What a hit by player `pid` takes off its victim (updater.py:313: attacker.damage.value - attacker.armor.value, the
 // attribles being base + the modifiers' flat bonuses, attribles.py:29-43). Only called from the combat branches.
+// FLAT: whether this instantiation looks at the bonus plane at all. The tile-pipeline kernels do not (ptxas folds the
+// combat branches into the straight-line tick, so even a never-taken look-up cost 16 predicated instructions per
+// game-tick, 8 % of the kernel): a state that carries a bonus plane is ticked by the one-thread-per-game kernels.
+template <bool FLAT>
 __device__ __forceinline__ int hit_of(const Params& P, const Stream& s, int pid)
 {
     int d = pid == 0 ? P.dmg0 : P.dmg1;
-    if (P.flat != nullptr) {
+    if (FLAT && P.flat != nullptr) {
         const size_t i = (size_t)(s.g0 - (uint32_t)P.gid_base);      // lane of this launch (< 2^30)
         d += (int)P.flat[i * 6 + 3 * pid] - (int)P.flat[i * 6 + 3 * pid + 1];
     }
@@ -287,7 +291,7 @@ __device__ __forceinline__ int hit_of(const Params& P, const Stream& s, int pid)
 
 // One Updater.update. mv = p1 command | p2 command << 8; w_init is word 2 of the tick's main
 // block. Returns the UpdateResult.
-template <int DGEN, class NV, bool EV>
+template <int DGEN, class NV, bool EV, bool FLAT = false>
 __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, const CmdEntry* lut, Lane& L, uint32_t mv,
                                          uint32_t w_init, const Stream& s, const NV& nv,
                                          EvSink<EV>& ev, Counters& cnt)
@@ -319,11 +323,11 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
         if (same & (tA == (pos >> 16))) {
             // Occupied by B, who acts later: Block if B stays, else Flee. (Parry, updater.py:229-234,
             // would need B.pos + delta == B.pos with a non-Stay move: unreachable.)
-            const int dmgA = hit_of(P, s, idA);
+            const int dmgA = hit_of<FLAT>(P, s, idA);
             if (dmgA > 0) { if (p2_first) hp1 -= dmgA; else hp2 -= dmgA; ++cnt.hits; }      // the victim is B
             ev.emit(ORX_EV_COMBAT, idA + 1, idB + 1, dB == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_FLEE, dmgA);
         } else if (NPC && (npc = npc_at(nv, depA(), tA)) >= 0) {
-            const int dmgA = hit_of(P, s, idA);
+            const int dmgA = hit_of<FLAT>(P, s, idA);
             if (dmgA > 0) { npc_hit(nv, npc, dmgA); ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idA + 1, 3 + npc, ORX_FLAG_BLOCK, dmgA);
         } else if (is_stairs<DGEN>(P, tiles, tA, st & 0xFFFFu)) {
@@ -346,11 +350,11 @@ __device__ __forceinline__ int tick_lane(const Params& P, const uint8_t* tiles, 
         const uint32_t tB = ((pos >> 16) + (uint32_t)dB) & 0xFFFFu;
         int npc = -1;
         if (same & (tB == (pos & 0xFFFFu))) {
-            const int dmgB = hit_of(P, s, idB);
+            const int dmgB = hit_of<FLAT>(P, s, idB);
             if (dmgB > 0) { if (p2_first) hp2 -= dmgB; else hp1 -= dmgB; ++cnt.hits; }      // the victim is A
             ev.emit(ORX_EV_COMBAT, idB + 1, idA + 1, dA == 0 ? ORX_FLAG_BLOCK : ORX_FLAG_AMBUSH, dmgB);
         } else if (NPC && (npc = npc_at(nv, depB(), tB)) >= 0) {
-            const int dmgB = hit_of(P, s, idB);
+            const int dmgB = hit_of<FLAT>(P, s, idB);
             if (dmgB > 0) { npc_hit(nv, npc, dmgB); ++cnt.hits; }
             ev.emit(ORX_EV_COMBAT, idB + 1, 3 + npc, ORX_FLAG_BLOCK, dmgB);
         } else if (is_stairs<DGEN>(P, tiles, tB, st >> 16)) {
