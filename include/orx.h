@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ORX_ABI_VERSION 4
+#define ORX_ABI_VERSION 5
 
 /* logic/moves.py:6-12 */
 enum { ORX_MOVE_UP = 1, ORX_MOVE_RIGHT = 2, ORX_MOVE_DOWN = 3, ORX_MOVE_LEFT = 4, ORX_MOVE_STAY = 5 };
@@ -118,7 +118,7 @@ typedef struct OrxConfig {
                                        to back overlap (see OrxState.sched). For queued command streams and for several
                                        states in flight; a loop that runs other kernels between two ticks (a policy
                                        network) is faster without it. Needs sched_words >= orx_sched_words(n); batches
-                                       above 2^20 games are ticked grid by grid regardless (faster there). */
+                                       above 2^22 games are ticked grid by grid regardless. */
 #define ORX_PATH_TILES_PER_CTA_SHIFT 8  /* bits 8..15: tiles per CTA in tile-flag mode (0 = built-in default) */
 
 /* Structure-of-arrays game state; game i of the batch is element i of every plane.
@@ -363,6 +363,49 @@ int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mov
 /* n_ticks fused ticks, both players uniform random over the six commands; stats as orx_rollout */
 int orx_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, unsigned long long* stats,
                    int64_t n, uint64_t game_id_base, void* cuda_stream);
+
+/* Replication log of an R1 tick (logic/updates.py: the reference's GameStateUpdate classes, which its Updater appends to
+ * in tick order, updater.py:71-74). Same 8-byte OrxEvent record as R0; idens are lane + 1 (players 1, 2; enemy slot e
+ * 3 + e; item slot i 11 + i). Kinds beyond R0's, with their (iden, a, b, depth) fields:
+ *   ORX_EV_SPAWN   EntitySpawnUpdate (updates.py:141): the new entity's iden, x, y, depth | aux << 16 (aux = hp of an
+ *                  enemy, kind of an item)
+ *   ORX_EV_HEALTH  EntityHealthUpdate (updates.py:222), health changed outside combat: entity iden, source iden,
+ *                  ORX_R1_HEALTH_* tag, signed amount
+ *   ORX_EV_PICKUP  a player took an item (the item's flat bonus is a Modifier, EntityModifierAddedUpdate updates.py:255):
+ *                  player iden, item iden, item kind, health gained (2 for the max-health item)
+ *   ORX_EV_XP      EntityEventUpdate (updates.py:31) 'xp': player iden, the enemy's iden, levels gained (a level-up
+ *                  refills health and mana), xp after
+ * and of R0's kinds: MOVE / DESCEND / DUNGEON as in R0; COMBAT: attacker iden, defender iden, ORX_R1_HIT_* tag, damage dealt;
+ * DEATH: iden, a = 1 when the entity vanished with its level instead of dying.
+ * Order within a tick (docs/RULESET_R1.md "Replication log"): heals; attacks by attacker lane; moves by lane; pickups by
+ * player; descents by player (DUNGEON only when the other player is not on that depth already, then DESCEND); enemy
+ * deaths by slot, each followed by its XP records; drops by slot; vanished enemies / items by lane; spawns by level;
+ * separation damage; player deaths. At most 51 records per tick can occur; ORX_R1_MAX_EVENTS slots never overflow,
+ * records beyond a smaller capacity are dropped. kind == ORX_EV_NONE terminates a game's list when it is shorter than
+ * the capacity; slots behind the terminator are not written. */
+enum { ORX_EV_SPAWN = 6, ORX_EV_HEALTH = 7, ORX_EV_PICKUP = 8, ORX_EV_XP = 9 };
+enum { ORX_R1_HIT_FULL = 1, ORX_R1_HIT_HALF = 2, ORX_R1_HIT_NEGATED = 3, ORX_R1_HIT_CONTEST = 4 };
+enum { ORX_R1_HEALTH_HEAL = 1, ORX_R1_HEALTH_SEPARATION = 2 };
+#define ORX_R1_MAX_EVENTS 64
+/* orx_r1_step + the tick's records: events device OrxEvent[n][max_events], 8-byte aligned, 1 <= max_events <= 255.
+ * One-thread-per-game kernel (not with ORX_R1_PATH_HALFWARP: ORX_ERR_UNSUPPORTED). */
+int orx_r1_step_events(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* moves, uint8_t* result,
+                       OrxEvent* events, int max_events, int64_t n, uint64_t game_id_base, void* cuda_stream);
+/* Scripted players (optimax_rogue_bots/randombot.py:20-21 widened to the six R1 commands -- the policy of
+ * orx_r1_rollout, same draws --, staircasebot.py:9-20 on the player's own level). ORX_BOT_NONE leaves that player's
+ * byte of moves (device uint8[n][2]) untouched. */
+int orx_r1_bot_moves(const OrxR1Config* cfg, const OrxR1State* st, int bot1, int bot2, uint8_t* moves,
+                     int64_t n, uint64_t game_id_base, void* cuda_stream);
+/* n_ticks ticks with both players' commands queued in advance, the state in registers in between (the loop of
+ * server/main.py:110-113 fed from a buffer): moves device uint8[n_ticks][n][2], results device uint8[n_ticks][n].
+ * Identical to n_ticks orx_r1_step calls; a game that ends without auto_reset repeats its status. */
+int orx_r1_replay(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* moves, uint8_t* results, int n_ticks,
+                  int64_t n, uint64_t game_id_base, void* cuda_stream);
+/* orx_r1_step with the caller's PINNED HOST buffers (cudaHostAlloc / cudaHostRegister; host_moves uint8[n][2],
+ * host_result uint8[n]): the kernel reads the commands and writes the results across PCIe itself, then the call waits
+ * for the stream -- on return host_result holds this tick's results. */
+int orx_r1_step_host_sync(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* host_moves, uint8_t* host_result,
+                          int64_t n, uint64_t game_id_base, void* cuda_stream);
 
 /* Per-player observation for ruleset R1: obs int16[n][2][ORX_R1_OBS_LEN] (GameState.view_for,
  * game/state.py:53-58, widened to the R1 state; "a ladder ... becomes visible when an agent gets

@@ -4,7 +4,7 @@ Kept free of torch so that the CPU test-suite can check the ABI without a GPU.
 """
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 MAX_NPC = 8
 MAX_EVENTS_BASE = 4
@@ -81,6 +81,10 @@ class OrxEvent(C.Structure):
 
 # ---- ruleset R1 (README-only rules; docs/RULESET_R1.md) ------------------------------------------
 R1_LANES, R1_ENEMIES, R1_ITEMS, MOVE_HEAL, R1_STATE_BYTES, R1_OBS_LEN = 16, 8, 4, 6, 241, 64
+EV_SPAWN, EV_HEALTH, EV_PICKUP, EV_XP = 6, 7, 8, 9                       # R1 replication-log kinds (include/orx.h)
+R1_HIT_FULL, R1_HIT_HALF, R1_HIT_NEGATED, R1_HIT_CONTEST = 1, 2, 3, 4
+R1_HEALTH_HEAL, R1_HEALTH_SEPARATION = 1, 2
+R1_MAX_EVENTS = 64
 
 
 class OrxR1Config(C.Structure):
@@ -155,6 +159,14 @@ PROTOTYPES = {
                                  C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_r1_observe': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_void_p, C.c_int,
                                  C.c_int64, C.c_void_p]),
+    'orx_r1_step_events': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_r1_bot_moves': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_int, C.c_int, C.c_void_p,
+                                   C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_r1_replay': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_int64, C.c_uint64, C.c_void_p]),
+    'orx_r1_step_host_sync': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_uint64, C.c_void_p]),
 }
 
 

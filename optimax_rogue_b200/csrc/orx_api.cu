@@ -16,7 +16,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxFixedTiles = 16384;   // shared-memory staging of the fixed map
-constexpr unsigned int kFlagModeMaxTiles = 4096;   // 2^20 games: the largest batch ticked in flag mode (tile_ctl)
+#ifndef ORX_FLAG_MODE_MAX_TILES
+#define ORX_FLAG_MODE_MAX_TILES 16384
+#endif
+constexpr unsigned int kFlagModeMaxTiles = ORX_FLAG_MODE_MAX_TILES;   // 2^22 games: the largest batch ticked in flag mode (tile_ctl)
 constexpr int64_t kMaxGamesPerCall = 1ll << 30;   // 32-bit lane index inside the kernels; larger batches: call per chunk
 
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p)
@@ -494,14 +497,16 @@ int device_sms(int dev)
 }
 
 // Tiles per CTA in flag mode: a function of the state's tile count, the device and the caller's override ONLY (never
-// of the kernel variant), because CTA b must own the same run of tiles in every launch on the state. Default: about
-// HALF a CTA per SM and launch -- in this mode a launch never has the machine to itself (several launches are in
-// flight, that is the point), long runs keep each CTA's pipeline full and amortise the hand-over protocol (measured at
-// 2^17 games: 2.52 us per step with 4 tiles per CTA, 2.29 with 8, 2.27 with 16) -- and at most kBitsMaxTiles tiles (a
-// CTA holds the bit-packed commands of its whole run, and the run is one hand-over chunk).
+// of the kernel variant), because CTA b must own the same run of tiles in every launch on the state. Default: about a
+// QUARTER of a CTA per SM and launch -- in this mode a launch never has the machine to itself (several launches are in
+// flight, that is the point), the next launch starts when EVERY CTA of this one has drawn its ticket, long runs keep
+// each CTA's pipeline full and amortise the hand-over protocol (measured at 2^17 games = 512 tiles, us per step with
+// 2 / 3 / 4 / 5 / 7 / 10 / 14 tiles per CTA: 3.45 / 2.70 / 2.33 / 2.11 / 1.94 / 1.84 / 1.82; at 2^20 with 10 / 14 / 20 /
+// 28 / 32: 11.3 / 10.7 / 10.2 / 9.89 / 9.87, profiles/r02_ab_ticket_first.log) -- and at most kBitsMaxTiles tiles (a CTA
+// holds the bit-packed commands of its whole run, and the run is one hand-over chunk).
 unsigned int flag_tiles_per_cta(unsigned int n_tiles, int sms, int override_tiles)
 {
-    const unsigned int target_ctas = (unsigned int)(sms > 1 ? sms / 2 : 1);
+    const unsigned int target_ctas = (unsigned int)(sms > 3 ? sms / 4 : 1);
     unsigned int m = override_tiles > 0 ? (unsigned int)override_tiles : (n_tiles + target_ctas - 1) / target_ctas;
     if (m < 1) m = 1;
     if (m > kBitsMaxTiles) m = kBitsMaxTiles;
@@ -522,8 +527,9 @@ TileCtl tile_ctl(const OrxConfig* cfg, const OrxState* st, unsigned int n_tiles)
     // Flag mode is the caller's choice (ORX_PATH_TILE_FLAGS): it pays about 2.5 us of latency per launch (tickets,
     // acquire, completion + release fence per chunk) for not having a grid-wide boundary between launches, which is a
     // gain for ticks enqueued back to back and a loss for a tick that runs alone (profiles/r02_batch_sweep.json).
-    // Above kFlagModeMaxTiles tiles (2^20 games) a launch is long enough for the boundary not to matter and grid-wait
-    // mode (dynamic tile hand-out, L2 prefetch across the boundary) is the faster one again: 21.5 against 23.2 us at 2^21.
+    // Measured up to kFlagModeMaxTiles tiles (2^22 games: 19.6 against 21.2 us per step at 2^21, 38.9 against 39.8 at
+    // 2^22, profiles/r02_ab_ticket_first.log); above that a launch is long enough for the boundary not to matter and the
+    // batch is ticked grid by grid.
     if ((cfg->path_flags & ORX_PATH_TILE_FLAGS) && st->sched_words >= need && n_tiles <= kFlagModeMaxTiles) {
         c.flags = st->sched + ORX_SCHED_HEADER_WORDS;
         c.tiles_per_cta = (int)flag_tiles_per_cta(n_tiles, sms, (int)((cfg->path_flags >> ORX_PATH_TILES_PER_CTA_SHIFT) & 255u));

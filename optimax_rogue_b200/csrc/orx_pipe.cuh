@@ -290,6 +290,38 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     // (griddepcontrol.wait) before it touches any plane. Flag mode: only after this CTA holds the tickets
     // of all its tiles (below), which is what keeps the tickets of consecutive launches in launch order.
     if (ORX_PIPE_PDL && !flagged) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Static assignment: tile of this CTA's it-th iteration. Strided over the grid, or (flag mode, CMD_BITS) a contiguous run.
+    constexpr uint32_t NONE = 0xFFFFFFFFu;    // published instead of a tile index: no more work for this CTA
+    auto tile_at = [&](unsigned int it) -> uint32_t {
+        if (CMD == CMD_BITS || flagged) {
+            const uint64_t t = (uint64_t)blockIdx.x * tiles_per_cta + it;
+            return it < tiles_per_cta && t < n_tiles ? (uint32_t)t : NONE;
+        }
+        const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
+        return t < n_tiles ? (uint32_t)t : NONE;
+    };
+    // flag mode: chunk c of this CTA = its tiles [c kChunk, (c+1) kChunk) (the last one may be shorter); chunks are
+    // numbered CTA by CTA, so a chunk is the same tiles in every launch on the state
+    const size_t chunk0 = (size_t)blockIdx.x * ((tiles_per_cta + (unsigned)kChunk - 1u) / (unsigned)kChunk);
+#ifndef ORX_PIPE_LATE_TICKET
+    if (flagged && tid >= kTile) {
+        // FIRST thing the producer warp does, ahead of the barrier set-up and the command table: lane c draws the
+        // ticket of this CTA's chunk c (one atomic instruction, one round trip for all of them) and the CTA lets the
+        // dependents go. The value has arrived when the shared-memory store that depends on it has been issued, i.e.
+        // the atomic has been performed at the L2 before the next launch can start -- which keeps the tickets of
+        // consecutive launches in launch order. The next launch starts once EVERY CTA of this one is past this
+        // point, so everything ahead of it is on the launch-to-launch critical path of back-to-back ticks.
+        const unsigned int c = tid - kTile;
+#ifdef ORX_EXPERIMENT_TRIGGER_BEFORE_TICKET     // tuning experiment only (tickets may come out of launch order): what the ticket's round trip costs the launch chain
+        if (ORX_PIPE_PDL && tid == kTile) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+        if (tile_at(c * (unsigned)kChunk) != NONE) sts_u32(tk0 + 4u * c, atomicAdd(flags + 2 * (chunk0 + c), 1u));
+        __syncwarp();
+#ifndef ORX_EXPERIMENT_TRIGGER_BEFORE_TICKET
+        if (ORX_PIPE_PDL && tid == kTile) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+    }
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -309,33 +341,19 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     }
     __syncthreads();
 
-    constexpr uint32_t NONE = 0xFFFFFFFFu;    // published instead of a tile index: no more work for this CTA
-    // Static assignment: tile of this CTA's it-th iteration. Strided over the grid, or (flag mode, CMD_BITS) a contiguous run.
-    auto tile_at = [&](unsigned int it) -> uint32_t {
-        if (CMD == CMD_BITS || flagged) {
-            const uint64_t t = (uint64_t)blockIdx.x * tiles_per_cta + it;
-            return it < tiles_per_cta && t < n_tiles ? (uint32_t)t : NONE;
-        }
-        const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
-        return t < n_tiles ? (uint32_t)t : NONE;
-    };
-
     if (tid >= kTile) {
         // ------------------------------------------------------------ producer (one thread)
-        // flag mode: chunk c of this CTA = its tiles [c kChunk, (c+1) kChunk) (the last one may be shorter); chunks are
-        // numbered CTA by CTA, so a chunk is the same tiles in every launch on the state
-        const size_t chunk0 = (size_t)blockIdx.x * ((tiles_per_cta + (unsigned)kChunk - 1u) / (unsigned)kChunk);
+#ifdef ORX_PIPE_LATE_TICKET       // tuning build: tickets and hand-off to the dependents after the set-up (the round-2 order until call P)
         if (flagged) {
-            // Lane c of the producer warp draws the ticket of this CTA's chunk c: one atomic instruction, one round
-            // trip for all of them. The value has arrived when the shared-memory store that depends on it has been
-            // issued, i.e. the atomic has been performed at the L2 before this CTA lets the dependents go -- which
-            // keeps the tickets of consecutive launches in launch order.
             const unsigned int c = tid - kTile;
             if (tile_at(c * (unsigned)kChunk) != NONE) sts_u32(tk0 + 4u * c, atomicAdd(flags + 2 * (chunk0 + c), 1u));
             __syncwarp();
         }
         if (tid != kTile) return;
         if (ORX_PIPE_PDL && flagged) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#else
+        if (tid != kTile) return;
+#endif
         if (use_map) asm volatile("prefetch.tensormap [%0];" ::"l"(&planes5) : "memory");     // descriptor fetch off the first copy's path
         auto peek = [&](unsigned int c) -> uint32_t {        // serving word of this CTA's chunk c (0 beyond its run)
             return tile_at(c * (unsigned)kChunk) != NONE ? ld_acquire_gpu(flags + 2 * (chunk0 + c) + 1) : 0u;

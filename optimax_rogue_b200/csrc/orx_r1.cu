@@ -584,18 +584,21 @@ int orx_r1_reset(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* ma
     return r1_done();
 }
 
-int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* moves, uint8_t* result,
-                int64_t n, uint64_t game_id_base, void* cuda_stream)
+// Common body of orx_r1_step / orx_r1_step_events / orx_r1_step_host_sync.
+static int r1_step_impl(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* moves, uint8_t* result, OrxEvent* events,
+                        int max_events, int64_t n, uint64_t game_id_base, void* cuda_stream)
 {
     const int rc = r1_check(cfg, st, n);
     if (rc != ORX_OK) return rc;
     if ((game_id_base >> 54) != 0 || ((game_id_base + (uint64_t)n) >> 54) != 0) return ORX_ERR_BAD_ARG;
     if (moves == nullptr || result == nullptr || (reinterpret_cast<uintptr_t>(moves) & 1)) return ORX_ERR_BAD_ARG;
+    if (events != nullptr && (max_events < 1 || max_events > 255 || (reinterpret_cast<uintptr_t>(events) & 7))) return ORX_ERR_BAD_ARG;
     if (n == 0) return ORX_OK;
     // Default: one thread per game (orx_r1t.cuh). ORX_R1_PATH_HALFWARP selects the sixteen-lanes-per-game
     // kernels instead (same results; kept as the warp-primitive formulation and as a cross-check).
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     if (cfg->path_flags & ORX_R1_PATH_HALFWARP) {
+        if (events != nullptr) return ORX_ERR_UNSUPPORTED;
         k_r1_step<<<r1_grid(n), kThreadsR1, 0, s>>>(r1_params(cfg, st, n, game_id_base), moves, result);
         return r1_done();
     }
@@ -603,10 +606,12 @@ int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mov
     const unsigned int grid = (unsigned)((n + r1t::kThreads - 1) / r1t::kThreads);
     const R1Params P = r1_params(cfg, st, n, game_id_base);
     const uint16_t* mv = reinterpret_cast<const uint16_t*>(moves);
+    uint2* evp = reinterpret_cast<uint2*>(events);
     const bool flagged = st->sched != nullptr && (reinterpret_cast<uintptr_t>(st->sched) & 3) == 0 &&
                          st->sched_words >= ORX_R1_SCHED_WORDS(n) && (cfg->path_flags & ORX_R1_PATH_BLOCK_FLAGS) != 0;
     if (!flagged) {
-        r1t::k_step<false><<<grid, r1t::kThreads, 0, s>>>(P, mv, result, nullptr);
+        if (events != nullptr) r1t::k_step<false, true><<<grid, r1t::kThreads, 0, s>>>(P, mv, result, nullptr, evp, max_events);
+        else r1t::k_step<false, false><<<grid, r1t::kThreads, 0, s>>>(P, mv, result, nullptr, nullptr, 0);
         return r1_done();
     }
     cudaLaunchConfig_t lc = {};
@@ -615,8 +620,63 @@ int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mov
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, r1t::k_step<true>, P, mv, result, st->sched);
+    const cudaError_t e = events != nullptr ? cudaLaunchKernelEx(&lc, r1t::k_step<true, true>, P, mv, result, st->sched, evp, max_events)
+                                            : cudaLaunchKernelEx(&lc, r1t::k_step<true, false>, P, mv, result, st->sched, (uint2*)nullptr, 0);
     return e == cudaSuccess ? r1_done() : ORX_ERR_CUDA_BASE - (int)e;
+}
+
+int orx_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* moves, uint8_t* result,
+                int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    return r1_step_impl(cfg, st, moves, result, nullptr, 0, n, game_id_base, cuda_stream);
+}
+
+int orx_r1_step_events(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* moves, uint8_t* result,
+                       OrxEvent* events, int max_events, int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    if (events == nullptr) return ORX_ERR_BAD_ARG;
+    return r1_step_impl(cfg, st, moves, result, events, max_events, n, game_id_base, cuda_stream);
+}
+
+int orx_r1_step_host_sync(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* host_moves, uint8_t* host_result,
+                          int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    // The buffers must be device-accessible host memory (pinned): the kernel reads / writes them across PCIe itself.
+    for (const void* p : {static_cast<const void*>(host_moves), static_cast<const void*>(host_result)}) {
+        if (p == nullptr) return ORX_ERR_BAD_ARG;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return ORX_ERR_BAD_ARG; }
+        if (a.type != cudaMemoryTypeHost && a.type != cudaMemoryTypeManaged) return ORX_ERR_BAD_ARG;
+    }
+    const int rc = r1_step_impl(cfg, st, host_moves, host_result, nullptr, 0, n, game_id_base, cuda_stream);
+    if (rc != ORX_OK) return rc;
+    const cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
+    return e == cudaSuccess ? ORX_OK : ORX_ERR_CUDA_BASE - (int)e;
+}
+
+int orx_r1_bot_moves(const OrxR1Config* cfg, const OrxR1State* st, int bot1, int bot2, uint8_t* moves,
+                     int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    const int rc = r1_check(cfg, st, n);
+    if (rc != ORX_OK) return rc;
+    if ((game_id_base >> 54) != 0 || ((game_id_base + (uint64_t)n) >> 54) != 0) return ORX_ERR_BAD_ARG;
+    if (moves == nullptr || bot1 < ORX_BOT_NONE || bot1 > ORX_BOT_STAIRCASE || bot2 < ORX_BOT_NONE || bot2 > ORX_BOT_STAIRCASE) return ORX_ERR_BAD_ARG;
+    if (n == 0 || (bot1 == ORX_BOT_NONE && bot2 == ORX_BOT_NONE)) return ORX_OK;
+    r1t::k_bot_moves<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(r1_params(cfg, st, n, game_id_base), bot1, bot2, moves);
+    return r1_done();
+}
+
+int orx_r1_replay(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* moves, uint8_t* results, int n_ticks,
+                  int64_t n, uint64_t game_id_base, void* cuda_stream)
+{
+    const int rc = r1_check(cfg, st, n);
+    if (rc != ORX_OK) return rc;
+    if ((game_id_base >> 54) != 0 || ((game_id_base + (uint64_t)n) >> 54) != 0) return ORX_ERR_BAD_ARG;
+    if (n_ticks < 0 || moves == nullptr || results == nullptr || (reinterpret_cast<uintptr_t>(moves) & 1)) return ORX_ERR_BAD_ARG;
+    if (n == 0 || n_ticks == 0) return ORX_OK;
+    r1t::k_replay<<<(unsigned)((n + r1t::kThreads - 1) / r1t::kThreads), r1t::kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        r1_params(cfg, st, n, game_id_base), reinterpret_cast<const uint16_t*>(moves), results, n_ticks);
+    return r1_done();
 }
 
 int orx_r1_rollout(const OrxR1Config* cfg, const OrxR1State* st, int n_ticks, unsigned long long* stats,

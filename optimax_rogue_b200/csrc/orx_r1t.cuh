@@ -64,17 +64,50 @@ __device__ __forceinline__ void setup_game(const R1Params& P, Game& G, const Str
     for (int i = 0; i < ORX_R1_ITEMS; ++i) { G.ikey[i] = DEAD; G.ikind[i] = 0; }
     level_init(P, s, 0, G.sx[0], G.sy[0], G.lkey[0]);
     G.sx[1] = G.sx[0]; G.sy[1] = G.sy[0]; G.lkey[1] = G.lkey[0];
+    // ONE copy of the free-tile search for both players (a rolled loop; the slot is written through selects): the rare
+    // paths are what made the tick's body 6k instructions, and a warp runs a rare path whenever one of its 32 games does
+#pragma unroll 1
+    for (int p = 0; p < 2; ++p) {
+        const uint32_t k = free_tile(P, G, s, DOM_RESET, 32u * (uint32_t)p, 0u, 0, G.lkey[0], G.sx[0], G.sy[0], -1);
+        if (p == 0) G.key[0] = k; else G.key[1] = k;
+    }
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        G.key[p] = free_tile(P, G, s, DOM_RESET, 32u * p, 0u, 0, G.lkey[0], G.sx[0], G.sy[0], -1);
         G.hp[p] = 10; G.mana[p] = 9; G.max_hp[p] = 10; G.max_mana[p] = 9; G.xp[p] = 0; G.level[p] = 1;
         G.n_items[p] = 0; G.cd[p] = 0; G.damage[p] = 2; G.armor[p] = 1;
     }
     G.sep = 0; G.tick = 1;
 }
 
+// element m of a register array through a select chain (m is a run-time value, the array stays in registers)
+template <int N>
+__device__ __forceinline__ uint32_t pick(const uint32_t (&a)[N], int m)
+{
+    uint32_t v = a[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) v = m == j ? a[j] : v;
+    return v;
+}
+
+// Replication log of one game-tick (include/orx.h "Replication log of an R1 tick"): records go straight to the game's
+// slots in global memory, in emission order; without EV every call folds away.
+template <bool EV>
+struct Sink {
+    uint2* base;
+    int n, cap;
+    __device__ __forceinline__ void emit(int kind, int iden, int a, int b, int value)
+    {
+        if (EV) {
+            if (n < cap) base[n] = make_uint2((uint32_t)kind | ((uint32_t)iden << 8) | ((uint32_t)(a & 255) << 16) | ((uint32_t)(b & 255) << 24), (uint32_t)value);
+            ++n;
+        }
+    }
+    __device__ __forceinline__ void finish() { if (EV) if (n < cap) base[n] = make_uint2(0u, 0u); }
+};
+
 // One tick (docs/RULESET_R1.md, oracle/orx_r1_oracle.c:r1_tick). Returns the UpdateResult.
-__device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s, int c1, int c2, R1Counters& cnt)
+template <bool EV = false>
+__device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s, int c1, int c2, R1Counters& cnt, Sink<EV>& ev)
 {
     int dl[NM];                                    // packed delta on the key: dx + 256*dy, 0 = stays
     const int cd_pre0 = G.cd[0], cd_pre1 = G.cd[1];
@@ -83,9 +116,10 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
     for (int p = 0; p < 2; ++p) {
         int c = p == 0 ? c1 : c2;
         if (c == ORX_MOVE_HEAL) {
-            const int h = min(G.mana[p], G.max_mana[p] / 3);
+            const int h = min(G.mana[p], G.max_mana[p] / 3), before = G.hp[p];
             G.hp[p] = min(G.max_hp[p], G.hp[p] + h);
             G.mana[p] -= h;
+            if (h > 0) ev.emit(ORX_EV_HEALTH, p + 1, p + 1, ORX_R1_HEALTH_HEAL, G.hp[p] - before);
             c = ORX_MOVE_STAY;
         }
         const int ddx = (c == ORX_MOVE_RIGHT) - (c == ORX_MOVE_LEFT), ddy = (c == ORX_MOVE_DOWN) - (c == ORX_MOVE_UP);
@@ -146,15 +180,18 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
                 if (o < 2 && o_cd == 0) {                           // negated; the attacker is stunned
                     if (m == 0) { newcd0 = max(newcd0, 1); spend0 = true; }
                     if (m == 1) { newcd1 = max(newcd1, 1); spend1 = true; }
+                    ev.emit(ORX_EV_COMBAT, m + 1, o + 1, ORX_R1_HIT_NEGATED, 0);
                 } else {
                     taken[o] += amount;
                     if (m == 0) { spend0 = true; if (amount > 0) credit[o] |= 1; }
                     if (m == 1) { spend1 = true; if (amount > 0) credit[o] |= 2; }
+                    ev.emit(ORX_EV_COMBAT, m + 1, o + 1, ORX_R1_HIT_FULL, amount);
                 }
             } else if (tgt[o] == G.key[m]) {                        // mutual attack: half damage, cooldown
                 taken[o] += amount / 2;
                 if (m == 0) { newcd0 = 3; spend0 = true; if (amount / 2 > 0) credit[o] |= 1; }
                 if (m == 1) { newcd1 = 3; spend1 = true; if (amount / 2 > 0) credit[o] |= 2; }
+                ev.emit(ORX_EV_COMBAT, m + 1, o + 1, ORX_R1_HIT_HALF, amount / 2);
             }
         }
         if (has_occ) continue;
@@ -170,6 +207,7 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
                 taken[c] += amount;
                 if (m == 0) { spend0 = true; if (amount > 0) credit[c] |= 1; }
                 if (m == 1) { spend1 = true; if (amount > 0) credit[c] |= 2; }
+                ev.emit(ORX_EV_COMBAT, m + 1, c + 1, ORX_R1_HIT_CONTEST, amount);
             }
         }
         moves[m] = !contested;
@@ -182,56 +220,84 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
         if (G.key[m] == DEAD) continue;
         G.hp[m] -= taken[m];
         cnt.hits += taken[m] > 0;
-        if (moves[m]) G.key[m] = tgt[m];
+        if (moves[m]) { G.key[m] = tgt[m]; ev.emit(ORX_EV_MOVE, m + 1, kx(G.key[m]), ky(G.key[m]), kd(G.key[m])); }
     }
+    uint32_t descending = 0;                     // players that reached their staircase this tick
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         if (!moves[p]) continue;
-        if (kx(G.key[p]) == G.sx[p] && ky(G.key[p]) == G.sy[p]) {                 // descend
-            const int nd = kd(G.key[p]) + 1;
-            level_init(P, s, nd, G.sx[p], G.sy[p], G.lkey[p]);
-            G.key[p] = free_tile(P, G, s, DOM_TICK, SUB_DESCEND + 64u * p, (uint32_t)G.tick, nd, G.lkey[p], G.sx[p], G.sy[p], p);
-            ++cnt.descents;
-            continue;
-        }
+        if (kx(G.key[p]) == G.sx[p] && ky(G.key[p]) == G.sy[p]) { descending |= 1u << p; continue; }
 #pragma unroll
         for (int i = 0; i < ORX_R1_ITEMS; ++i)                                     // pickup
             if (G.ikey[i] == G.key[p] && G.n_items[p] < 4) {
                 if (G.ikind[i] == 0) G.damage[p] += 1; else if (G.ikind[i] == 1) G.armor[p] += 1; else { G.max_hp[p] += 2; G.hp[p] += 2; }
                 G.n_items[p] += 1;
                 G.ikey[i] = DEAD;
+                ev.emit(ORX_EV_PICKUP, p + 1, NM + i + 1, G.ikind[i], G.ikind[i] == 2 ? 2 : 0);
             }
     }
+    // Descents, player 1 before player 2 (the second search sees the first player's new tile), as ONE copy of the
+    // level draw and the free-tile search: games in which player 1 descends and games in which player 2 does run
+    // the same instructions together. Pickups above touch neither the movers' keys nor the levels, so taking them
+    // first changes nothing.
+    while (descending != 0u) {
+        const int p = __ffs((int)descending) - 1;
+        descending &= descending - 1u;
+        const int nd = kd(p == 0 ? G.key[0] : G.key[1]) + 1;
+        int nsx, nsy; uint32_t nlk;
+        level_init(P, s, nd, nsx, nsy, nlk);
+        const uint32_t nk = free_tile(P, G, s, DOM_TICK, SUB_DESCEND + 64u * (uint32_t)p, (uint32_t)G.tick, nd, nlk, nsx, nsy, p);
+        if (kd(p == 0 ? G.key[1] : G.key[0]) != nd) ev.emit(ORX_EV_DUNGEON, 0, nsx, nsy, nd);      // nobody stood there: the level is new
+        ev.emit(ORX_EV_DESCEND, p + 1, kx(nk), ky(nk), nd);
+        if (p == 0) { G.sx[0] = nsx; G.sy[0] = nsy; G.lkey[0] = nlk; G.key[0] = nk; }
+        else { G.sx[1] = nsx; G.sy[1] = nsy; G.lkey[1] = nlk; G.key[1] = nk; }
+        ++cnt.descents;
+    }
     // 6. enemy deaths in slot order: xp, level-ups, drops
+    uint32_t died = 0;                            // enemy slots that died this tick
 #pragma unroll
     for (int m = 2; m < NM; ++m) {
         if (G.key[m] == DEAD || G.hp[m] > 0) continue;
-        const uint32_t where = G.key[m];
-        G.key[m] = DEAD;
+        died |= 1u << m;
+        ev.emit(ORX_EV_DEATH, m + 1, 0, 0, 0);
 #pragma unroll
         for (int p = 0; p < 2; ++p)
             if ((credit[m] >> p) & 1) {
+                int gained = 0;
                 G.xp[p] += 1;
-                while (G.xp[p] >= 3) { G.xp[p] -= 3; G.level[p] += 1; G.hp[p] = G.max_hp[p]; G.mana[p] = G.max_mana[p]; }
+                while (G.xp[p] >= 3) { G.xp[p] -= 3; G.level[p] += 1; G.hp[p] = G.max_hp[p]; G.mana[p] = G.max_mana[p]; ++gained; }
+                ev.emit(ORX_EV_XP, p + 1, m + 1, gained, G.xp[p]);
             }
+    }
+    // Drops in slot order, ONE copy of the draw: a warp in which enemy 2 of one game and enemy 5 of another die runs it
+    // once for both (unrolled per slot it was eight Philox blocks in the instruction stream, each run for one lane).
+    // xp and level-ups above read nothing a drop writes, and a drop reads nothing they write.
+    for (uint32_t left = died; left != 0u; left &= left - 1u) {
+        const int m = __ffs((int)left) - 1;
+        const uint32_t where = pick(G.key, m);
         const uint4 b = draw_block(s, DOM_TICK, SUB_DROP + (uint32_t)((m - 2) >> 1), (uint32_t)G.tick);
         const uint32_t chance = ((m - 2) & 1) ? b.z : b.x, kind = (((m - 2) & 1) ? b.w : b.y) % 3u;
         if (chance < (1u << 30)) {
             bool placed = false;
 #pragma unroll
             for (int i = 0; i < ORX_R1_ITEMS; ++i)
-                if (!placed && G.ikey[i] == DEAD) { placed = true; G.ikey[i] = where; G.ikind[i] = (int)kind; }
+                if (!placed && G.ikey[i] == DEAD) {
+                    placed = true; G.ikey[i] = where; G.ikind[i] = (int)kind;
+                    ev.emit(ORX_EV_SPAWN, NM + i + 1, kx(where), ky(where), kd(where) | ((int)kind << 16));
+                }
         }
     }
+#pragma unroll
+    for (int m = 2; m < NM; ++m) if ((died >> m) & 1u) G.key[m] = DEAD;
     // 7. levels without a player vanish; spawn roll every fourth tick
     const uint32_t d0 = G.key[0] >> 16, d1 = G.key[1] >> 16;
 #pragma unroll
-    for (int m = 2; m < NM; ++m) if (G.key[m] != DEAD && (G.key[m] >> 16) != d0 && (G.key[m] >> 16) != d1) G.key[m] = DEAD;
+    for (int m = 2; m < NM; ++m) if (G.key[m] != DEAD && (G.key[m] >> 16) != d0 && (G.key[m] >> 16) != d1) { G.key[m] = DEAD; ev.emit(ORX_EV_DEATH, m + 1, 1, 0, 0); }
 #pragma unroll
-    for (int i = 0; i < ORX_R1_ITEMS; ++i) if (G.ikey[i] != DEAD && (G.ikey[i] >> 16) != d0 && (G.ikey[i] >> 16) != d1) G.ikey[i] = DEAD;
+    for (int i = 0; i < ORX_R1_ITEMS; ++i) if (G.ikey[i] != DEAD && (G.ikey[i] >> 16) != d0 && (G.ikey[i] >> 16) != d1) { G.ikey[i] = DEAD; ev.emit(ORX_EV_DEATH, NM + i + 1, 1, 0, 0); }
     if ((G.tick & 3) == 0) {
         const uint4 sb = draw_block(s, DOM_TICK, SUB_SPAWN, (uint32_t)G.tick);
-#pragma unroll
+#pragma unroll 1                  // one copy of the search for both levels
         for (int p = 0; p < 2; ++p) {
             if (p == 1 && d1 == d0) continue;
             if ((p == 0 ? sb.x : sb.y) >= (1u << 30)) continue;
@@ -240,11 +306,15 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
             for (int m = 2; m < NM; ++m) any_free |= G.key[m] == DEAD;
             if (!any_free) continue;
             const int d = (int)(p == 0 ? d0 : d1);
-            const uint32_t t = free_tile(P, G, s, DOM_TICK, SUB_SPAWN_TRY + 32u * p, (uint32_t)G.tick, d, G.lkey[p], G.sx[p], G.sy[p], -1);
+            const uint32_t t = free_tile(P, G, s, DOM_TICK, SUB_SPAWN_TRY + 32u * (uint32_t)p, (uint32_t)G.tick, d, p == 0 ? G.lkey[0] : G.lkey[1],
+                                         p == 0 ? G.sx[0] : G.sx[1], p == 0 ? G.sy[0] : G.sy[1], -1);
             bool placed = false;
 #pragma unroll
             for (int m = 2; m < NM; ++m)
-                if (!placed && G.key[m] == DEAD) { placed = true; G.key[m] = t; G.hp[m] = min(20, 2 + d / 2); }
+                if (!placed && G.key[m] == DEAD) {
+                    placed = true; G.key[m] = t; G.hp[m] = min(20, 2 + d / 2);
+                    ev.emit(ORX_EV_SPAWN, m + 1, kx(t), ky(t), d | (G.hp[m] << 16));
+                }
         }
     }
     // 8. mana, 9. separation, 10. cooldowns
@@ -252,12 +322,15 @@ __device__ __forceinline__ int tick(const R1Params& P, Game& G, const Stream& s,
     if (d0 != d1) {
         G.sep += 1;
         if (d0 < d1) G.hp[0] -= G.sep / 16; else G.hp[1] -= G.sep / 16;
+        if (G.sep / 16 > 0) ev.emit(ORX_EV_HEALTH, d0 < d1 ? 1 : 2, d0 < d1 ? 1 : 2, ORX_R1_HEALTH_SEPARATION, -(G.sep / 16));
     } else G.sep = 0;
     G.cd[0] = cd_pre0 > 0 ? cd_pre0 - 1 : newcd0;
     G.cd[1] = cd_pre1 > 0 ? cd_pre1 - 1 : newcd1;
     const int tick_pre = G.tick;
     G.tick += 1;
     const bool dead0 = G.hp[0] <= 0, dead1 = G.hp[1] <= 0;
+    if (dead0) ev.emit(ORX_EV_DEATH, 1, 0, 0, 0);
+    if (dead1) ev.emit(ORX_EV_DEATH, 2, 0, 0, 0);
     int res = ORX_RESULT_IN_PROGRESS;
     if (P.max_ticks != 0 && G.tick >= P.max_ticks) res = ORX_RESULT_TIE;
     if (dead1) res = ORX_RESULT_PLAYER1_WIN;
@@ -364,8 +437,16 @@ __device__ __forceinline__ void store_game(const R1Params& P, unsigned int game,
 #ifndef ORX_R1T_THREADS
 #define ORX_R1T_THREADS 128
 #endif
+// CTAs per SM the register allocation is held to. Five (96 registers, 100 bytes of spills in the rare paths) for the
+// kernels whose launches overlap or whose threads live long -- 20 instead of 16 warps per SM hide more of the
+// fixed-latency dependencies that bound this tick: 10.7 against 11.0 us per 65,536-game step in throughput mode, the
+// fused rollout 5.7e9 against 4.3e9 game-ticks/s -- four (as many registers as it likes, up to 128) for a tick launched
+// alone, which was 4 % slower with five (profiles/r02_r1_rare_paths.log).
 #ifndef ORX_R1T_MINBLOCKS
-#define ORX_R1T_MINBLOCKS 1
+#define ORX_R1T_MINBLOCKS 5
+#endif
+#ifndef ORX_R1T_MINBLOCKS_ALONE
+#define ORX_R1T_MINBLOCKS_ALONE 4
 #endif
 constexpr int kThreads = ORX_R1T_THREADS;
 
@@ -374,9 +455,11 @@ constexpr int kThreads = ORX_R1T_THREADS;
 // before it lets dependents launch (programmatic dependent launch), touches the state once the block's serving word
 // equals the ticket, releases serving = ticket + 1 at gpu scope after the barrier that follows its last store, and
 // waits for the grid dependency last, so that the completion of this grid implies that of every earlier one.
-template <bool FLAGGED>
-__global__ void __launch_bounds__(kThreads, ORX_R1T_MINBLOCKS)
-k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result, unsigned int* __restrict__ flags)
+// EV: also write the tick's replication log, max_events record slots per game (orx_r1_step_events).
+template <bool FLAGGED, bool EV = false>
+__global__ void __launch_bounds__(kThreads, FLAGGED ? ORX_R1T_MINBLOCKS : ORX_R1T_MINBLOCKS_ALONE)
+k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result, unsigned int* __restrict__ flags,
+       uint2* __restrict__ events, int max_events)
 {
     __shared__ unsigned int s_ticket;
     if (FLAGGED) {
@@ -398,12 +481,15 @@ k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, u
         uint32_t mvw, status;
         asm volatile("ld.global.u16 %0, [%1];" : "=r"(mvw) : "l"(moves + game));
         asm volatile("ld.global.u8 %0, [%1];" : "=r"(status) : "l"(P.status + game));
+        Sink<EV> ev{EV ? events + (size_t)game * (size_t)max_events : nullptr, 0, max_events};
         if (status != ORX_RESULT_IN_PROGRESS) {
             result[game] = (uint8_t)status;
+            ev.finish();                                   // a frozen game: the terminator only
         } else {
             Stream s = make_stream(P, game, G.episode);
             R1Counters cnt{};
-            int res = tick(P, G, s, (int)(mvw & 255u), (int)(mvw >> 8), cnt);
+            int res = tick<EV>(P, G, s, (int)(mvw & 255u), (int)(mvw >> 8), cnt, ev);
+            ev.finish();
             result[game] = (uint8_t)res;
             if (res != ORX_RESULT_IN_PROGRESS && P.auto_reset) {
                 G.episode += 1;
@@ -439,7 +525,8 @@ k_rollout(const __grid_constant__ R1Params P, int n_ticks, unsigned long long* _
             Stream s = make_stream(P, game, G.episode);
             for (int t = 0; t < n_ticks; ++t) {
                 const uint4 b = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)G.tick);
-                const int res = tick(P, G, s, 1 + (int)bounded(b.x, 6u), 1 + (int)bounded(b.y, 6u), cnt);
+                Sink<false> ev{nullptr, 0, 0};
+                const int res = tick<false>(P, G, s, 1 + (int)bounded(b.x, 6u), 1 + (int)bounded(b.y, 6u), cnt, ev);
                 ++cnt.ticks;
                 cnt.p1 += res == ORX_RESULT_PLAYER1_WIN; cnt.p2 += res == ORX_RESULT_PLAYER2_WIN; cnt.ties += res == ORX_RESULT_TIE;
                 if (res != ORX_RESULT_IN_PROGRESS) {
@@ -460,6 +547,58 @@ k_rollout(const __grid_constant__ R1Params P, int n_ticks, unsigned long long* _
         __syncthreads();
         if (threadIdx.x < ORX_STAT_COUNT && s_cnt[threadIdx.x] != 0)
             atomicAdd(&stats[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    }
+}
+
+// orx_r1_replay: n_ticks ticks with both players' commands queued in advance (uint16[n_ticks][n] = p1 | p2 << 8),
+// state in registers in between; results uint8[n_ticks][n]. Same outcome as n_ticks k_step launches.
+__global__ void __launch_bounds__(kThreads, ORX_R1T_MINBLOCKS)
+k_replay(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ results, int n_ticks)
+{
+    const unsigned int game = blockIdx.x * kThreads + threadIdx.x;
+    if (game >= P.n) return;
+    int status = P.status[game];
+    Game G;
+    load_game(P, game, G);
+    Stream s = make_stream(P, game, G.episode);
+    R1Counters cnt{};
+    Sink<false> ev{nullptr, 0, 0};
+    bool touched = false;
+    for (int t = 0; t < n_ticks; ++t) {
+        const size_t at = (size_t)t * P.n + game;
+        if (status != ORX_RESULT_IN_PROGRESS) { results[at] = (uint8_t)status; continue; }       // frozen until reset
+        const uint32_t mvw = moves[at];
+        const int res = tick<false>(P, G, s, (int)(mvw & 255u), (int)(mvw >> 8), cnt, ev);
+        results[at] = (uint8_t)res;
+        touched = true;
+        if (res != ORX_RESULT_IN_PROGRESS) {
+            if (P.auto_reset) { G.episode += 1; s.episode = G.episode; setup_game(P, G, s); }
+            else status = res;
+        }
+    }
+    if (touched) store_game(P, game, G, status);
+}
+
+// orx_r1_bot_moves: RandomBot over the six R1 commands (words 0 / 1 of the tick's main block, the draws of the fused
+// rollout), StaircaseBot towards the staircase of the player's own level (staircasebot.py:9-20).
+__global__ void __launch_bounds__(256)
+k_bot_moves(const __grid_constant__ R1Params P, int bot1, int bot2, uint8_t* __restrict__ moves)
+{
+    const unsigned int game = blockIdx.x * 256u + threadIdx.x;
+    if (game >= P.n) return;
+    const uint2 loc = ldg64(P.ent_loc + (size_t)game * 16);          // lanes 0, 1: x | y << 8 | ...
+    const uint32_t sw = ldg32(P.lvl_stairs + game);
+    Stream s = make_stream(P, game, P.episode[game]);
+    const uint4 b = draw_block(s, DOM_TICK, SUB_MAIN, (uint32_t)P.tick[game]);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int kind = p == 0 ? bot1 : bot2;
+        const uint32_t l = p == 0 ? loc.x : loc.y;
+        if (kind == ORX_BOT_RANDOM) moves[2 * (size_t)game + p] = (uint8_t)(1u + bounded(p == 0 ? b.x : b.y, 6u));
+        else if (kind == ORX_BOT_STAIRCASE) {
+            const int ddx = (int)((sw >> (16 * p)) & 255u) - (int)(l & 255u), ddy = (int)((sw >> (16 * p + 8)) & 255u) - (int)((l >> 8) & 255u);
+            moves[2 * (size_t)game + p] = (uint8_t)(abs(ddx) > abs(ddy) ? (ddx > 0 ? ORX_MOVE_RIGHT : ORX_MOVE_LEFT) : (ddy > 0 ? ORX_MOVE_DOWN : ORX_MOVE_UP));
+        }
     }
 }
 

@@ -70,6 +70,58 @@ class R1GameState:
         _lib.check(rc, 'orx_r1_step')
         return result
 
+    def update_events(self, moves: torch.Tensor, out: typing.Optional[torch.Tensor] = None,
+                      events: typing.Optional[torch.Tensor] = None, max_events: int = _abi.R1_MAX_EVENTS):
+        """One tick plus its replication log (orx_r1_step_events): returns (result uint8[N], records int32[N, max_events, 2]).
+        A game's list ends at the first record of kind 0; slots behind it keep whatever the buffer held.
+        ``logic.updates.decode_r1_events`` turns one game's records into GameStateUpdate objects."""
+        if tuple(moves.shape) != (self.n, 2) or moves.dtype != torch.uint8 or not moves.is_cuda:
+            raise ValueError(f'moves must be a CUDA uint8 tensor of shape ({self.n}, 2)')
+        result = out if out is not None else torch.empty((self.n,), dtype=torch.uint8, device=self.device)
+        if events is None:
+            events = torch.zeros((self.n, int(max_events), 2), dtype=torch.int32, device=self.device)
+        if events.dtype != torch.int32 or events.dim() != 3 or events.shape[0] != self.n or events.shape[2] != 2 or not events.is_contiguous():
+            raise ValueError(f'events must be a contiguous CUDA int32 tensor of shape ({self.n}, max_events, 2)')
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().orx_r1_step_events(C.byref(self.cfg), C.byref(self._st), moves.contiguous().data_ptr(),
+                                               result.data_ptr(), events.data_ptr(), int(events.shape[1]), self.n,
+                                               self.game_id_base, self._stream())
+        _lib.check(rc, 'orx_r1_step_events')
+        return result, events
+
+    def bot_moves(self, bot1: int, bot2: int, out: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Commands of scripted players (BOT_RANDOM over the six R1 commands, BOT_STAIRCASE; BOT_NONE leaves the byte)."""
+        moves = out if out is not None else torch.full((self.n, 2), 5, dtype=torch.uint8, device=self.device)   # Move.Stay
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().orx_r1_bot_moves(C.byref(self.cfg), C.byref(self._st), int(bot1), int(bot2), moves.data_ptr(),
+                                             self.n, self.game_id_base, self._stream())
+        _lib.check(rc, 'orx_r1_bot_moves')
+        return moves
+
+    def replay(self, moves: torch.Tensor, out: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """T ticks with queued commands (uint8[T,N,2]) in one launch, state in registers in between; uint8[T,N] results."""
+        if moves.dim() != 3 or tuple(moves.shape[1:]) != (self.n, 2) or moves.dtype != torch.uint8 or not moves.is_cuda:
+            raise ValueError(f'moves must be a CUDA uint8 tensor of shape (T, {self.n}, 2)')
+        t = int(moves.shape[0])
+        results = out if out is not None else torch.empty((t, self.n), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().orx_r1_replay(C.byref(self.cfg), C.byref(self._st), moves.contiguous().data_ptr(),
+                                          results.data_ptr(), t, self.n, self.game_id_base, self._stream())
+        _lib.check(rc, 'orx_r1_replay')
+        return results
+
+    def update_host(self, host_moves: torch.Tensor, host_result: torch.Tensor) -> torch.Tensor:
+        """One tick told and answered through PINNED host tensors (uint8[N,2] in, uint8[N] out); returns after the
+        stream has been synchronised, i.e. ``host_result`` is readable."""
+        for t, shape in ((host_moves, (self.n, 2)), (host_result, (self.n,))):
+            if t.is_cuda or not t.is_pinned() or t.dtype != torch.uint8 or tuple(t.shape) != shape or not t.is_contiguous():
+                raise ValueError('host buffers must be pinned contiguous uint8 CPU tensors of shape (N, 2) / (N,)')
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().orx_r1_step_host_sync(C.byref(self.cfg), C.byref(self._st), host_moves.data_ptr(),
+                                                  host_result.data_ptr(), self.n, self.game_id_base, self._stream())
+        _lib.check(rc, 'orx_r1_step_host_sync')
+        return host_result
+
     def rollout(self, n_ticks: int, stats: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
         """n_ticks fused ticks, both players uniform over the six commands."""
         if stats is None:

@@ -38,6 +38,10 @@ _PROTOS = {
                                  C.c_void_p, C.c_int64, C.c_uint64]),
     'oro_r1_observe': (C.c_int, [C.POINTER(_abi.OrxR1Config), C.POINTER(_abi.OrxR1State), C.c_void_p, C.c_int,
                                  C.c_int64]),
+    'oro_r1_step_events': (C.c_int, [C.POINTER(_abi.OrxR1Config), C.POINTER(_abi.OrxR1State), C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_uint64]),
+    'oro_r1_bot_moves': (C.c_int, [C.POINTER(_abi.OrxR1Config), C.POINTER(_abi.OrxR1State), C.c_int, C.c_int,
+                                   C.c_void_p, C.c_int64, C.c_uint64]),
 }
 
 
@@ -221,6 +225,23 @@ class R1Oracle:
         lib().oro_r1_step(C.byref(self.c_cfg), C.byref(st), moves.ctypes.data, result.ctypes.data, self.n,
                           self.game_id_base)
         return result
+
+    def step_events(self, moves, max_events=_abi.R1_MAX_EVENTS):
+        """The tick and its replication log: (result uint8[n], records int32[n, max_events, 2] as the kernel writes them;
+        slots behind a game's terminator are zero here)."""
+        moves = np.ascontiguousarray(moves, np.uint8).reshape(self.n, 2)
+        result = np.zeros(self.n, np.uint8)
+        events = np.zeros((self.n, max_events, 2), np.int32)
+        st = self.state.c_struct()
+        lib().oro_r1_step_events(C.byref(self.c_cfg), C.byref(st), moves.ctypes.data, result.ctypes.data,
+                                 events.ctypes.data, max_events, self.n, self.game_id_base)
+        return result, events
+
+    def bot_moves(self, bot1, bot2, moves=None):
+        moves = np.zeros((self.n, 2), np.uint8) if moves is None else moves
+        st = self.state.c_struct()
+        lib().oro_r1_bot_moves(C.byref(self.c_cfg), C.byref(st), bot1, bot2, moves.ctypes.data, self.n, self.game_id_base)
+        return moves
 
     def observe(self, radius=4):
         obs = np.zeros((self.n, 2, _abi.R1_OBS_LEN), np.int16)

@@ -52,7 +52,20 @@ typedef struct {
     uint32_t key[2];
     int sep, tick, status;
     unsigned long long* stats;
+    OrxEvent* ev;            /* this game's record slots for the tick (docs/RULESET_R1.md "Replication log"), or NULL */
+    int n_ev, cap_ev;
 } G;
+
+/* one record; beyond the capacity records are dropped (ORX_R1_MAX_EVENTS slots never overflow) */
+static void emit(G* g, int kind, int iden, int a, int b, int value)
+{
+    if (!g->ev) return;
+    if (g->n_ev < g->cap_ev) {
+        OrxEvent* e = &g->ev[g->n_ev];
+        e->kind = (uint8_t)kind; e->iden = (uint8_t)iden; e->a = (uint8_t)a; e->b = (uint8_t)b; e->depth = value;
+    }
+    g->n_ev++;
+}
 
 static uint32_t mix(uint32_t x, uint32_t y, uint32_t key)
 {
@@ -141,9 +154,10 @@ static int r1_tick(G* g, int c1, int c2)
         Ent* e = &g->e[p];
         int c = cmd[p];
         if (c == ORX_MOVE_HEAL) {
-            int h = imin(e->aux, g->p[p].max_mana / 3);
+            int h = imin(e->aux, g->p[p].max_mana / 3), before = e->hp;
             e->hp = imin(g->p[p].max_hp, e->hp + h);
             e->aux -= h;
+            if (h > 0) emit(g, ORX_EV_HEALTH, p + 1, p + 1, ORX_R1_HEALTH_HEAL, e->hp - before);
             c = ORX_MOVE_STAY;
         }
         int ddx = (c == ORX_MOVE_RIGHT) - (c == ORX_MOVE_LEFT), ddy = (c == ORX_MOVE_DOWN) - (c == ORX_MOVE_UP);
@@ -186,11 +200,12 @@ static int r1_tick(G* g, int c1, int c2)
             if (m >= 2 && o >= 2) continue;
             int amount = attack_amount(g, m, o);
             if (!(dx[o] || dy[o])) {
-                if (o < 2 && cd_pre[o] == 0) { if (m < 2) { newcd[m] = imax(newcd[m], 1); spend[m] = 1; } }
-                else { taken[o] += amount; if (m < 2) { spend[m] = 1; if (o >= 2 && amount > 0) credit[o][m] = 1; } }
+                if (o < 2 && cd_pre[o] == 0) { if (m < 2) { newcd[m] = imax(newcd[m], 1); spend[m] = 1; } emit(g, ORX_EV_COMBAT, m + 1, o + 1, ORX_R1_HIT_NEGATED, 0); }
+                else { taken[o] += amount; if (m < 2) { spend[m] = 1; if (o >= 2 && amount > 0) credit[o][m] = 1; } emit(g, ORX_EV_COMBAT, m + 1, o + 1, ORX_R1_HIT_FULL, amount); }
             } else if (g->e[o].x + dx[o] == e->x && g->e[o].y + dy[o] == e->y) {
                 taken[o] += amount / 2;
                 if (m < 2) { newcd[m] = 3; spend[m] = 1; if (o >= 2 && amount / 2 > 0) credit[o][m] = 1; }
+                emit(g, ORX_EV_COMBAT, m + 1, o + 1, ORX_R1_HIT_HALF, amount / 2);
             }
             continue;
         }
@@ -208,6 +223,7 @@ static int r1_tick(G* g, int c1, int c2)
             int amount = attack_amount(g, m, victim);
             taken[victim] += amount;
             if (m < 2) { spend[m] = 1; if (victim >= 2 && amount > 0) credit[victim][m] = 1; }
+            emit(g, ORX_EV_COMBAT, m + 1, victim + 1, ORX_R1_HIT_CONTEST, amount);
         }
     }
     /* 5. apply */
@@ -215,20 +231,15 @@ static int r1_tick(G* g, int c1, int c2)
     for (int m = 0; m < NM; ++m) if (g->e[m].alive) {
         g->e[m].hp -= taken[m];
         if (taken[m] > 0 && g->stats) g->stats[ORX_STAT_HITS]++;
-        if (moves[m]) { g->e[m].x += dx[m]; g->e[m].y += dy[m]; }
+        if (moves[m]) { g->e[m].x += dx[m]; g->e[m].y += dy[m]; emit(g, ORX_EV_MOVE, m + 1, g->e[m].x, g->e[m].y, g->e[m].depth); }
     }
+    /* pickups of both players, then descents of both players: neither reads what the other writes, and the
+     * replication log lists them in this order */
+    int descends[2] = { 0, 0 };
     for (int p = 0; p < 2; ++p) {
         Ent* e = &g->e[p];
         if (!moves[p]) continue;
-        if (e->x == g->sx[p] && e->y == g->sy[p]) {          /* descend */
-            int nd = e->depth + 1, x, y;
-            e->alive = 0;                                   /* not an obstacle for its own spawn search */
-            level_init(g, nd, &g->sx[p], &g->sy[p], &g->key[p]);
-            free_tile(g, DOM_TICK, SUB_DESCEND + 64 * p, (uint32_t)g->tick, nd, g->key[p], g->sx[p], g->sy[p], &x, &y);
-            e->alive = 1; e->depth = nd; e->x = x; e->y = y;
-            if (g->stats) g->stats[ORX_STAT_DESCENTS]++;
-            continue;
-        }
+        if (e->x == g->sx[p] && e->y == g->sy[p]) { descends[p] = 1; continue; }
         for (int i = NM; i < NM + ORX_R1_ITEMS; ++i) {       /* pickup */
             Ent* it = &g->e[i];
             if (it->alive && it->depth == e->depth && it->x == e->x && it->y == e->y && g->p[p].n_items < 4) {
@@ -237,28 +248,55 @@ static int r1_tick(G* g, int c1, int c2)
                 else { g->p[p].max_hp += 2; e->hp += 2; }
                 g->p[p].n_items += 1;
                 it->alive = 0;
+                emit(g, ORX_EV_PICKUP, p + 1, i + 1, it->aux, it->aux == 2 ? 2 : 0);
             }
         }
     }
+    for (int p = 0; p < 2; ++p) {
+        Ent* e = &g->e[p];
+        if (!descends[p]) continue;
+        int nd = e->depth + 1, x, y;
+        e->alive = 0;                                       /* not an obstacle for its own spawn search */
+        level_init(g, nd, &g->sx[p], &g->sy[p], &g->key[p]);
+        free_tile(g, DOM_TICK, SUB_DESCEND + 64 * p, (uint32_t)g->tick, nd, g->key[p], g->sx[p], g->sy[p], &x, &y);
+        e->alive = 1; e->depth = nd; e->x = x; e->y = y;
+        if (g->e[1 - p].depth != nd) emit(g, ORX_EV_DUNGEON, 0, g->sx[p], g->sy[p], nd);   /* nobody stood there: the level is new */
+        emit(g, ORX_EV_DESCEND, p + 1, x, y, nd);
+        if (g->stats) g->stats[ORX_STAT_DESCENTS]++;
+    }
     /* 6. enemy deaths, xp, drops */
+    int died[NM] = { 0 };
     for (int m = 2; m < NM; ++m) {
         Ent* e = &g->e[m];
         if (!e->alive || e->hp > 0) continue;
+        died[m] = 1;
         e->alive = 0;
+        emit(g, ORX_EV_DEATH, m + 1, 0, 0, 0);
         for (int p = 0; p < 2; ++p) if (credit[m][p]) {
+            int gained = 0;
             g->p[p].xp += 1;
-            while (g->p[p].xp >= 3) { g->p[p].xp -= 3; g->p[p].level += 1; g->e[p].hp = g->p[p].max_hp; g->e[p].aux = g->p[p].max_mana; }
+            while (g->p[p].xp >= 3) { g->p[p].xp -= 3; g->p[p].level += 1; g->e[p].hp = g->p[p].max_hp; g->e[p].aux = g->p[p].max_mana; ++gained; }
+            emit(g, ORX_EV_XP, p + 1, m + 1, gained, g->p[p].xp);
         }
+    }
+    /* drops in slot order, after every death of the tick has been recorded */
+    for (int m = 2; m < NM; ++m) {
+        Ent* e = &g->e[m];
+        if (!died[m]) continue;
         uint32_t w[4];
         draw_block(&g->rng, DOM_TICK, SUB_DROP + (m - 2) / 2, (uint32_t)g->tick, w);
         uint32_t chance = w[2 * ((m - 2) & 1)], kind = w[2 * ((m - 2) & 1) + 1] % 3u;
         if (chance < (1u << 30))
             for (int i = NM; i < NM + ORX_R1_ITEMS; ++i)
-                if (!g->e[i].alive) { Ent* it = &g->e[i]; it->alive = 1; it->depth = e->depth; it->x = e->x; it->y = e->y; it->aux = (int)kind; it->hp = 0; break; }
+                if (!g->e[i].alive) {
+                    Ent* it = &g->e[i]; it->alive = 1; it->depth = e->depth; it->x = e->x; it->y = e->y; it->aux = (int)kind; it->hp = 0;
+                    emit(g, ORX_EV_SPAWN, i + 1, it->x, it->y, it->depth | ((int)kind << 16));
+                    break;
+                }
     }
     /* 7. vanish + spawn */
     for (int l = 2; l < NM + ORX_R1_ITEMS; ++l)
-        if (g->e[l].alive && g->e[l].depth != g->e[0].depth && g->e[l].depth != g->e[1].depth) g->e[l].alive = 0;
+        if (g->e[l].alive && g->e[l].depth != g->e[0].depth && g->e[l].depth != g->e[1].depth) { g->e[l].alive = 0; emit(g, ORX_EV_DEATH, l + 1, 1, 0, 0); }
     uint32_t sw[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0 };
     if (g->tick % 4 == 0) draw_block(&g->rng, DOM_TICK, SUB_SPAWN, (uint32_t)g->tick, sw);
     for (int p = 0; p < 2; ++p) {
@@ -271,6 +309,7 @@ static int r1_tick(G* g, int c1, int c2)
         free_tile(g, DOM_TICK, SUB_SPAWN_TRY + 32 * p, (uint32_t)g->tick, d, g->key[p], g->sx[p], g->sy[p], &x, &y);
         Ent* e = &g->e[slot];
         e->alive = 1; e->depth = d; e->x = x; e->y = y; e->hp = imin(20, 2 + d / 2); e->aux = 0;
+        emit(g, ORX_EV_SPAWN, slot + 1, x, y, d | (e->hp << 16));
     }
     /* 8. mana, 9. separation, 10. cooldowns */
     if (g->tick % 4 == 0) for (int p = 0; p < 2; ++p) g->e[p].aux = imin(g->p[p].max_mana, g->e[p].aux + 1);
@@ -278,12 +317,15 @@ static int r1_tick(G* g, int c1, int c2)
         g->sep += 1;
         int behind = g->e[0].depth < g->e[1].depth ? 0 : 1;
         g->e[behind].hp -= g->sep / 16;
+        if (g->sep / 16 > 0) emit(g, ORX_EV_HEALTH, behind + 1, behind + 1, ORX_R1_HEALTH_SEPARATION, -(g->sep / 16));
     } else g->sep = 0;
     for (int p = 0; p < 2; ++p) g->p[p].cd = cd_pre[p] > 0 ? cd_pre[p] - 1 : newcd[p];
     uint32_t w[4];
     draw_block(&g->rng, DOM_TICK, SUB_MAIN, (uint32_t)g->tick, w);
     g->tick += 1;
     int d0 = g->e[0].hp <= 0, d1 = g->e[1].hp <= 0;
+    if (d0) emit(g, ORX_EV_DEATH, 1, 0, 0, 0);
+    if (d1) emit(g, ORX_EV_DEATH, 2, 0, 0, 0);
     if (d0 && d1) return (w[2] >> 31) ? ORX_RESULT_PLAYER1_WIN : ORX_RESULT_PLAYER2_WIN;
     if (d0) return ORX_RESULT_PLAYER2_WIN;
     if (d1) return ORX_RESULT_PLAYER1_WIN;
@@ -362,6 +404,44 @@ int oro_r1_step(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* mov
         int res = r1_tick(&g, moves[2 * i], moves[2 * i + 1]);
         finish(&g, res, &result[i]);
         store_game(&g, st, i);
+    }
+    return 0;
+}
+/* The tick with its replication log: events[i * max_events + k], terminated by kind == ORX_EV_NONE when fewer than
+ * max_events records were written (slots behind the terminator are left alone); a frozen game writes the terminator only. */
+int oro_r1_step_events(const OrxR1Config* cfg, const OrxR1State* st, const uint8_t* moves, uint8_t* result, OrxEvent* events,
+                       int max_events, int64_t n, uint64_t base)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        G g; load_game(&g, cfg, st, i, base + (uint64_t)i);
+        g.ev = events + i * max_events; g.cap_ev = max_events; g.n_ev = 0;
+        if (g.status != ORX_RESULT_IN_PROGRESS) { result[i] = (uint8_t)g.status; }
+        else {
+            int res = r1_tick(&g, moves[2 * i], moves[2 * i + 1]);
+            finish(&g, res, &result[i]);
+            store_game(&g, st, i);
+        }
+        if (g.n_ev < max_events) memset(&g.ev[g.n_ev], 0, sizeof(OrxEvent));
+    }
+    return 0;
+}
+/* Scripted players for R1 (docs/RULESET_R1.md "Bots"): RandomBot draws uniformly from the six commands with the words the
+ * fused rollout uses (TICK sub 0, word p), StaircaseBot walks towards the staircase of its own level
+ * (optimax_rogue_bots/staircasebot.py:9-20). ORX_BOT_NONE leaves the player's byte untouched. */
+int oro_r1_bot_moves(const OrxR1Config* cfg, const OrxR1State* st, int bot1, int bot2, uint8_t* moves, int64_t n, uint64_t base)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        G g; load_game(&g, cfg, st, i, base + (uint64_t)i);
+        uint32_t w[4];
+        draw_block(&g.rng, DOM_TICK, SUB_MAIN, (uint32_t)g.tick, w);
+        for (int p = 0; p < 2; ++p) {
+            int kind = p == 0 ? bot1 : bot2;
+            if (kind == ORX_BOT_RANDOM) moves[2 * i + p] = (uint8_t)(1 + bounded(w[p], 6));
+            else if (kind == ORX_BOT_STAIRCASE) {
+                int ddx = g.sx[p] - g.e[p].x, ddy = g.sy[p] - g.e[p].y;
+                moves[2 * i + p] = (uint8_t)(abs(ddx) > abs(ddy) ? (ddx > 0 ? ORX_MOVE_RIGHT : ORX_MOVE_LEFT) : (ddy > 0 ? ORX_MOVE_DOWN : ORX_MOVE_UP));
+            }
+        }
     }
     return 0;
 }

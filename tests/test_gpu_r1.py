@@ -147,3 +147,91 @@ def test_r1_unsynchronised_ticks_in_a_graph():
             want = np.stack([orc.step(m[t]) for t in range(per)])
         assert np.array_equal(res.cpu().numpy(), want)
         assert_equal(gs, orc, 'after the replayed graph')
+
+
+def _trim(ev):
+    """Records up to each game's terminator; slots behind it are not written by the kernel."""
+    ev = ev.copy()
+    kind = ev[:, :, 0] & 0xFF
+    ended = np.cumsum(kind == 0, axis=1) > 0
+    ev[ended] = 0
+    return ev
+
+
+@pytest.mark.parametrize('w,h,density,cap', [(60, 10, 26, _abi.R1_MAX_EVENTS), (12, 8, 10, _abi.R1_MAX_EVENTS), (14, 9, 20, 5)])
+def test_r1_replication_log_matches_oracle(r1_kernel_flavour, w, h, density, cap):
+    """orx_r1_step_events: every record of every tick, in emission order, equals the oracle's (and the state with it);
+    the buffer is poisoned first, so slots behind a game's terminator prove to be left alone."""
+    if r1_kernel_flavour == 'half_warp':
+        gs = R1GameState(256, path_flags=_abi.R1_PATH_HALFWARP).reset()
+        with pytest.raises(RuntimeError):
+            gs.update_events(torch.full((256, 2), 5, dtype=torch.uint8, device='cuda'))
+        return
+    n = 3000
+    gs, orc = pair(n, width=w, height=h, wall_density=density, seed=21, max_ticks=120, auto_reset=True)
+    rng = np.random.default_rng(w + cap)
+    ev = torch.empty((n, cap, 2), dtype=torch.int32, device='cuda')
+    kinds = set()
+    for t in range(300):
+        mv = rng.integers(0, 8, size=(n, 2), dtype=np.uint8)
+        if t % 3:
+            orc.bot_moves(_abi.BOT_STAIRCASE, _abi.BOT_RANDOM, mv)
+        ro, eo = orc.step_events(mv, max_events=cap)
+        ev.fill_(0x5A5A5A5A)
+        rg, _ = gs.update_events(torch.from_numpy(mv).cuda(), events=ev)
+        got = ev.cpu().numpy()
+        assert np.array_equal(rg.cpu().numpy(), ro), f'tick {t}: results differ'
+        assert np.array_equal(_trim(got), _trim(eo)), f'tick {t}: records differ'
+        kind = got[:, :, 0] & 0xFF
+        behind = np.cumsum(kind == 0, axis=1) > 1                  # strictly behind the terminator
+        assert (got[behind] == 0x5A5A5A5A).all()
+        kinds |= set(np.unique(_trim(got)[:, :, 0] & 0xFF).tolist())
+        if t % 25 == 0:
+            assert_equal(gs, orc, f'tick {t}')
+    assert_equal(gs, orc, 'end')
+    if cap == _abi.R1_MAX_EVENTS:
+        assert kinds >= {_abi.EV_MOVE, _abi.EV_COMBAT, _abi.EV_DEATH, _abi.EV_SPAWN, _abi.EV_HEALTH, _abi.EV_DESCEND}
+
+
+def test_r1_bot_moves_match_oracle():
+    n = 5000
+    gs, orc = pair(n, base=1 << 35, seed=8, max_ticks=90, auto_reset=True)
+    for t in range(120):
+        b1, b2 = [(1, 1), (2, 1), (1, 2), (2, 2), (0, 2), (1, 0)][t % 6]
+        mo = orc.bot_moves(b1, b2, np.full((n, 2), 4, np.uint8))
+        mg = gs.bot_moves(b1, b2, out=torch.full((n, 2), 4, dtype=torch.uint8, device='cuda'))
+        assert np.array_equal(mg.cpu().numpy(), mo), f'tick {t}'
+        orc.step(mo)
+        gs.update(mg)
+    assert_equal(gs, orc, 'end')
+
+
+@pytest.mark.parametrize('auto_reset', [True, False])
+def test_r1_replay_equals_step_loop(auto_reset):
+    """orx_r1_replay (T queued ticks, state in registers) == T orx_r1_step calls == the oracle."""
+    n, T = 3000, 90
+    gs, orc = pair(n, width=10, height=8, wall_density=10, seed=13, max_ticks=50, auto_reset=auto_reset)
+    rng = np.random.default_rng(4)
+    mv = rng.integers(0, 8, size=(T, n, 2), dtype=np.uint8)
+    want = np.stack([orc.step(mv[t]) for t in range(T)])
+    got = gs.replay(torch.from_numpy(mv).cuda())
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert_equal(gs, orc, 'after replay')
+
+
+def test_r1_host_buffers():
+    """orx_r1_step_host_sync: pinned host commands in, pinned host results out, readable when the call returns."""
+    n = 4096 + 77
+    gs, orc = pair(n, seed=17, max_ticks=70, auto_reset=True)
+    rng = np.random.default_rng(6)
+    hm = torch.empty((n, 2), dtype=torch.uint8).pin_memory()
+    hr = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    for t in range(60):
+        mv = rng.integers(1, 7, size=(n, 2), dtype=np.uint8)
+        hm.copy_(torch.from_numpy(mv))
+        hr.fill_(0)
+        gs.update_host(hm, hr)                 # no synchronize here: the call returns after the stream has drained
+        assert np.array_equal(hr.numpy(), orc.step(mv)), f'tick {t}'
+    assert_equal(gs, orc, 'end')
+    with pytest.raises(ValueError):
+        gs.update_host(torch.empty((n, 2), dtype=torch.uint8), hr)       # not pinned

@@ -203,3 +203,107 @@ def test_observation_layout_and_ladder_visibility():
             x = 3 + col - 3
             wall = x <= 0 or y <= 0 or x >= 11 or y >= 7
             assert (bits >> (row * 7 + col)) & 1 == int(wall), (row, col)
+
+
+# ---------------------------------------------------------------- replication log (include/orx.h, orx_r1_step_events)
+def _shadow_from_state(s, g):
+    """iden -> [x, y, depth, hp-or-kind] of every living lane of game g, plus the players' max health."""
+    sh = {}
+    for lane in range(14):
+        loc = int(s.ent_loc[g, lane])
+        if (loc >> 16) & 1:
+            val = int(np.int16(int(s.ent_stat[g, lane]) & 0xFFFF)) if lane < 10 else (loc >> 17) & 3
+            sh[lane + 1] = [loc & 255, (loc >> 8) & 255, int(s.ent_depth[g, lane]), val]
+    max_hp = [int(np.int16(int(s.pl_a[g, p]) & 0xFFFF)) for p in range(2)]
+    return sh, max_hp
+
+
+def test_replication_log_reproduces_the_state():
+    """A replica that starts from the same state and applies only the tick's GameStateUpdate records (the way the
+    reference's clients do, networking/... -> update.apply, logic/updates.py) ends up with the same entities, tiles,
+    depths and health as the oracle -- every tick, over bot-driven and random commands, descents, drops, pickups,
+    level-ups, vanishing levels and separation damage. Ticks that end a game re-synchronise (auto-reset re-deals it)."""
+    from optimax_rogue_b200 import _abi
+    from optimax_rogue_b200.logic import updates as U
+    n = 48
+    o = cport.R1Oracle(n, width=14, height=9, wall_density=20, seed=11, max_ticks=300, auto_reset=True)
+    o.reset()
+    s = o.state
+    rng = np.random.default_rng(2)
+    shadows = [_shadow_from_state(s, g) for g in range(n)]
+    seen = set()
+    orders = [0] * n
+    for t in range(700):
+        mv = rng.integers(1, 7, size=(n, 2), dtype=np.uint8)
+        if t % 4:
+            o.bot_moves(_abi.BOT_STAIRCASE, _abi.BOT_RANDOM if t % 8 < 4 else _abi.BOT_STAIRCASE, mv)
+        res, ev = o.step_events(mv)
+        rec = U.unpack_events(ev)
+        for g in range(n):
+            ups = U.decode_r1_events(rec[g], first_order=orders[g])
+            assert [u.order for u in ups] == list(range(orders[g], orders[g] + len(ups)))
+            orders[g] += len(ups)
+            sh, max_hp = shadows[g]
+            for u in ups:
+                seen.add(type(u).__name__)
+                if isinstance(u, U.EntityPositionUpdate):
+                    sh[u.entity_iden][:3] = [u.posx, u.posy, u.depth]
+                elif isinstance(u, U.EntityCombatUpdate):
+                    sh[u.defender_iden][3] -= u.og_damage
+                elif isinstance(u, U.EntityHealthUpdate):
+                    sh[u.entity_iden][3] += u.amount
+                elif isinstance(u, U.EntitySpawnUpdate):
+                    e = u.entity
+                    assert e.iden not in sh
+                    sh[e.iden] = [e.x, e.y, e.depth, e.item_kind if e.iden > 10 else e.health]
+                elif isinstance(u, U.EntityDeathUpdate):
+                    del sh[u.entity_iden]
+                elif isinstance(u, U.EntityModifierAddedUpdate):
+                    del sh[u.item_iden]                        # the item left the ground
+                    max_hp[u.entity_iden - 1] += u.modifier.flat_max_health
+                elif isinstance(u, U.EntityEventUpdate):
+                    if u.args['levels_gained']:
+                        sh[u.entity_iden][3] = max_hp[u.entity_iden - 1]
+            if res[g] != 1:                                     # the game ended: players' DEATH records removed them; re-deal
+                shadows[g] = _shadow_from_state(s, g)
+                continue
+            want, want_max = _shadow_from_state(s, g)
+            assert sh == want, (t, g, sh, want)
+            assert max_hp == want_max
+    assert seen == {'EntityPositionUpdate', 'EntityCombatUpdate', 'EntityHealthUpdate', 'EntitySpawnUpdate', 'EntityDeathUpdate',
+                    'EntityModifierAddedUpdate', 'EntityEventUpdate', 'DungeonCreatedUpdate'}
+
+
+def test_event_capacity_drops_but_never_corrupts():
+    """With fewer slots than records the first max_events records are the same and nothing is written past them."""
+    o1 = cport.R1Oracle(32, width=14, height=9, wall_density=20, seed=3, max_ticks=200, auto_reset=True)
+    o2 = cport.R1Oracle(32, width=14, height=9, wall_density=20, seed=3, max_ticks=200, auto_reset=True)
+    o1.reset(); o2.reset()
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        mv = rng.integers(1, 7, size=(32, 2), dtype=np.uint8)
+        r1, e1 = o1.step_events(mv)
+        r2, e2 = o2.step_events(mv, max_events=3)
+        assert np.array_equal(r1, r2) and np.array_equal(e1[:, :3], e2)
+    for name in ('ent_loc', 'ent_stat', 'ent_depth'):
+        assert np.array_equal(getattr(o1.state, name), getattr(o2.state, name))
+
+
+def test_r1_bots():
+    """RandomBot = the fused rollout's policy (same draws), StaircaseBot walks to the staircase of its level."""
+    o = cport.R1Oracle(64, seed=9, max_ticks=0, auto_reset=True)
+    o.reset()
+    ref = cport.R1Oracle(64, seed=9, max_ticks=0, auto_reset=True)
+    ref.reset()
+    for _ in range(50):
+        o.step(o.bot_moves(1, 1))
+    ref.rollout(50)
+    for name in ('ent_loc', 'ent_stat', 'ent_depth', 'tick', 'episode'):
+        assert np.array_equal(getattr(o.state, name), getattr(ref.state, name)), name
+    o2, s2 = game()
+    put(s2, 0, 2, 2); put(s2, 1, 9, 6)
+    s2.lvl_stairs[0] = 7 | (3 << 8) | (9 << 16) | (2 << 24)
+    mv = o2.bot_moves(2, 2)
+    assert mv.tolist() == [[RIGHT, UP]]
+    keep = np.full((1, 2), 77, np.uint8)
+    assert o2.bot_moves(0, 2, keep).tolist() == [[77, UP]]
