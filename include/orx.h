@@ -146,12 +146,14 @@ typedef struct OrxState {
      *   sched_words >= ORX_SCHED_HEADER_WORDS: word 0 is a tile counter, 256-game tiles are handed out
      *     dynamically (CTAs that run slower take fewer); zero again when a launch completes.
      *   sched_words >= orx_sched_words(n) and ORX_PATH_TILE_FLAGS set: words 4.. hold {tickets, completed passes} per
-     *     chunk of four tiles, and consecutive tick launches on the state are ordered chunk by chunk instead of grid
-     *     by grid: tick k+1 starts on a chunk as soon as tick k has written it, and ticks of different states in one
-     *     stream overlap freely. Measured per step with ticks enqueued back to back (rotating states): 2.5 against
-     *     4.2 us at 2^17 games, 3.8 / 5.5 at 2^18, 6.2 / 7.9 at 2^19, 11.6 / 12.2 at 2^20. The protocol costs about
-     *     2.5 us of latency per launch, so with an ordinary kernel between two ticks the same launches take 9.1 / 6.7,
-     *     12.4 / 8.4, 18.9 / 11.0 and 26.8 / 15.5 us: opt in only where ticks really follow each other.
+     *     run of tiles (a CTA's run: n_tiles / (SMs / 4) tiles, at most 32), and consecutive tick launches on the state
+     *     are ordered run by run instead of grid by grid: CTA b of tick k+1 starts as soon as CTA b of tick k has
+     *     written its run, and ticks of different states in one stream overlap freely. Measured per step with ticks
+     *     enqueued back to back (rotating states), this mode against the default: 1.8 against 4.2 us at 2^17 games,
+     *     2.9 / 5.5 at 2^18, 5.2 / 7.9 at 2^19, 9.9 / 12.2 at 2^20, 19.6 / 21.2 at 2^21. The protocol costs latency per
+     *     launch (ticket, acquire, completion of the run's stores, release), so a tick that runs alone, with an
+     *     ordinary kernel between two ticks or back to back on ONE small state is slower in this mode (9.4 against
+     *     3.6 us at 2^17 games on one state): opt in only where ticks of several states really follow each other.
      *     Stream order towards everything else is kept (a tick completes only after all earlier work has).
      *     In this mode two consecutive tick calls on DIFFERENT states must not share a result / observation /
      *     event buffer unless something else in the stream consumes it in between. */
