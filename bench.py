@@ -270,8 +270,8 @@ def run_b200(args, rank, local_rank, world):
     G_total = args.games
     G = G_total // world                     # this rank's shard (strong scaling: the total is fixed)
     # Every device-timed leg enqueues its ticks back to back (K steps in one CUDA graph): the states opt into the
-    # throughput mode (SimConfig.overlap_ticks = ORX_PATH_TILE_FLAGS), in which consecutive tick launches overlap chunk
-    # by chunk. The e2e legs synchronise after every tick; their *_sync entry points run in grid-wait mode regardless.
+    # throughput mode (SimConfig.overlap_ticks = ORX_PATH_TILE_FLAGS), in which consecutive tick launches overlap run
+    # by run (a run = the tiles of one CTA). The e2e legs synchronise after every tick; their *_sync entry points run in grid-wait mode regardless.
     cfg = sim_config(overlap_ticks=True)
     upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, MAX_TICKS, auto_reset=True)
     gen = torch.Generator(device=dev)
@@ -546,8 +546,8 @@ def run_b200(args, rank, local_rank, world):
             'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic', 'config': workload_config(args, world),
             'measurement': {'l2': f'rotating {nb} independent batches per GPU ({nb * 32 * G / 1e6:.0f} MB of planes > 126 MB L2), no flush needed',
                             'launch': f'K steps captured in one CUDA graph, replayed {replays}x back to back inside one CUDA-event pair',
-                            'ordering': 'throughput mode (SimConfig.overlap_ticks / ORX_PATH_TILE_FLAGS): consecutive tick launches are ordered chunk by chunk, '
-                                        'not grid by grid; every tick of a state still sees the previous one complete, chunk for chunk',
+                            'ordering': 'throughput mode (SimConfig.overlap_ticks / ORX_PATH_TILE_FLAGS): consecutive tick launches are ordered run by run (a run = the '
+                                        'tiles of one CTA), not grid by grid; every tick of a state still sees the previous one complete, run for run',
                             'numa': numa if numa is not None else 'process not bound (single NUMA node, one GPU, or topology not exposed)'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (tr or {}).get('dram_bytes_per_launch'), 'peak_source': peak_src,

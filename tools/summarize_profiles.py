@@ -29,7 +29,12 @@ STALLS = 'smsp__average_warps_issue_stalled_'
 
 
 def raw_rows(rep):
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    """Raw page of a report: from <rep>.raw.csv when the box exported it (gpurun brings back at most 64 MiB, the
+    reports themselves are 10-20 MB each), else from the .ncu-rep."""
+    if os.path.exists(rep + '.raw.csv'):
+        out = open(rep + '.raw.csv').read()
+    else:
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     return hdr, units, rows[2:]
