@@ -233,6 +233,22 @@ constexpr int kChunk = ORX_PIPE_CHUNK;
 constexpr int kMaxChunksPerCta = 32;          // one ticket per lane of the producer warp
 constexpr uint32_t kTicketBytes = 4u * kMaxChunksPerCta;
 
+#ifdef ORX_PIPE_JITTER
+// Schedule fuzzing (tuning build only, tests/test_gpu_tile_flags.py under ORX_LIB=liborx_jitter.so): pseudo-random pauses
+// of up to 2 us at the points where the roles of the pipeline and consecutive launches hand data to each other. A
+// missing fence or a wrong barrier phase that the natural timing happens to hide shows up as a parity failure.
+__device__ __forceinline__ void orx_jitter(unsigned int salt)
+{
+    unsigned int t;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(t));
+    const unsigned int h = (t ^ (blockIdx.x * 2654435761u) ^ (salt * 40503u) ^ (threadIdx.x >> 5)) * 2246822519u;
+    if ((h >> 29) == 0u) __nanosleep((h >> 8) & 2047u);
+}
+#define ORX_JITTER(salt) orx_jitter(salt)
+#else
+#define ORX_JITTER(salt) do { } while (0)
+#endif
+
 #ifdef ORX_PIPE_TRACE
 // Tuning aid (tools/pipetrace.py, separate build): per-CTA %globaltimer stamps of the last 16 launches.
 __device__ unsigned long long g_trace[16][512][24];     // 0-7: see tools/pipetrace.py; 8+k: producer saw tile k of this CTA done
@@ -312,6 +328,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
         // consecutive launches in launch order. The next launch starts once EVERY CTA of this one is past this
         // point, so everything ahead of it is on the launch-to-launch critical path of back-to-back ticks.
         const unsigned int c = tid - kTile;
+        ORX_JITTER(1u);
 #ifdef ORX_EXPERIMENT_TRIGGER_BEFORE_TICKET     // tuning experiment only (tickets may come out of launch order): what the ticket's round trip costs the launch chain
         if (ORX_PIPE_PDL && tid == kTile) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
@@ -360,10 +377,12 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
         };
         auto await = [&](unsigned int c, uint32_t seen) {    // seen: an earlier peek at the chunk's serving word
             const uint32_t want = lds_u32(tk0 + 4u * c);
+            ORX_JITTER(2u + c);
             while (seen != want) seen = ld_acquire_gpu(flags + 2 * (chunk0 + c) + 1);
             fence_proxy_async_global();         // the acquire (generic proxy) before the bulk loads (async proxy)
         };
         auto publish = [&](unsigned int c) {                 // this CTA's bulk stores of its chunk c have completed
+            ORX_JITTER(40u + c);
             fence_proxy_async_global();
             st_release_gpu(flags + 2 * (chunk0 + c) + 1, lds_u32(tk0 + 4u * c) + 1u);
         };
@@ -371,6 +390,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
         auto issue = [&](unsigned int it, uint32_t tile) {
             const unsigned int s = it % kStages;
             const uint32_t bar = full0 + 8 * s, base = stage0 + s * STAGE_BYTES;
+            ORX_JITTER(100u + it);
             sts_u32(tidx0 + 4 * s, tile);
             if (tile == NONE) { mbar_arrive(bar); return; }
             const size_t g = (size_t)tile * kTile;     // first game of the tile
@@ -488,6 +508,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             const uint32_t tile = lds_u32(tidx0 + 4 * s);
             if (tile == NONE) break;
             mbar_wait(done0 + 8 * s, (it / kStages) & 1u);
+            ORX_JITTER(200u + it);
 #ifdef ORX_PIPE_TRACE
             if (trace_tiles < 14) ORX_TRACE(trace_slot, 8 + trace_tiles);
             ++trace_tiles;
@@ -588,6 +609,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
     for (unsigned int it = 0;; ++it) {
         const unsigned int s = it % kStages;
         const uint32_t b4 = a4 + s * STAGE_BYTES, b8 = b4 + tid * 4u, b1 = b4 - tid * 3u, b2 = b4 - tid * 2u;
+        ORX_JITTER(300u + it);
         mbar_wait(full0 + 8 * s, (it / kStages) & 1u);
         const uint32_t tile = lds_u32(tidx0 + 4 * s);
         if (tid == 0 && it == 0) ORX_TRACE(trace_slot, 2);
@@ -676,6 +698,7 @@ k_step_pipe(const __grid_constant__ Params P, const __grid_constant__ CUtensorMa
             sts_u32x4(bo + 32u, w[8], w[9], w[10], w[11]);
         }
         if (tid == 0 && it == 0) ORX_TRACE(trace_slot, 22);          // first tile ticked (warp 0)
+        ORX_JITTER(400u + it);
         fence_proxy_async();                 // generic-proxy writes -> visible to the bulk-store engine
         __syncwarp();
         if ((tid & 31u) == 0) mbar_arrive(done0 + 8 * s);

@@ -456,6 +456,19 @@ constexpr int kThreads = ORX_R1T_THREADS;
 // equals the ticket, releases serving = ticket + 1 at gpu scope after the barrier that follows its last store, and
 // waits for the grid dependency last, so that the completion of this grid implies that of every earlier one.
 // EV: also write the tick's replication log, max_events record slots per game (orx_r1_step_events).
+#ifdef ORX_PIPE_JITTER      // schedule fuzzing (tuning build, see orx_pipe.cuh): random pauses around the block hand-over
+__device__ __forceinline__ void jitter(unsigned int salt)
+{
+    unsigned int t;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(t));
+    const unsigned int h = (t ^ (blockIdx.x * 2654435761u) ^ (salt * 40503u) ^ (threadIdx.x >> 5)) * 2246822519u;
+    if ((h >> 29) == 0u) __nanosleep((h >> 8) & 2047u);
+}
+#define ORX_R1_JITTER(salt) jitter(salt)
+#else
+#define ORX_R1_JITTER(salt) do { } while (0)
+#endif
+
 template <bool FLAGGED, bool EV = false>
 __global__ void __launch_bounds__(kThreads, FLAGGED ? ORX_R1T_MINBLOCKS : ORX_R1T_MINBLOCKS_ALONE)
 k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, uint8_t* __restrict__ result, unsigned int* __restrict__ flags,
@@ -464,6 +477,7 @@ k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, u
     __shared__ unsigned int s_ticket;
     if (FLAGGED) {
         if (threadIdx.x == 0) {
+            ORX_R1_JITTER(1u);
             unsigned int* f = flags + 2 * (size_t)blockIdx.x;
             const unsigned int ticket = atomicAdd(f, 1u);
             unsigned int serving;
@@ -475,6 +489,7 @@ k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, u
         __syncthreads();
     }
     const unsigned int game = blockIdx.x * kThreads + threadIdx.x;
+    ORX_R1_JITTER(2u);
     if (game < P.n) {
         Game G;
         load_game(P, game, G);
@@ -500,6 +515,7 @@ k_step(const __grid_constant__ R1Params P, const uint16_t* __restrict__ moves, u
             store_game(P, game, G, res);
         }
     }
+    ORX_R1_JITTER(3u);
     if (FLAGGED) {
         __syncthreads();                       // every store of the block has been issued
         if (threadIdx.x == 0) {
