@@ -17,7 +17,7 @@ often as that takes (``replays``), and the mean step time is reported.
   e2e       the public ``BatchedUpdater.host_stepper`` call with pinned HOST command/result buffers: each
             step's commands cross PCIe host->device and its results device->host inside the timed region,
             then a stream sync so the caller can read the results -- every step
-  extras    roofline.large_batch (4x the games per launch), step_observe, rollout, config2 (BASELINE.json
+  extras    roofline.large_batch (4x the games per launch), roofline.grid_wait_mode (the default ordering), step_observe, rollout, config2 (BASELINE.json
             configs[1]: 4,096 games on one fixed wall map), r1 (README-only ruleset, parity unpinned)
 L2: each leg rotates over B independent batches whose combined state exceeds the 126 MB L2.
 
@@ -496,6 +496,14 @@ def run_b200(args, rank, local_rank, world):
                                   'note': f'same kernel, same config, 4x the games per launch ({nbl} rotating batches): a launch\'s fixed cost weighs a quarter as much'}
             del big, big_moves, big_res
 
+            # ------------------------------------------------------------ the same leg in grid-wait mode (the library's default ordering)
+            gw = make_batches(G, nb, (1 << 41) + rank * nb * G, c=sim_config(overlap_ticks=False))
+            ms_gw, _, _, _ = timed_graph(lambda k: upd.update(gw[k % nb], moves[k % n_move_sets], out=results[k % nb]), K, nb)
+            out['grid_wait_mode'] = {'games_per_launch': G, 'us_per_step': ms_gw * 1e3, 'achieved': B_ALG * G / (ms_gw * 1e-3) / 1e9,
+                                     'note': 'same kernel, same batches and graph, states WITHOUT overlap_ticks: every tick launch waits for the whole previous grid '
+                                             '(what a loop with other kernels between two ticks gets; throughput mode is opt-in)'}
+            del gw
+
             # ------------------------------------------------------------ BASELINE.json configs[1]: 4,096 games, one fixed wall map
             rng = np.random.default_rng(0)
             t = np.full((60, 10), 1, np.uint8); t[[0, -1], :] = 2; t[:, [0, -1]] = 2
@@ -555,6 +563,10 @@ def run_b200(args, rank, local_rank, world):
             'e2e': out.pop('e2e'),
             'gpu_launches': value_launches,
         }
+        if 'grid_wait_mode' in out:
+            gwm = out.pop('grid_wait_mode')
+            gwm['frac'] = gwm['achieved'] / peak
+            line['roofline']['grid_wait_mode'] = gwm
         if 'large_batch' in out:
             lb = out.pop('large_batch')
             lb['frac'] = lb['achieved'] / peak
