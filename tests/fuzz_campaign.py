@@ -17,12 +17,75 @@ import torch                                               # noqa: E402
 from optimax_rogue_b200 import SimConfig, _abi             # noqa: E402
 import gpu_util as gu                                      # noqa: E402
 
+from oracle import cport                                   # noqa: E402
+from optimax_rogue_b200.r1 import R1GameState              # noqa: E402
+
+
+def r1_case(rng):
+    """One random ruleset-R1 configuration (parity unpinned: CUDA against oracle/orx_r1_oracle.c, the written spec):
+    every plane after the run, every result, and -- in the event-log variant -- every record of every tick."""
+    w, h = int(rng.integers(5, 65)), int(rng.integers(5, 21))
+    kw = dict(width=w, height=h, wall_density=int(rng.integers(0, 70)), seed=int(rng.integers(0, 2**63)),
+              max_ticks=int(rng.integers(0, 120)), auto_reset=bool(rng.integers(0, 2)))
+    flavour = int(rng.integers(0, 3))
+    flags = (0, _abi.R1_PATH_BLOCK_FLAGS, _abi.R1_PATH_HALFWARP)[flavour]
+    n = int(rng.integers(1, 500)) if rng.integers(0, 3) == 0 else int(rng.integers(500, 30000))
+    base = int(rng.integers(0, 2**53))
+    ticks = int(rng.integers(20, 100))
+    gs = R1GameState(n, game_id_base=base, path_flags=flags, **kw).reset()
+    orc = cport.R1Oracle(n, game_id_base=base, **kw)
+    orc.reset()
+    mode = int(rng.integers(0, 4)) if flavour != 2 else int(rng.integers(0, 2))
+    mrng = np.random.default_rng(int(rng.integers(0, 2**31)))
+    if mode == 3:                                               # queued commands: one replay launch against T oracle steps
+        mv = mrng.integers(0, 8, size=(ticks, n, 2), dtype=np.uint8)
+        want = np.stack([orc.step(mv[t]) for t in range(ticks)])
+        assert np.array_equal(gs.replay(torch.from_numpy(mv).cuda()).cpu().numpy(), want), 'R1 replay'
+        what = 'replay'
+    elif mode == 2:                                             # the tick with its replication log
+        ev = torch.empty((n, _abi.R1_MAX_EVENTS, 2), dtype=torch.int32, device='cuda')
+        for t in range(ticks):
+            mv = mrng.integers(0, 8, size=(n, 2), dtype=np.uint8)
+            ro, eo = orc.step_events(mv)
+            ev.fill_(0)
+            rg, _ = gs.update_events(torch.from_numpy(mv).cuda(), events=ev)
+            assert np.array_equal(rg.cpu().numpy(), ro), f'R1 tick {t}: results'
+            got = ev.cpu().numpy()
+            live = np.cumsum((got[:, :, 0] & 0xFF) == 0, axis=1) == 0
+            assert np.array_equal(live, np.cumsum((eo[:, :, 0] & 0xFF) == 0, axis=1) == 0) and np.array_equal(got[live], eo[live]), f'R1 tick {t}: records'
+        what = 'event log'
+    elif mode == 1:                                             # scripted players, a burst of unsynchronised ticks
+        b1, b2 = int(mrng.integers(1, 3)), int(mrng.integers(1, 3))
+        res = torch.empty((ticks, n), dtype=torch.uint8, device='cuda')
+        for t in range(ticks):
+            gs.update(gs.bot_moves(b1, b2), out=res[t])
+        want = np.stack([orc.step(orc.bot_moves(b1, b2)) for _ in range(ticks)])
+        assert np.array_equal(res.cpu().numpy(), want), 'R1 bots'
+        what = 'bots, burst'
+    else:
+        for t in range(ticks):
+            mv = mrng.integers(0, 8, size=(n, 2), dtype=np.uint8)
+            assert np.array_equal(gs.update(torch.from_numpy(mv).cuda()).cpu().numpy(), orc.step(mv)), f'R1 tick {t}'
+        what = 'random bytes'
+    p = gs.planes_cpu()
+    for name, _, _ in _abi.R1_PLANES:
+        assert np.array_equal(p[name], getattr(orc.state, name)), f'R1 plane {name}'
+    return ('ruleset R1 (parity unpinned)', what, ('thread per game', 'thread per game, throughput mode', 'half warp')[flavour]), n, ticks
+
+
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 20261018)
 t0 = time.time()
 runs = games = ticks_total = 0
 kinds = {}
 while time.time() - t0 < budget:
+    if rng.integers(0, 5) == 0:                                 # every fifth configuration: ruleset R1
+        key, n, n_ticks = r1_case(rng)
+        kinds[key] = kinds.get(key, 0) + 1
+        runs += 1
+        games += n
+        ticks_total += n * n_ticks
+        continue
     w, h = int(rng.integers(4, 65)), int(rng.integers(4, 21))
     kw = dict(width=w, height=h, hp=(int(rng.integers(1, 10)), int(rng.integers(1, 10))),
               damage=(int(rng.integers(0, 5)), int(rng.integers(0, 5))), armor=(int(rng.integers(0, 3)), int(rng.integers(0, 3))),
