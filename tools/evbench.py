@@ -8,11 +8,12 @@ from optimax_rogue_b200.logic.updater import BatchedUpdater, reset_games
 from optimax_rogue_b200.logic.worldgen import EmptyDungeonGenerator
 
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+OVERLAP = len(sys.argv) > 2 and sys.argv[2] == 'overlap'      # throughput mode (SimConfig.overlap_ticks)
 dev = torch.device('cuda')
 
 
 def run(n_npc, events, track=True, steps=60, reps=5):
-    cfg = SimConfig(max_ticks=1000, seed=1, auto_reset=True, n_npc=n_npc)
+    cfg = SimConfig(max_ticks=1000, seed=1, auto_reset=True, n_npc=n_npc, overlap_ticks=OVERLAP)
     upd = BatchedUpdater(EmptyDungeonGenerator(60, 10), 1, 1000, auto_reset=True)
     upd.track_order = track
     nb = 9
@@ -53,4 +54,4 @@ def run(n_npc, events, track=True, steps=60, reps=5):
 
 for n_npc, ev, track in ((0, False, False), (0, True, False), (0, True, True), (1, False, False), (2, False, False), (4, False, False), (8, False, False), (2, True, False)):
     us = run(n_npc, ev, track)
-    print(f'G={G} npc={n_npc} events={ev} track_order={track}: {us:.1f} us/step (CUDA graph), {G / us * 1e6:.3e} ticks/s', flush=True)
+    print(f'G={G} overlap={int(OVERLAP)} npc={n_npc} events={ev} track_order={track}: {us:.1f} us/step (CUDA graph), {G / us * 1e6:.3e} ticks/s', flush=True)
