@@ -26,9 +26,10 @@ class SimConfig:
     seed: int = 0
     fixed_tiles: typing.Optional[np.ndarray] = None   # uint8[W,H] Tile codes (DGEN_FIXED)
     path_flags: int = 0                 # _abi.PATH_* bits: pins a kernel path for tests / A-B runs, never changes results
-    overlap_ticks: bool = False         # throughput mode (ORX_PATH_TILE_FLAGS): ticks enqueued back to back on this state (and
-                                        # on others in the same stream) overlap chunk by chunk. For queued command streams /
-                                        # several states in flight; slower when other kernels run between two ticks
+    overlap_ticks: bool = False         # throughput mode (ORX_PATH_TILE_FLAGS): ticks enqueued back to back on this state and
+                                        # on others in the same stream overlap run by run (a run = the tiles of one CTA).
+                                        # For several states in flight; 2-3x slower when a tick has to wait for something
+                                        # (other kernels between two ticks, one small state ticked again and again)
 
     def __setattr__(self, name, value):
         # every assignment bumps a version number: holders of structs marshalled from this config (BatchedUpdater)
