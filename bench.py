@@ -541,6 +541,18 @@ def run_b200(args, rank, local_rank, world):
                          'value': world * G1 / (ms_r1 * 1e-3), 'unit': UNIT, 'games_per_gpu': G1, 'us_per_step': ms_r1 * 1e3,
                          'alg_bytes_per_game_tick': r1_bytes, 'achieved': r1_bytes * G1 / (ms_r1 * 1e-3) / 1e9}
             del r1_batches
+            # the same ruleset at the headline's size (SURVEY config 4 "run for R0 and R1"): this rank's shard of 2^20 games
+            nb4 = max(2, -(-300_000_000 // (244 * G)))
+            r1_big = [R1GameState(G, max_ticks=MAX_TICKS, auto_reset=True, seed=SEED, device=dev, overlap_ticks=True,
+                                  game_id_base=(1 << 42) + (rank * nb4 + b) * G).reset() for b in range(nb4)]
+            r1_big_moves = torch.randint(1, 7, (2, G, 2), dtype=torch.uint8, device=dev, generator=gen)
+            r1_big_res = [torch.empty((G,), dtype=torch.uint8, device=dev) for _ in range(nb4)]
+            for b in range(nb4):
+                r1_big[b].rollout(64)
+            ms_r1b, _, _, _ = timed_graph(lambda k: r1_big[k % nb4].update(r1_big_moves[k % 2], out=r1_big_res[k % nb4]), min(K, 24), nb4)
+            out['r1']['headline_size'] = {'games_per_gpu': G, 'global_games': world * G, 'value': world * G / (ms_r1b * 1e-3), 'us_per_step': ms_r1b * 1e3,
+                                          'achieved': r1_bytes * G / (ms_r1b * 1e-3) / 1e9, 'rotating_batches': nb4}
+            del r1_big, r1_big_moves, r1_big_res
 
     if rank == 0:
         time.sleep(0.15)
@@ -575,6 +587,8 @@ def run_b200(args, rank, local_rank, world):
             if key in out:
                 num = out[key].pop('hbm_frac_of', None) or out[key].get('achieved')
                 out[key]['hbm_frac'] = num / peak
+        if 'r1' in out and 'headline_size' in out['r1']:
+            out['r1']['headline_size']['hbm_frac'] = out['r1']['headline_size']['achieved'] / peak
         line.update(out)
         line['clocks'] = sampler.summary(t_wall0, t_wall1)
         if not args.no_cpu_baseline and world == 1:     # CPU baseline: rank 0 at N=1 only (other ranks would spin on host cores)
