@@ -105,6 +105,26 @@ int main()
         for (int i = 0; i < 2000; ++i) { k_ldg<<<1, 32, 0, s>>>((const uint4*)d, 1, sink); cudaStreamSynchronize(s); }
         clock_gettime(CLOCK_MONOTONIC, &t1);
         printf("launch(empty kernel) + cudaStreamSynchronize: %.2f us per iteration (host clock)\n", ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 2000 / 1e3);
+        // other ways to wait for the same kernel: spinning on cudaStreamQuery, on an event, and on a word the kernel writes
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (int i = 0; i < 2000; ++i) { k_ldg<<<1, 32, 0, s>>>((const uint4*)d, 1, sink); while (cudaStreamQuery(s) == cudaErrorNotReady) { } }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        printf("launch(empty kernel) + spin on cudaStreamQuery: %.2f us per iteration\n", ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 2000 / 1e3);
+        cudaEvent_t ev;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (int i = 0; i < 2000; ++i) { k_ldg<<<1, 32, 0, s>>>((const uint4*)d, 1, sink); cudaEventRecord(ev, s); while (cudaEventQuery(ev) == cudaErrorNotReady) { } }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        printf("launch(empty kernel) + event record + spin on cudaEventQuery: %.2f us per iteration\n", ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 2000 / 1e3);
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (int i = 0; i < 2000; ++i) { cudaStreamSynchronize(s); }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        printf("cudaStreamSynchronize on an idle stream: %.2f us per call\n", ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 2000 / 1e3);
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (int i = 0; i < 2000; ++i) { k_ldg<<<1, 32, 0, s>>>((const uint4*)d, 1, sink); }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        cudaStreamSynchronize(s);
+        printf("launch(empty kernel) alone, host time per call: %.2f us\n", ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 2000 / 1e3);
     }
     return 0;
 }
