@@ -57,7 +57,7 @@ def test_back_to_back_ticks_on_one_state(n, tpc):
         assert used == 2 * -(-(n // _abi.TILE) // tpc)
 
 
-@pytest.mark.parametrize('n,ticks', [(1 << 18, 600), (1 << 20, 160), (1 << 21, 80)])
+@pytest.mark.parametrize('n,ticks', [(1 << 18, 600), (1 << 20, 160), (1 << 21, 80), (1 << 22, 40)])     # up to the largest batch ticked in this mode (16,384 tiles)
 def test_long_unsynchronised_runs(n, ticks):
     """Hundreds of ticks in flight behind each other (a CUDA graph replayed without a pause), the state planes of
     the bigger batch far larger than what is in flight: the end state equals the oracle's after the same commands."""
