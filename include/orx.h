@@ -288,6 +288,10 @@ int orx_replay(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, u
 #define ORX_OBS_LEN 12
 int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stairs_radius,
                 int64_t n, void* cuda_stream);
+/* The rest of GameState.view_for (state.py:53-58) for states with NPC slots: the entities besides the players that
+ * stand on the viewer's depth. npc_obs: device int16[n][2][n_npc][4] = per player, per slot { on_my_depth, x, y, health }
+ * ({0, -1, -1, 0} for an empty slot or one on another depth), 8-byte aligned. n_npc == 0: nothing to do. */
+int orx_observe_npc(const OrxConfig* cfg, const OrxState* st, int16_t* npc_obs, int64_t n, void* cuda_stream);
 
 /* orx_step with scripted players (optimax_rogue_bots/randombot.py:20-21, staircasebot.py:9-20): a player whose
  * bot kind is ORX_BOT_RANDOM / ORX_BOT_STAIRCASE gets the command orx_bot_moves would compute for this tick, inside

@@ -151,6 +151,7 @@ PROTOTYPES = {
                                    C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_observe': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_int,
                               C.c_int64, C.c_void_p]),
+    'orx_observe_npc': (C.c_int, [C.POINTER(OrxConfig), C.POINTER(OrxState), C.c_void_p, C.c_int64, C.c_void_p]),
     'orx_r1_reset': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_void_p, C.c_int,
                                C.c_int64, C.c_uint64, C.c_void_p]),
     'orx_r1_step': (C.c_int, [C.POINTER(OrxR1Config), C.POINTER(OrxR1State), C.c_void_p, C.c_void_p,

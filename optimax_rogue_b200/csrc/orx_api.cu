@@ -299,6 +299,27 @@ k_observe(const __grid_constant__ Params P, int16_t* __restrict__ obs, int radiu
     o[2] = make_uint4(w[8], w[9], w[10], w[11]);
 }
 
+// orx_observe_npc: what view_for (state.py:53-58) keeps of the entities besides the players -- the NPC slots on the
+// viewer's depth. One thread per game, 8 bytes per (player, slot).
+__global__ void __launch_bounds__(kThreads)
+k_observe_npc(const __grid_constant__ Params P, uint2* __restrict__ out)
+{
+    const unsigned int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P.n) return;
+    const int2 d = P.depth[i];
+    const int e = P.n_npc;
+    for (int k = 0; k < e; ++k) {
+        const size_t at = (size_t)i * e + k;
+        const int nd = P.npc_depth[at], hp = P.npc_hp[at];
+        const int x = P.npc_pos[2 * at], y = P.npc_pos[2 * at + 1];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const bool here = nd >= 0 && nd == (p == 0 ? d.x : d.y);
+            out[((size_t)i * 2 + p) * e + k] = make_uint2(pack_i16x2(here, here ? x : -1), pack_i16x2(here ? y : -1, here ? hp : 0));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ Updater.current_update_order (updater.py:71-74)
 __global__ void __launch_bounds__(kThreads)
 k_event_count_add(const uint2* __restrict__ events, int max_ev, unsigned long long* __restrict__ order, unsigned int n)
@@ -1024,6 +1045,16 @@ int orx_replay(const OrxConfig* cfg, const OrxState* st, const uint8_t* moves, u
         k_replay<DGEN, NPC><<<grid, kThreads, smem, s>>>(P, mv, results, n_ticks);
         return launch_done();
     });
+}
+
+int orx_observe_npc(const OrxConfig* cfg, const OrxState* st, int16_t* npc_obs, int64_t n, void* cuda_stream)
+{
+    const int rc = check_common(cfg, st, n);
+    if (rc != ORX_OK) return rc;
+    if (cfg->n_npc == 0 || n == 0) return ORX_OK;
+    if (npc_obs == nullptr || !aligned(npc_obs, 8)) return ORX_ERR_BAD_ARG;
+    k_observe_npc<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(make_params(cfg, st, n, 0), reinterpret_cast<uint2*>(npc_obs));
+    return launch_done();
 }
 
 int orx_observe(const OrxConfig* cfg, const OrxState* st, int16_t* obs, int stairs_radius,

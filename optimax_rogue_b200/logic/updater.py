@@ -403,6 +403,24 @@ class BatchedUpdater:
         _lib.check(rc, 'orx_observe')
         return obs
 
+    def observe_npc(self, game_state: BatchedGameState, out: typing.Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The entities besides the players that each player sees (GameState.view_for, state.py:53-58, keeps the
+        viewer's depth): int16[N,2,n_npc,4] = on_my_depth, x, y, health per NPC slot (0, -1, -1, 0 when the slot is empty
+        or on another depth). ``orx_observe_npc``; a state without NPC slots returns an empty tensor."""
+        gs = game_state
+        _require_cuda(gs)
+        e = gs.cfg.n_npc
+        obs = out if out is not None else torch.empty((gs.n, 2, e, 4), dtype=torch.int16, device=gs.device)
+        if e == 0:
+            return obs
+        if tuple(obs.shape) != (gs.n, 2, e, 4) or obs.dtype != torch.int16 or not obs.is_cuda or not obs.is_contiguous():
+            raise ValueError(f'out must be a contiguous CUDA int16 tensor of shape ({gs.n}, 2, {e}, 4)')
+        cfg, st = self._cfg(gs)
+        with _on_device(gs.device):
+            rc = _lib.lib().orx_observe_npc(C.byref(cfg), C.byref(st), obs.data_ptr(), gs.n, _stream_ptr(gs.device))
+        _lib.check(rc, 'orx_observe_npc')
+        return obs
+
     def update_observe(self, game_state: BatchedGameState, moves: torch.Tensor, *, packed: bool = False,
                        stairs_radius: int = -1, out: typing.Optional[torch.Tensor] = None,
                        obs_out: typing.Optional[torch.Tensor] = None):

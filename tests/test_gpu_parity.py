@@ -386,6 +386,37 @@ def expected_obs(p, radius):
     return obs.astype(np.int16)
 
 
+@pytest.mark.parametrize('n_npc', [1, 3, 8])
+def test_observe_npc_slots_on_the_viewers_depth(n_npc):
+    """orx_observe_npc: view_for (state.py:53-58) keeps the entities on the viewer's depth -- per player and NPC slot
+    { on_my_depth, x, y, health }, against a numpy restatement, while StaircaseBot takes player 1 down the levels and
+    hits wear the NPCs down (dead ones leave their slot, updater.py:137-145)."""
+    n = 3000
+    cfg = SimConfig(max_ticks=0, seed=12, n_npc=n_npc, width=14, height=6, hp=(200, 200))
+    gs, upd, orc = gu.make_pair(cfg, n)
+    rng = np.random.default_rng(n_npc)
+    live = rng.random((n, n_npc)) < 0.7
+    gs.npc_depth.copy_(torch.from_numpy(np.where(live, rng.integers(0, 3, size=(n, n_npc)), -1).astype(np.int32)))
+    gs.npc_pos.copy_(torch.from_numpy(np.stack([rng.integers(1, 13, size=(n, n_npc)), rng.integers(1, 5, size=(n, n_npc))], axis=-1).astype(np.uint8)))
+    gs.npc_hp.copy_(torch.from_numpy(rng.integers(1, 5, size=(n, n_npc)).astype(np.int16)))
+    seen = 0
+    for t in range(30):
+        p = gs.planes_cpu()
+        want = np.zeros((n, 2, n_npc, 4), np.int16)
+        for pl in range(2):
+            here = (p['npc_depth'] >= 0) & (p['npc_depth'] == p['depth'][:, pl:pl + 1])
+            want[:, pl, :, 0] = here
+            want[:, pl, :, 1] = np.where(here, p['npc_pos'][:, :, 0].astype(int), -1)
+            want[:, pl, :, 2] = np.where(here, p['npc_pos'][:, :, 1].astype(int), -1)
+            want[:, pl, :, 3] = np.where(here, p['npc_hp'], 0)
+        got = upd.observe_npc(gs).cpu().numpy()
+        assert np.array_equal(got, want), t
+        seen += int(want[:, :, :, 0].sum())
+        upd.update(gs, upd.bot_moves(gs, 2, 1))
+    assert seen > 0 and (gs.planes_cpu()['npc_depth'] < 0).sum() > (~live).sum()        # visible NPCs existed, and some died on the way
+    assert upd.observe_npc(gu.make_pair(SimConfig(seed=1), 64)[0]).shape == (64, 2, 0, 4)
+
+
 @pytest.mark.parametrize('n', [100, 2000, 70000])
 def test_observe_all_columns_and_paths(n):
     """n = 100: simple kernel; 2000: TMA pipeline + ragged tail; 70000: pipeline with claimed tiles."""
