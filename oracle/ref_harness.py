@@ -287,6 +287,14 @@ def snapshot(gs, result, events):
         'npcs': [(e.iden, e.depth, e.x, e.y, e.health) for e in gs.entities
                  if e.iden not in (gs.player_1_iden, gs.player_2_iden)],
     }
+    # what each player is shown: GameState.view_for (game/state.py:53-58) -- the entities on the viewer's depth, that
+    # level alone, the tick. Not part of the digests; pins the observation records (orx_observe, orx_observe_npc).
+    views = []
+    for viewer in (p1, p2):
+        v = gs.view_for(viewer)
+        views.append({'tick': v.tick, 'levels': sorted(v.world.dungeons.keys()), 'stairs': _stairs_of(v, viewer.depth),
+                      'ents': sorted((e.iden, e.depth, e.x, e.y, e.health) for e in v.entities)})
+    rec['views'] = views
     return rec
 
 

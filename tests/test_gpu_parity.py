@@ -367,23 +367,7 @@ def test_dynamic_tile_scheduler_equals_static_assignment(n):
     gu.assert_state_equal(gs, orc, 'dynamic tiles')
 
 
-def expected_obs(p, radius):
-    """numpy restatement of the observation record (GameState.view_for + stairs visibility radius)."""
-    n = p['pos'].shape[0]
-    obs = np.zeros((n, 2, 12), dtype=np.int64)
-    same = p['depth'][:, 0] == p['depth'][:, 1]
-    for pl in range(2):
-        o = 1 - pl
-        x, y = p['pos'][:, 2 * pl].astype(int), p['pos'][:, 2 * pl + 1].astype(int)
-        sx, sy = p['stairs'][:, 2 * pl].astype(int), p['stairs'][:, 2 * pl + 1].astype(int)
-        vis = (sx != 255) & ((radius < 0) | (np.maximum(np.abs(sx - x), np.abs(sy - y)) <= radius))
-        cols = [x, y, np.minimum(p['depth'][:, pl], 32767), p['hp'][:, pl], same,
-                np.where(same, p['pos'][:, 2 * o].astype(int), -1), np.where(same, p['pos'][:, 2 * o + 1].astype(int), -1),
-                np.where(same, p['hp'][:, o], 0), vis, np.where(vis, sx, -1), np.where(vis, sy, -1),
-                np.minimum(p['tick'], 32767)]
-        for c, v in enumerate(cols):
-            obs[:, pl, c] = v
-    return obs.astype(np.int16)
+from obs_util import expected_obs, expected_npc_obs      # numpy restatements, pinned to the live view_for in test_observation_vs_reference.py
 
 
 @pytest.mark.parametrize('n_npc', [1, 3, 8])
@@ -402,13 +386,7 @@ def test_observe_npc_slots_on_the_viewers_depth(n_npc):
     seen = 0
     for t in range(30):
         p = gs.planes_cpu()
-        want = np.zeros((n, 2, n_npc, 4), np.int16)
-        for pl in range(2):
-            here = (p['npc_depth'] >= 0) & (p['npc_depth'] == p['depth'][:, pl:pl + 1])
-            want[:, pl, :, 0] = here
-            want[:, pl, :, 1] = np.where(here, p['npc_pos'][:, :, 0].astype(int), -1)
-            want[:, pl, :, 2] = np.where(here, p['npc_pos'][:, :, 1].astype(int), -1)
-            want[:, pl, :, 3] = np.where(here, p['npc_hp'], 0)
+        want = expected_npc_obs(p)
         got = upd.observe_npc(gs).cpu().numpy()
         assert np.array_equal(got, want), t
         seen += int(want[:, :, :, 0].sum())
