@@ -235,3 +235,16 @@ def test_r1_host_buffers():
     assert_equal(gs, orc, 'end')
     with pytest.raises(ValueError):
         gs.update_host(torch.empty((n, 2), dtype=torch.uint8), hr)       # not pinned
+
+
+def test_r1_cuda_reproduces_the_committed_trajectory_digests(r1_kernel_flavour):
+    """The same fixture from the CUDA kernels: whole trajectories (every result, the planes every 20 ticks) hash to the
+    digests the oracle committed (tests/golden/r1_oracle_digests.json; a regression fixture of the written spec, not a
+    reference-derived vector)."""
+    import json
+    from oracle import gen_golden_r1 as gg
+    want = json.load(open(gg.PATH))
+    for k, case in enumerate(gg.CASES):
+        gs = R1GameState(case['n'], game_id_base=case['base'], path_flags=FLAVOUR['flags'], **case['cfg']).reset()
+        got = gg.run_case(k, lambda mv: gs.update(torch.from_numpy(mv).cuda()).cpu().numpy(), gs.planes_cpu)
+        assert got == want[case['name']], case['name']

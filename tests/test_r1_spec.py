@@ -307,3 +307,11 @@ def test_r1_bots():
     assert mv.tolist() == [[RIGHT, UP]]
     keep = np.full((1, 2), 77, np.uint8)
     assert o2.bot_moves(0, 2, keep).tolist() == [[77, UP]]
+
+
+def test_oracle_reproduces_its_committed_trajectory_digests():
+    """Regression fixture (tests/golden/r1_oracle_digests.json, oracle/gen_golden_r1.py): an edit of the R1 oracle or of the
+    spec it restates must not pass unnoticed. Not a reference-derived vector -- R1 has no reference code (parity unpinned)."""
+    import json
+    from oracle import gen_golden_r1 as gg
+    assert gg.oracle_digests() == json.load(open(gg.PATH))
